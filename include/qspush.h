@@ -1,0 +1,174 @@
+/* include/qspush.h — C-ABI of the B200-native batched pusher-slider NMPC engine.
+ *
+ * This is the drop-in boundary for the acados v0.2.1 solver object that
+ * /root/reference/acados_nmpc/NMPC_controller.m drives through acados' MATLAB class `acados_ocp`
+ * (NMPC_controller.m:304 create, :334-348 set, :382-384 init, :389 solve, :392-394,:403 get,
+ * :420 get_cost; helper.m:253,264-269 status/statistics), plus the numeric entry points of
+ * bspline_shape / PusherSliderModel that the controller and the closed loop call
+ * (bspline_shape.m:146-152,192-199; PusherSliderModel.m:606-608).
+ *
+ * Conventions
+ *   - plain C, opaque handles, caller-owned buffers, FP64 everywhere;
+ *   - every function returns 0 on success, a negative qspush_err on argument / runtime errors;
+ *     qspush_solve never fails because a problem did not converge — poll QSPUSH_STATUS per problem
+ *     (acados v0.2.1 enum: 0 success, 1 NaN/failure, 2 max iter, 3 min step, 4 QP failure);
+ *   - a solver is bound to one CUDA device and owns one stream; calls on one handle must be
+ *     serialised by the caller (same contract as one acados_ocp object);
+ *   - batched per-problem arrays use the MATLAB-natural layout  [batch][stage][dim]  (i.e. the
+ *     column-major dim x stages x batch array); with stage >= 0 the layout is [batch][dim];
+ *   - `mem` says where the caller's buffer lives (host or device of the solver's GPU);
+ *   - there is NO CPU fallback: every compute entry point needs a CUDA device.
+ */
+#ifndef QSPUSH_H
+#define QSPUSH_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qspush_model qspush_model;
+typedef struct qspush_solver qspush_solver;
+
+typedef enum {
+    QSPUSH_OK = 0,
+    QSPUSH_ERR_ARG = -1,      /* bad pointer / size / field / range               */
+    QSPUSH_ERR_CUDA = -2,     /* CUDA runtime error (see qspush_last_error)       */
+    QSPUSH_ERR_IO = -3,       /* .ply could not be read / parsed                  */
+    QSPUSH_ERR_NO_DEVICE = -4 /* no CUDA device: the engine has no CPU path       */
+} qspush_err;
+
+typedef enum { QSPUSH_MEM_HOST = 0, QSPUSH_MEM_DEVICE = 1 } qspush_mem;
+
+/* solver modes: acados nlp_solver "sqp_rti" / "sqp" (NMPC_controller.m:272) */
+typedef enum { QSPUSH_MODE_RTI = 0, QSPUSH_MODE_SQP = 1 } qspush_mode;
+
+/* Options; zero-initialise then call qspush_opts_default. Mirrors create_ocp_opts
+ * (NMPC_controller.m:270-300) plus the acados defaults the reference does not override. */
+typedef struct {
+    int    mode;                    /* qspush_mode                                            */
+    int    max_sqp_iter;            /* nlp_solver_max_iter = 30                               */
+    double tol_stat, tol_eq, tol_ineq, tol_comp;   /* nlp_solver_tol_* = 1e-6                 */
+    int    qp_max_iter;             /* qp_solver_iter_max = 50                                */
+    double qp_tol;                  /* IPM residual / complementarity tolerance               */
+    double qp_mu0;                  /* IPM initial barrier parameter                          */
+    double qp_thr;                  /* IPM lower clamp on the initial slacks                  */
+    double qp_tau;                  /* IPM fraction to the boundary                           */
+    int    globalization;           /* 1 = merit backtracking, 0 = fixed full step            */
+    double alpha_min, alpha_reduction, eps_sufficient_descent;   /* 0.05, 0.7, 1e-4           */
+    int    matlab_single_quirk;     /* reproduce MATLAB `single` rounding of mod(s,b) in prepare */
+    int    problems_per_warp;       /* QP kernel packing: 32, 16 or 8 (0 = auto)              */
+} qspush_opts;
+
+/* controller-side constants of NMPC_controller (NMPC_controller.m:23-26, 98-100) */
+typedef struct {
+    double v_alpha, d_v_bound, t_angle0, u_t_ub, u_n_lb;
+} qspush_ctrl;
+
+typedef enum {
+    /* per problem, double */
+    QSPUSH_X0 = 0,        /* constr_x0, 4                          NMPC_controller.m:170,334 */
+    QSPUSH_YREF = 1,      /* cost_y_ref, 6 per stage 0..N-1         :345                      */
+    QSPUSH_YREF_E = 2,    /* cost_y_ref_e, 4                        :348                      */
+    QSPUSH_X = 3,         /* init_x / get('x'), 4 per stage 0..N    :382,:393                 */
+    QSPUSH_U = 4,         /* init_u / get('u'), 2 per stage 0..N-1  :383,:392,:403            */
+    QSPUSH_PI = 5,        /* init_pi / get('pi'), 4 per stage 0..N-1  :384,:394               */
+    QSPUSH_LAM = 6,       /* inequality multipliers, 6 per stage 0..N-1: [lower(s,un,ut); upper] */
+    QSPUSH_COST = 7,      /* get_cost, 1                            :420                      */
+    QSPUSH_RES = 8,       /* residuals [stat, eq, ineq, comp], 4                              */
+    /* shared by the whole batch, double (batch_lo/batch_hi ignored) */
+    QSPUSH_W = 16,        /* cost_W: stage k<N 6x6 col-major in y=[x;u] order; k==N 4x4  :154,157 */
+    QSPUSH_LH = 17,       /* constr_lh, 3                           :137,:251                 */
+    QSPUSH_UH = 18,       /* constr_uh, 3                           :138,:252                 */
+    /* per problem, int (qspush_get_int / qspush_set_int) */
+    QSPUSH_STATUS = 32,   /* helper.m:253                                                     */
+    QSPUSH_SQP_ITER = 33, /* helper.m:264                                                     */
+    QSPUSH_QP_ITER = 34,  /* total IPM iterations of the last solve                           */
+    QSPUSH_OBJECT_ID = 35,/* index into the model list given at creation                      */
+    QSPUSH_COLD = 36      /* 1 = no previous solution (isempty(utraj), NMPC_controller.m:351) */
+} qspush_field;
+
+/* scalar statistics of the last qspush_solve (helper.m:264-269), seconds, CUDA-event timed */
+typedef enum { QSPUSH_TIME_TOT = 0, QSPUSH_TIME_LIN = 1, QSPUSH_TIME_QP = 2, QSPUSH_TIME_PREP = 3 } qspush_stat;
+
+const char* qspush_last_error(void);
+const char* qspush_version(void);
+int qspush_device_count(void);
+
+/* ---------------- model: PusherSliderModel + bspline_shape ---------------- */
+
+/* From tables: knots S (n+p+1), control points (n x 2 row-major), degree p, slider/pusher
+ * friction and limit-surface constant (bspline_shape.m:25-38; PusherSliderModel.m:53-55).
+ * single_coeffs != 0 reproduces the MATLAB `single` arithmetic of the derivative-coefficient
+ * tables when S and P come from pcread. */
+int qspush_model_create(const double* knots, int nknots, const double* ctrl_xy, int n, int degree,
+                        double mu_sp, double c_ellipse, int single_coeffs, qspush_model** out);
+
+/* From an objects_database entry and its .ply outline (PusherSliderModel.m:45-60, 84-132):
+ * binary_little_endian float32 vertices -> sortCadPoints (flip_order for montana/pulirapid,
+ * :107-109) -> getSpline. */
+int qspush_model_create_from_ply(const char* ply_path, int flip_order, int degree, double mu_sg,
+                                 double mu_sp, double mass, double tau_max, qspush_model** out);
+
+void qspush_model_free(qspush_model* m);
+
+/* sizes and constants: n control points, nknots, total length b, c_ellipse, mu_sp */
+int qspush_model_info(const qspush_model* m, int* n, int* nknots, double* b, double* c_ellipse, double* mu_sp);
+/* copy out knots (nknots), control points (n x 2), cj_1 (n x 2), cj_2 (n x 2); any may be NULL */
+int qspush_model_tables(const qspush_model* m, double* knots, double* ctrl_xy, double* c1, double* c2);
+
+/* ---------------- stateless batched evaluation (config 2 entry points) ----------------
+ * cnt samples; all pointers are in `mem`; outputs may be NULL to skip.  Arrays are [cnt][dim].
+ * wrap: 0 none, 1 MATLAB mod(s,b) (evalSpline, bspline_shape.m:193), 2 fmod(s,b)+(s<0)b (PusherSliderModel.m:526) */
+int qspush_eval_spline(const qspush_model* m, int device, qspush_mem mem, int cnt, const double* s, int wrap,
+                       double* C, double* Cd, double* Cdd, double* tvers, double* nvers, double* kappa);
+/* xdot = f(x,u) (evalModelVariableShape, PusherSliderModel.m:606); Jx [cnt][16], Ju [cnt][8] row-major, optional */
+int qspush_eval_dynamics(const qspush_model* m, int device, qspush_mem mem, int cnt, const double* x, const double* u,
+                         double* f, double* Jx, double* Ju);
+/* one ERK4 step with forward sensitivities (acados sim_erk): Phi [cnt][4], A [cnt][16], B [cnt][8] row-major */
+int qspush_eval_erk4_sens(const qspush_model* m, int device, qspush_mem mem, int cnt, const double* x, const double* u,
+                          double dt, double* Phi, double* A, double* B);
+/* v_bound and |kappa| of update_tangential_velocity_bounds (NMPC_controller.m:319-327); outputs [cnt] */
+int qspush_eval_v_bound(const qspush_model* m, int device, qspush_mem mem, int cnt, const double* s,
+                        const qspush_ctrl* ctrl, int single_quirk, double* v_bound, double* t_angle);
+
+/* ---------------- batched OCP solver: the acados_ocp replacement ---------------- */
+
+void qspush_opts_default(qspush_opts* o);
+void qspush_ctrl_default(qspush_ctrl* c);
+
+/* models[nmodels]: the objects a batch may mix (QSPUSH_OBJECT_ID selects per problem, default 0).
+ * N = horizon Hp, dt = sample time, batch = number of independent NMPC instances. */
+int qspush_solver_create(const qspush_model* const* models, int nmodels, int N, double dt, int batch,
+                         int device, const qspush_opts* opts, qspush_solver** out);
+void qspush_solver_free(qspush_solver* s);
+
+int qspush_solver_set_opts(qspush_solver* s, const qspush_opts* opts);
+int qspush_solver_set_ctrl(qspush_solver* s, const qspush_ctrl* ctrl);
+
+/* stage = -1 addresses all stages of the field at once ([batch][stage][dim]); problems [batch_lo, batch_hi). */
+int qspush_set(qspush_solver* s, qspush_field f, int stage, int batch_lo, int batch_hi, const double* data, qspush_mem mem);
+int qspush_get(qspush_solver* s, qspush_field f, int stage, int batch_lo, int batch_hi, double* out, qspush_mem mem);
+int qspush_set_int(qspush_solver* s, qspush_field f, int batch_lo, int batch_hi, const int* data, qspush_mem mem);
+int qspush_get_int(qspush_solver* s, qspush_field f, int batch_lo, int batch_hi, int* out, qspush_mem mem);
+
+/* NMPC_controller.solve pre-processing on the device (NMPC_controller.m:332, 351-380): x0 wrap,
+ * cold start, v_bound clipping of the warm start, Euler rollout. Uses QSPUSH_X0, QSPUSH_COLD. */
+int qspush_prepare(qspush_solver* s);
+/* ocp_solver.solve() (NMPC_controller.m:389): asynchronous on the solver's stream. */
+int qspush_solve(qspush_solver* s);
+/* post-processing shift (NMPC_controller.m:397-399): drop stage 0, duplicate the last column. */
+int qspush_shift(qspush_solver* s);
+/* one forward-Euler plant step x <- x + dt*f(x,u) on caller arrays [batch][4], [batch][2] (helper.m:294,307) */
+int qspush_plant_step(qspush_solver* s, double* x, const double* u, qspush_mem mem);
+/* wait for everything queued on the solver's stream */
+int qspush_sync(qspush_solver* s);
+/* the solver's cudaStream_t (as void*) so callers can order their own work / events on it */
+void* qspush_stream(qspush_solver* s);
+int qspush_get_stat(qspush_solver* s, qspush_stat which, double* out);
+/* number of kernels launched by this solver since creation (bench bookkeeping) */
+long long qspush_launch_count(const qspush_solver* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QSPUSH_H */

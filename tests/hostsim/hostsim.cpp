@@ -1,0 +1,191 @@
+// tests/hostsim/hostsim.cpp — TEST-ONLY host simulation of the CUDA kernels.
+//
+// Compiles the __host__ __device__ kernel bodies (qs_device.cuh, qs_qp.cuh, qs_solver.cuh) with
+// g++ and runs them thread-by-thread on the CPU over the same structure-of-arrays slabs, so the
+// kernel logic can be checked against the oracle in a container without a GPU
+// (`pytest -m "not gpu"`).  It is never part of the product: libqspush.so does not contain it and
+// the package never loads it.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../uclv_qs_pushing_matlab_b200/csrc/qs_model.hpp"
+#include "../../uclv_qs_pushing_matlab_b200/csrc/qs_solver.cuh"
+
+using namespace qs;
+
+static std::string g_err;
+
+extern "C" {
+
+const char* hs_last_error() { return g_err.c_str(); }
+
+void* hs_model_create(const double* S, int nknots, const double* P, int n, int p, double mu_sp, double c_ellipse, int single) {
+    HostModel* m = new HostModel();
+    g_err = model_from_tables(S, nknots, P, n, p, mu_sp, c_ellipse, single != 0, *m);
+    if (!g_err.empty()) { delete m; return nullptr; }
+    return m;
+}
+void* hs_model_from_ply(const char* path, int flip, int p, double mu_sg, double mu_sp, double mass, double tau_max) {
+    HostModel* m = new HostModel();
+    g_err = model_from_ply(path, flip != 0, p, mu_sg, mu_sp, mass, tau_max, *m);
+    if (!g_err.empty()) { delete m; return nullptr; }
+    return m;
+}
+void hs_model_free(void* m) { delete (HostModel*)m; }
+void hs_model_info(void* m_, int* n, int* nknots, double* b, double* c_ellipse, double* mu_sp) {
+    HostModel* m = (HostModel*)m_;
+    *n = m->n; *nknots = (int)m->S.size(); *b = m->b; *c_ellipse = m->c_ellipse; *mu_sp = m->mu_sp;
+}
+void hs_model_tables(void* m_, double* S, double* P, double* c1, double* c2, double* blob) {
+    HostModel* m = (HostModel*)m_;
+    if (S) std::memcpy(S, m->S.data(), m->S.size() * 8);
+    if (P) std::memcpy(P, m->P.data(), m->P.size() * 8);
+    if (c1) std::memcpy(c1, m->c1.data(), m->c1.size() * 8);
+    if (c2) std::memcpy(c2, m->c2.data(), m->c2.size() * 8);
+    if (blob) std::memcpy(blob, m->blob.data(), MODEL_DOUBLES * 8);
+}
+int hs_model_doubles() { return MODEL_DOUBLES; }
+
+// mirrors k_eval_spline
+void hs_eval_spline(void* m_, int cnt, const double* s, int wrap, double* C, double* Cd, double* Cdd, double* tv, double* nv, double* kappa) {
+    HostModel* hm = (HostModel*)m_; const double* M = hm->blob.data();
+    for (int i = 0; i < cnt; ++i) {
+        double sg = s[i];
+        if (wrap == 1) sg = matlab_mod(sg, M[1], hm->single_coeffs);
+        else if (wrap == 2) sg = wrap_dyn(sg, M[1]);
+        Curve c; curve_eval(M, sg, c);
+        if (C) { C[2 * i] = c.cx; C[2 * i + 1] = c.cy; }
+        if (Cd) { Cd[2 * i] = c.dx; Cd[2 * i + 1] = c.dy; }
+        if (Cdd) { curve_dd(M, sg, Cdd[2 * i], Cdd[2 * i + 1]); }
+        if (tv || nv) {
+            const double nrm = sqrt(c.dx * c.dx + c.dy * c.dy);
+            const double tx = c.dx / nrm, ty = c.dy / nrm;
+            if (tv) { tv[2 * i] = tx; tv[2 * i + 1] = ty; }
+            if (nv) { nv[2 * i] = ty; nv[2 * i + 1] = -tx; }
+        }
+        if (kappa) kappa[i] = (c.dx * c.hy - c.dy * c.hx) / (c.dx * c.dx + c.dy * c.dy);
+    }
+}
+// mirrors k_eval_dynamics
+void hs_eval_dynamics(void* m_, int cnt, const double* x, const double* u, double* f, double* Jx, double* Ju) {
+    const double* M = ((HostModel*)m_)->blob.data();
+    for (int i = 0; i < cnt; ++i) {
+        Dyn d;
+        dyn_eval<true>(M, x[4 * i + 2], x[4 * i + 3], u[2 * i], u[2 * i + 1], d);
+        for (int r = 0; r < 4; ++r) f[4 * i + r] = d.f[r];
+        if (Jx) {
+            const double jt[4] = {-d.f[1], d.f[0], 0.0, 0.0};
+            for (int r = 0; r < 4; ++r) { Jx[16 * i + 4 * r] = 0; Jx[16 * i + 4 * r + 1] = 0; Jx[16 * i + 4 * r + 2] = jt[r]; Jx[16 * i + 4 * r + 3] = d.fs[r]; }
+        }
+        if (Ju) for (int r = 0; r < 4; ++r) { Ju[8 * i + 2 * r] = d.fun[r]; Ju[8 * i + 2 * r + 1] = d.fut[r]; }
+    }
+}
+// mirrors k_eval_erk4
+void hs_eval_erk4(void* m_, int cnt, const double* x, const double* u, double dt, double* Phi, double* A, double* B) {
+    const double* M = ((HostModel*)m_)->blob.data();
+    for (int i = 0; i < cnt; ++i) {
+        double Sm[16];
+        erk4_sens(M, x + 4 * i, u[2 * i], u[2 * i + 1], dt, Phi + 4 * i, Sm);
+        for (int r = 0; r < 4; ++r) {
+            A[16 * i + 4 * r] = r == 0; A[16 * i + 4 * r + 1] = r == 1;
+            A[16 * i + 4 * r + 2] = Sm[4 * r]; A[16 * i + 4 * r + 3] = Sm[4 * r + 1];
+            B[8 * i + 2 * r] = Sm[4 * r + 2]; B[8 * i + 2 * r + 1] = Sm[4 * r + 3];
+        }
+    }
+}
+void hs_eval_vbound(void* m_, int cnt, const double* s, const double* ctrl5, int single, double* vb, double* ta) {
+    const double* M = ((HostModel*)m_)->blob.data();
+    for (int i = 0; i < cnt; ++i) vb[i] = v_bound_of(M, s[i], ctrl5[0], ctrl5[1], ctrl5[2], ctrl5[3], single != 0, ta ? ta + i : nullptr);
+}
+
+// Whole solver pipeline in kernel order on host slabs.
+//   opts_d: [qp_tol, qp_mu0, qp_thr, qp_tau, tol_stat, tol_eq, tol_ineq, tol_comp, alpha_min, alpha_red, eps_sd]
+//   opts_i: [mode(0 rti,1 sqp,2 qp-only), qp_max_iter, max_sqp_iter, globalization, single_quirk, do_prepare, do_shift]
+//   ctrl5 : [v_alpha, d_v_bound, t_angle0, u_t_ub, u_n_lb]
+// AoS in/out: x0 [nb][4] (in/out: wrapped by prepare), yref [nb][N][6], yref_e [nb][4], x [nb][N+1][4], u [nb][N][2],
+//             pi [nb][N][4], lam [nb][N][6], cold [nb]
+// outputs : stats_i [nb][3] (status, sqp_iter, qp_iter), stats_d [nb][6] (cost, res[4], alpha),
+//           step_z [nb][N+1][6] (QP solution du,dx), qp_pi [nb][N][4], qp_lam [nb][N][6], lin_* optional (A [nb][N][8] ...)
+int hs_solve(void* const* models, int nmodels, int N, double dt, int nb, const int* objid,
+             const double* W, const double* We, const double* lh, const double* uh,
+             const double* opts_d, const int* opts_i, const double* ctrl5,
+             double* x0, const double* yref, const double* yref_e, double* x, double* u, double* pi, double* lam, int* cold,
+             int* stats_i, double* stats_d, double* step_z, double* qp_pi, double* qp_lam,
+             double* lin_A, double* lin_B, double* lin_b, double* lin_g) {
+    const int Bp = (nb + 31) / 32 * 32;
+    std::vector<double> blobs((size_t)nmodels * MODEL_DOUBLES);
+    for (int i = 0; i < nmodels; ++i) std::memcpy(&blobs[(size_t)i * MODEL_DOUBLES], ((HostModel*)models[i])->blob.data(), MODEL_DOUBLES * 8);
+    SolverDev S; std::memset(&S, 0, sizeof S);
+    S.B = nb; S.Bp = Bp; S.N = N; S.nmodels = nmodels; S.dt = dt; S.models = blobs.data();
+    std::vector<int> v_obj(Bp, 0), v_status(Bp, 0), v_sqp(Bp, 0), v_qpit(Bp, 0), v_cold(Bp, 0), v_done(Bp, 0), v_qpstat(Bp, 0), v_ndone(32, 0);
+    for (int b = 0; b < nb; ++b) { v_obj[b] = objid ? objid[b] : 0; v_cold[b] = cold ? cold[b] : 0; }
+    S.objid = v_obj.data(); S.status = v_status.data(); S.sqp_iter = v_sqp.data(); S.qp_iter = v_qpit.data();
+    S.cold = v_cold.data(); S.done = v_done.data(); S.qpstat = v_qpstat.data(); S.ndone = v_ndone.data();
+    auto slab = [&](size_t rows) { return std::vector<double>(rows * Bp, 0.0); };
+    auto sx = slab((N + 1) * 4), su = slab(N * 2), spi = slab(N * 4), slam = slab(N * 6), sx0 = slab(4), syr = slab(N * 6), sye = slab(4);
+    auto sA = slab(N * 8), sB = slab(N * 8), sb = slab(N * 4), sg = slab(N * 6), sqN = slab(4), sdx0 = slab(4);
+    auto sz = slab((N + 1) * 6), szp = slab((N + 1) * 6), szc = slab(N * 3), slq = slab(N * 6), st = slab(N * 6);
+    auto sK = slab(N * 8), sLi = slab(N * 3), sPb = slab(N * 4), skf = slab(N * 2), spq = slab(N * 4);
+    auto srg = slab((N + 1) * 6), srb = slab(N * 4), srgs = slab(N);
+    auto scost = slab(1), sres = slab(4), salpha = slab(1), swpi = slab(N * 4), swlam = slab(N * 6), swx0 = slab(4);
+    S.x = sx.data(); S.u = su.data(); S.pi = spi.data(); S.lam = slam.data(); S.x0 = sx0.data(); S.yref = syr.data(); S.yref_e = sye.data();
+    S.A = sA.data(); S.Bm = sB.data(); S.b = sb.data(); S.g = sg.data(); S.qN = sqN.data(); S.dx0 = sdx0.data();
+    S.z = sz.data(); S.zp = szp.data(); S.zc = szc.data(); S.lamq = slq.data(); S.t = st.data();
+    S.K = sK.data(); S.Li = sLi.data(); S.Pb = sPb.data(); S.kff = skf.data(); S.piq = spq.data();
+    S.rg = srg.data(); S.rb = srb.data(); S.rgs = srgs.data();
+    S.cost = scost.data(); S.res = sres.data(); S.alpha = salpha.data(); S.wpi = swpi.data(); S.wlam = swlam.data(); S.wx0 = swx0.data();
+    // cost constants exactly like flush_cost() in qspush_capi.cu
+    std::vector<double> Wdt((size_t)N * 36), H((size_t)N * 21), QN(10), Wev(We, We + 16);
+    auto perm = [](int zi) { return zi < 2 ? 4 + zi : zi - 2; };
+    for (int k = 0; k < N; ++k) {
+        for (int i = 0; i < 36; ++i) Wdt[(size_t)k * 36 + i] = dt * W[(size_t)k * 36 + i];
+        for (int i = 0; i < 6; ++i) for (int j = 0; j <= i; ++j)
+            H[(size_t)k * 21 + LT(i, j)] = dt * 0.5 * (W[(size_t)k * 36 + perm(i) + 6 * perm(j)] + W[(size_t)k * 36 + perm(j) + 6 * perm(i)]);
+    }
+    for (int i = 0; i < 4; ++i) for (int j = 0; j <= i; ++j) QN[LT(i, j)] = 0.5 * (We[i + 4 * j] + We[j + 4 * i]);
+    S.Wdt = Wdt.data(); S.We = Wev.data(); S.H = H.data(); S.QN = QN.data();
+    for (int i = 0; i < 3; ++i) { S.lh[i] = lh[i]; S.uh[i] = uh[i]; }
+    // AoS -> SoA (k_aos_to_soa)
+    auto in = [&](const double* src, std::vector<double>& dst, int R) { for (int b = 0; b < nb; ++b) for (int r = 0; r < R; ++r) dst[(size_t)r * Bp + b] = src[(size_t)b * R + r]; };
+    auto out = [&](const std::vector<double>& src, double* dst, int R) { if (!dst) return; for (int b = 0; b < nb; ++b) for (int r = 0; r < R; ++r) dst[(size_t)b * R + r] = src[(size_t)r * Bp + b]; };
+    in(x0, sx0, 4); in(yref, syr, N * 6); in(yref_e, sye, 4); in(x, sx, (N + 1) * 4); in(u, su, N * 2);
+    if (pi) in(pi, spi, N * 4);
+    if (lam) in(lam, slam, N * 6);
+    const int mode = opts_i[0];
+    IpmOpts io{opts_i[1], opts_d[0], opts_d[1], opts_d[2], opts_d[3]};
+    SqpOpts so{opts_i[2], {opts_d[4], opts_d[5], opts_d[6], opts_d[7]}, opts_i[3], opts_d[8], opts_d[9], opts_d[10]};
+    CtrlDev cp{ctrl5[0], ctrl5[1], ctrl5[2], ctrl5[3], ctrl5[4], opts_i[4]};
+    const double* Mall = blobs.data();
+    if (opts_i[5]) for (int b = 0; b < nb; ++b) prepare_one(S, cp, Mall, b);
+    auto linearise_all = [&]() { for (int k = 0; k <= N; ++k) for (int b = 0; b < nb; ++b) if (!S.done[b]) linearise_one(S, Mall, k, b); };
+    if (mode == 0 || mode == 2) {
+        linearise_all();
+        for (int b = 0; b < nb; ++b) qp_one(S, io, b, mode == 0 ? 1 : 0);
+    } else {
+        for (int it = 0; it <= so.max_iter; ++it) {
+            linearise_all();
+            int nd = 0;
+            for (int b = 0; b < nb; ++b) { if (!S.done[b]) nlp_res_one(S, so, it, b); nd += S.done[b]; }
+            if (nd >= nb || it == so.max_iter) break;
+            for (int b = 0; b < nb; ++b) if (!S.done[b]) qp_one(S, io, b, 0);
+            for (int b = 0; b < nb; ++b) if (!S.done[b]) linesearch_one(S, so, Mall, it, b);
+        }
+        for (int b = 0; b < nb; ++b) cost_one(S, b);
+    }
+    out(sz, step_z, (N + 1) * 6); out(mode == 0 ? spi : spq, qp_pi, N * 4); out(mode == 0 ? slam : slq, qp_lam, N * 6);
+    out(sA, lin_A, N * 8); out(sB, lin_B, N * 8); out(sb, lin_b, N * 4); out(sg, lin_g, N * 6);
+    if (opts_i[6]) for (int b = 0; b < nb; ++b) for (int c = 0; c < 16; ++c) shift_one(S, c, b);
+    out(sx0, x0, 4); out(sx, x, (N + 1) * 4); out(su, u, N * 2);
+    if (pi) out(spi, pi, N * 4);
+    if (lam) out(slam, lam, N * 6);
+    for (int b = 0; b < nb; ++b) {
+        if (cold) cold[b] = S.cold[b];
+        if (stats_i) { stats_i[3 * b] = S.status[b]; stats_i[3 * b + 1] = S.sqp_iter[b]; stats_i[3 * b + 2] = S.qp_iter[b]; }
+        if (stats_d) { stats_d[6 * b] = scost[b]; for (int i = 0; i < 4; ++i) stats_d[6 * b + 1 + i] = sres[(size_t)i * Bp + b]; stats_d[6 * b + 5] = salpha[b]; }
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,235 @@
+// qs_kernels.cuh — sm_100a kernels of the batched pusher-slider NMPC engine.
+//
+// Data layout (HBM): every per-problem quantity is a structure-of-arrays slab
+//     slab[(stage * DIM + comp) * Bp + problem],   Bp = batch rounded up to 32,
+// so a warp that walks problems reads/writes one 256-byte line per instruction, both in the
+// (problem, stage)-parallel linearisation kernel and in the problem-per-thread QP kernel.
+// The per-object spline tables (pp-form, 10 KB each) are staged once per CTA into shared memory
+// by a single bulk TMA copy (cp.async.bulk + mbarrier).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "qs_solver.cuh"
+
+namespace qs {
+
+// ------------------------------------------------------------------------------------------------
+// model staging: one bulk TMA copy global -> shared per CTA, completion on an mbarrier
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ const double* stage_models(const double* __restrict__ gmodels, int nmodels) {
+    extern __shared__ __align__(128) unsigned char qs_smem[];
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(qs_smem);
+    double* dst = reinterpret_cast<double*>(qs_smem + 128);
+    const uint32_t bytes = (uint32_t)nmodels * MODEL_DOUBLES * 8u;
+    const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(mbar);
+    const uint32_t dst_s = (uint32_t)__cvta_generic_to_shared(dst);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst_s), "l"(gmodels), "r"(bytes), "r"(mbar_s) : "memory");
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(mbar_s), "r"(0u) : "memory");
+    }
+    return dst;
+}
+inline size_t model_smem_bytes(int nmodels) { return 128 + (size_t)nmodels * MODEL_DOUBLES * 8; }
+
+// ------------------------------------------------------------------------------------------------
+// AoS <-> SoA transposition (set/get): user buffer [nb][R]  <->  slab rows [row0 .. row0+R) x Bp
+// ------------------------------------------------------------------------------------------------
+__global__ void k_aos_to_soa(const double* __restrict__ src, double* __restrict__ dst, int nb, int R, int row0, int lo, int Bp) {
+    __shared__ double tile[32][33];
+    const int bx = blockIdx.x * 32, ry = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {          // read: r fastest
+        const int i = bx + j, r = ry + threadIdx.x;
+        if (i < nb && r < R) tile[j][threadIdx.x] = src[(size_t)i * R + r];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {          // write: problem fastest
+        const int r = ry + j, i = bx + threadIdx.x;
+        if (i < nb && r < R) dst[(size_t)(row0 + r) * Bp + lo + i] = tile[threadIdx.x][j];
+    }
+}
+__global__ void k_soa_to_aos(const double* __restrict__ src, double* __restrict__ dst, int nb, int R, int row0, int lo, int Bp) {
+    __shared__ double tile[32][33];
+    const int bx = blockIdx.x * 32, ry = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = ry + j, i = bx + threadIdx.x;
+        if (i < nb && r < R) tile[j][threadIdx.x] = src[(size_t)(row0 + r) * Bp + lo + i];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int i = bx + j, r = ry + threadIdx.x;
+        if (i < nb && r < R) dst[(size_t)i * R + r] = tile[threadIdx.x][j];
+    }
+}
+__global__ void k_fill_int(int* p, int n, int v) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+
+// ------------------------------------------------------------------------------------------------
+// K1 / K2 stateless evaluation kernels (config 2 entry points), AoS [cnt][dim] like the C-ABI
+// ------------------------------------------------------------------------------------------------
+__global__ void k_eval_spline(const double* __restrict__ gmodel, int cnt, const double* __restrict__ s, int wrap, int single,
+                              double* C, double* Cd, double* Cdd, double* tv, double* nv, double* kappa) {
+    const double* M = stage_models(gmodel, 1);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    double sg = s[i];
+    if (wrap == 1) sg = matlab_mod(sg, M[1], single != 0);
+    else if (wrap == 2) sg = wrap_dyn(sg, M[1]);
+    Curve c; curve_eval(M, sg, c);
+    if (C) reinterpret_cast<double2*>(C)[i] = make_double2(c.cx, c.cy);
+    if (Cd) reinterpret_cast<double2*>(Cd)[i] = make_double2(c.dx, c.dy);
+    if (Cdd) { double ex, ey; curve_dd(M, sg, ex, ey); reinterpret_cast<double2*>(Cdd)[i] = make_double2(ex, ey); }
+    if (tv || nv) {
+        const double nrm = sqrt(c.dx * c.dx + c.dy * c.dy);
+        const double tx = c.dx / nrm, ty = c.dy / nrm;
+        if (tv) reinterpret_cast<double2*>(tv)[i] = make_double2(tx, ty);
+        if (nv) reinterpret_cast<double2*>(nv)[i] = make_double2(ty, -tx);
+    }
+    if (kappa) kappa[i] = (c.dx * c.hy - c.dy * c.hx) / (c.dx * c.dx + c.dy * c.dy);
+}
+
+__global__ void k_eval_dynamics(const double* __restrict__ gmodel, int cnt, const double* __restrict__ x, const double* __restrict__ u,
+                                double* f, double* Jx, double* Ju) {
+    const double* M = stage_models(gmodel, 1);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const double2 xa = reinterpret_cast<const double2*>(x)[2 * i + 1];   // theta, s
+    const double2 ua = reinterpret_cast<const double2*>(u)[i];
+    Dyn d;
+    if (Jx || Ju) dyn_eval<true>(M, xa.x, xa.y, ua.x, ua.y, d); else dyn_eval<false>(M, xa.x, xa.y, ua.x, ua.y, d);
+    double2* fo = reinterpret_cast<double2*>(f) + 2 * i;
+    fo[0] = make_double2(d.f[0], d.f[1]); fo[1] = make_double2(d.f[2], d.f[3]);
+    if (Jx) {
+        double2* o = reinterpret_cast<double2*>(Jx) + 8 * i;
+        const double jt[4] = {-d.f[1], d.f[0], 0.0, 0.0};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { o[2 * r] = make_double2(0.0, 0.0); o[2 * r + 1] = make_double2(jt[r], d.fs[r]); }
+    }
+    if (Ju) {
+        double2* o = reinterpret_cast<double2*>(Ju) + 4 * i;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) o[r] = make_double2(d.fun[r], d.fut[r]);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_eval_erk4(const double* __restrict__ gmodel, int cnt, const double* __restrict__ x, const double* __restrict__ u, double dt,
+            double* Phi, double* A, double* Bo) {
+    const double* M = stage_models(gmodel, 1);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const double2 x01 = reinterpret_cast<const double2*>(x)[2 * i], x23 = reinterpret_cast<const double2*>(x)[2 * i + 1];
+    const double2 ua = reinterpret_cast<const double2*>(u)[i];
+    const double xv[4] = {x01.x, x01.y, x23.x, x23.y};
+    double P4[4], Sm[16];
+    erk4_sens(M, xv, ua.x, ua.y, dt, P4, Sm);
+    double2* po = reinterpret_cast<double2*>(Phi) + 2 * i;
+    po[0] = make_double2(P4[0], P4[1]); po[1] = make_double2(P4[2], P4[3]);
+    if (A) {
+        double2* o = reinterpret_cast<double2*>(A) + 8 * i;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            o[2 * r] = make_double2(r == 0 ? 1.0 : 0.0, r == 1 ? 1.0 : 0.0);
+            o[2 * r + 1] = make_double2(Sm[4 * r + 0], Sm[4 * r + 1]);
+        }
+    }
+    if (Bo) {
+        double2* o = reinterpret_cast<double2*>(Bo) + 4 * i;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) o[r] = make_double2(Sm[4 * r + 2], Sm[4 * r + 3]);
+    }
+}
+
+__global__ void k_eval_vbound(const double* __restrict__ gmodel, int cnt, const double* __restrict__ s, CtrlDev cp,
+                              double* vb, double* ta) {
+    const double* M = stage_models(gmodel, 1);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    double t;
+    const double v = v_bound_of(M, s[i], cp.v_alpha, cp.d_v_bound, cp.t_angle0, cp.u_t_ub, cp.single != 0, &t);
+    if (vb) vb[i] = v;
+    if (ta) ta[i] = t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// solver kernels: thin launch wrappers around the per-thread bodies in qs_solver.cuh
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_prepare(SolverDev S, CtrlDev cp) {
+    const double* Mall = stage_models(S.models, S.nmodels);
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= S.B) return;
+    prepare_one(S, cp, Mall, b);
+}
+
+// one thread per (problem, stage); consecutive threads walk problems -> coalesced slab accesses
+__global__ void __launch_bounds__(128) k_linearise(SolverDev S) {
+    const double* Mall = stage_models(S.models, S.nmodels);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = (int)(tid / S.Bp), b = (int)(tid % S.Bp);
+    if (k > S.N || b >= S.B) return;
+    if (S.done && S.done[b]) return;
+    linearise_one(S, Mall, k, b);
+}
+
+// one problem per thread, ppw problems packed per warp (one warp per CTA)
+__global__ void __launch_bounds__(32) k_qp(SolverDev S, IpmOpts o, int ppw, int apply) {
+    const int lane = threadIdx.x & 31;
+    if (lane >= ppw) return;
+    const int b = blockIdx.x * ppw + lane;
+    if (b >= S.B) return;
+    if (S.done && S.done[b]) return;
+    qp_one(S, o, b, apply);
+}
+
+__global__ void __launch_bounds__(64) k_nlp_res(SolverDev S, SqpOpts o, int it) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= S.B || S.done[b]) return;
+    if (nlp_res_one(S, o, it, b)) atomicAdd(S.ndone, 1);
+}
+
+__global__ void __launch_bounds__(64) k_linesearch(SolverDev S, SqpOpts o, int it) {
+    const double* Mall = stage_models(S.models, S.nmodels);
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= S.B || S.done[b]) return;
+    if (linesearch_one(S, o, Mall, it, b)) atomicAdd(S.ndone, 1);
+}
+
+__global__ void k_cost(SolverDev S) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= S.B) return;
+    cost_one(S, b);
+}
+
+__global__ void k_shift(SolverDev S) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= S.B) return;
+    shift_one(S, blockIdx.y, b);
+}
+
+// forward-Euler plant step on caller arrays [B][4], [B][2] (helper.m:294, 307)
+__global__ void k_plant_step(SolverDev S, double* x, const double* u) {
+    const double* Mall = stage_models(S.models, S.nmodels);
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= S.B) return;
+    const double* M = Mall + (size_t)S.objid[b] * MODEL_DOUBLES;
+    double2* xp = reinterpret_cast<double2*>(x) + 2 * b;
+    const double2 x01 = xp[0], x23 = xp[1];
+    const double2 ua = reinterpret_cast<const double2*>(u)[b];
+    Dyn d;
+    dyn_eval<false>(M, x23.x, x23.y, ua.x, ua.y, d);
+    xp[0] = make_double2(fma(S.dt, d.f[0], x01.x), fma(S.dt, d.f[1], x01.y));
+    xp[1] = make_double2(fma(S.dt, d.f[2], x23.x), fma(S.dt, d.f[3], x23.y));
+}
+
+}  // namespace qs

@@ -1,0 +1,431 @@
+// qs_solver.cuh — per-problem / per-(problem, stage) bodies of the solver kernels.
+//
+// Each function does the work of ONE thread of the corresponding kernel in qs_kernels.cuh on the
+// structure-of-arrays slabs described there.  They are __host__ __device__ only so that
+// tests/hostsim can execute the identical logic on a GPU-less CI box; the product launches them
+// exclusively from the sm_100a kernels.
+#pragma once
+#include "qs_device.cuh"
+#include "qs_qp.cuh"
+
+namespace qs {
+
+// ------------------------------------------------------------------------------------------------
+// device-side view of a solver (passed by value to the kernels)
+// ------------------------------------------------------------------------------------------------
+struct SolverDev {
+    int B, Bp, N, nmodels;
+    double dt;
+    const double* models;   // [nmodels][MODEL_DOUBLES]
+    const int* objid;       // [Bp]
+    // iterate and references
+    double *x, *u, *pi, *lam;            // [(N+1)*4] [N*2] [N*4] [N*6]  x Bp
+    double *x0, *yref, *yref_e;          // [4] [N*6] [4]
+    // linearisation
+    double *A, *Bm, *b, *g, *qN, *dx0;   // [N*8] [N*8] [N*4] [N*6] [4] [4]
+    // QP work
+    double *z, *zp, *zc, *lamq, *t, *K, *Li, *Pb, *kff, *piq, *rg, *rb, *rgs;
+    // cost / constraint constants
+    const double *Wdt;      // [N][36] dt*W, y = [x;u] order, column-major
+    const double *We;       // [16]
+    const double *H;        // [N][21] packed, z order
+    const double *QN;       // [10]
+    double lh[3], uh[3];
+    // bookkeeping
+    int *status, *sqp_iter, *qp_iter, *cold, *done, *qpstat, *ndone;
+    double *cost, *res, *alpha;
+    // SQP merit weights
+    double *wpi, *wlam, *wx0;
+};
+
+struct IpmOpts { int max_iter; double tol, mu0, thr, tau; };
+struct SqpOpts { int max_iter; double tol[4]; int globalization; double alpha_min, alpha_red, eps_sd; };
+struct CtrlDev { double v_alpha, d_v_bound, t_angle0, u_t_ub, u_n_lb; int single; };
+
+#define QS_EL(p, row, b) (p)[(size_t)(row) * S.Bp + (b)]
+
+
+#define QS_EL(p, row, b) (p)[(size_t)(row) * S.Bp + (b)]
+
+// K6 prepare: NMPC_controller.solve pre-processing (NMPC_controller.m:332, 351-380)
+QS_HD void prepare_one(const SolverDev& S, const CtrlDev& cp, const double* __restrict__ Mall, int b) {
+    const double* M = Mall + (size_t)S.objid[b] * MODEL_DOUBLES;
+    const int N = S.N;
+    const double bb = M[1];
+    double x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = QS_EL(S.x0, i, b);
+    {   // :332  x0(4) = mod(x0(4), b) - b*(x0(4) < 0)
+        double w = matlab_mod(x[3], bb, cp.single != 0);
+        if (cp.single) w = (double)((float)w - (float)bb * (x[3] < 0.0 ? 1.f : 0.f));
+        else w = w - bb * (x[3] < 0.0 ? 1.0 : 0.0);
+        x[3] = w;
+        QS_EL(S.x0, 3, b) = w;                                   // :334 constr_x0 <- wrapped x0
+    }
+    const bool cold = S.cold[b] != 0;
+    if (cold) {                                                  // :351-355
+        for (int k = 0; k < N; ++k) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) QS_EL(S.pi, k * 4 + i, b) = 0.0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) QS_EL(S.lam, k * 6 + i, b) = 0.0;
+        }
+        S.cold[b] = 0;
+    }
+    double vb = v_bound_of(M, x[3], cp.v_alpha, cp.d_v_bound, cp.t_angle0, cp.u_t_ub, cp.single != 0, nullptr);   // :357
+    for (int k = 0; k < N; ++k) {
+        double un = cold ? cp.u_n_lb : QS_EL(S.u, k * 2 + 0, b);
+        double ut = cold ? 0.0 : QS_EL(S.u, k * 2 + 1, b);
+        if (fabs(ut) > vb) {                                     // :358-364, :375-379
+            const double old = ut;
+            ut = (double)((old > 0.0) - (old < 0.0)) * vb;
+            un = ut * un / old;
+        }
+        QS_EL(S.u, k * 2 + 0, b) = un; QS_EL(S.u, k * 2 + 1, b) = ut;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) QS_EL(S.x, k * 4 + i, b) = x[i];
+        Dyn d;
+        dyn_eval<false>(M, x[2], x[3], un, ut, d);               // :369-370 forward Euler
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = fma(S.dt, d.f[i], x[i]);
+        if (k + 1 < N) vb = v_bound_of(M, x[3], cp.v_alpha, cp.d_v_bound, cp.t_angle0, cp.u_t_ub, cp.single != 0, nullptr);   // :371
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) QS_EL(S.x, N * 4 + i, b) = x[i];
+}
+
+// K2 + K3 linearise, one (problem, stage) pair; stage index N does the terminal terms.
+//   A_k, B_k, b_k = Phi(x_k,u_k) - x_{k+1}   (ERK4 + forward sensitivities)
+//   g_k = dt * W_k ([x_k;u_k] - yref_k) in z = [u;x] order ; q_N = W_e (x_N - yref_e) ; dx0 = x0 - x_0
+QS_HD void linearise_one(const SolverDev& S, const double* __restrict__ Mall, int k, int b) {
+    const int N = S.N;
+    if (k == N) {
+        double r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r[i] = QS_EL(S.x, N * 4 + i, b) - QS_EL(S.yref_e, i, b);
+            QS_EL(S.dx0, i, b) = QS_EL(S.x0, i, b) - QS_EL(S.x, i, b);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double a = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a = fma(S.We[i + 4 * j], r[j], a);
+            QS_EL(S.qN, i, b) = a;
+        }
+        return;
+    }
+    const double* M = Mall + (size_t)S.objid[b] * MODEL_DOUBLES;
+    double x[4], xn[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { x[i] = QS_EL(S.x, k * 4 + i, b); xn[i] = QS_EL(S.x, (k + 1) * 4 + i, b); }
+    const double un = QS_EL(S.u, k * 2 + 0, b), ut = QS_EL(S.u, k * 2 + 1, b);
+    double yr[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) yr[i] = QS_EL(S.yref, k * 6 + i, b);
+    double Phi[4], Sm[16];
+    erk4_sens(M, x, un, ut, S.dt, Phi, Sm);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        QS_EL(S.A, k * 8 + i, b) = Sm[4 * i + 0];
+        QS_EL(S.A, k * 8 + 4 + i, b) = Sm[4 * i + 1];
+        QS_EL(S.Bm, k * 8 + i, b) = Sm[4 * i + 2];
+        QS_EL(S.Bm, k * 8 + 4 + i, b) = Sm[4 * i + 3];
+        QS_EL(S.b, k * 4 + i, b) = Phi[i] - xn[i];
+    }
+    const double r[6] = {x[0] - yr[0], x[1] - yr[1], x[2] - yr[2], x[3] - yr[3], un - yr[4], ut - yr[5]};
+    const double* W = S.Wdt + (size_t)k * 36;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double a = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) a = fma(W[i + 6 * j], r[j], a);
+        QS_EL(S.g, k * 6 + (i < 4 ? 2 + i : i - 4), b) = a;       // y index -> z index
+    }
+}
+
+QS_HD double stage_cost(const SolverDev& S, int k, int b) {
+    double r[6];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = QS_EL(S.x, k * 4 + i, b) - QS_EL(S.yref, k * 6 + i, b);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) r[4 + i] = QS_EL(S.u, k * 2 + i, b) - QS_EL(S.yref, k * 6 + 4 + i, b);
+    const double* W = S.Wdt + (size_t)k * 36;
+    double q = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double a = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) a = fma(W[i + 6 * j], r[j], a);
+        q = fma(r[i], a, q);
+    }
+    return 0.5 * q;
+}
+QS_HD double terminal_cost(const SolverDev& S, int b) {
+    double r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = QS_EL(S.x, S.N * 4 + i, b) - QS_EL(S.yref_e, i, b);
+    double q = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double a = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a = fma(S.We[i + 4 * j], r[j], a);
+        q = fma(r[i], a, q);
+    }
+    return 0.5 * q;
+}
+
+// K4 QP (+ K5 in RTI mode: full step, multipliers replaced, cost, status) for problem b
+QS_HD void qp_one(const SolverDev& S, const IpmOpts& o, int b, int apply) {
+    QpConst C;
+    C.N = S.N; C.H = S.H; C.QN = S.QN;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { C.lh[i] = S.lh[i]; C.uh[i] = S.uh[i]; }
+    C.max_iter = o.max_iter; C.tol = o.tol; C.mu0 = o.mu0; C.thr = o.thr; C.tau = o.tau;
+    QpView V;
+    V.stride = (size_t)S.Bp;
+    V.A = S.A + b; V.B = S.Bm + b; V.b = S.b + b; V.g = S.g + b; V.qN = S.qN + b; V.dx0 = S.dx0 + b;
+    V.x = S.x + b; V.u = S.u + b;
+    V.z = S.z + b; V.zp = S.zp + b; V.zc = S.zc + b; V.t = S.t + b;
+    V.K = S.K + b; V.Li = S.Li + b; V.Pb = S.Pb + b; V.kff = S.kff + b;
+    V.rg = S.rg + b; V.rb = S.rb + b; V.rgs = S.rgs + b;
+    V.lam = (apply ? S.lam : S.lamq) + b;      // RTI: multipliers are replaced by the QP's
+    V.pi = (apply ? S.pi : S.piq) + b;
+    int iters, status; double res[4];
+    qp_ipm(C, V, iters, status, res);
+    S.qpstat[b] = status;
+    if (apply) S.qp_iter[b] = iters; else S.qp_iter[b] += iters;
+    if (!apply) return;
+    // ---- K5 (RTI): x += dx, u += du, cost, status
+    const int N = S.N;
+    bool nan = false;
+    double cost = 0.0;
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { const double v = QS_EL(S.u, k * 2 + i, b) + QS_EL(S.z, k * 6 + i, b); QS_EL(S.u, k * 2 + i, b) = v; nan = nan || !(v == v); }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) QS_EL(S.x, k * 4 + i, b) += QS_EL(S.z, k * 6 + 2 + i, b);
+        cost += stage_cost(S, k, b);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) QS_EL(S.x, N * 4 + i, b) += QS_EL(S.z, N * 6 + 2 + i, b);
+    cost += terminal_cost(S, b);
+    S.cost[b] = cost;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) QS_EL(S.res, i, b) = res[i];
+    S.sqp_iter[b] = 1;
+    S.alpha[b] = 1.0;
+    S.status[b] = nan ? 1 : (status == 2 ? 4 : 0);     // QP iteration limit is tolerated
+}
+
+// NLP residuals (inf-norms) and the convergence test of one SQP iteration; returns 1 when problem b finishes
+QS_HD int nlp_res_one(const SolverDev& S, const SqpOpts& o, int it, int b) {
+    const int N = S.N;
+    double r_stat = 0.0, r_eq = 0.0, r_in = 0.0, r_cp = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r_eq = fmax(r_eq, fabs(QS_EL(S.dx0, i, b)));
+    for (int k = 0; k < N; ++k) {
+        double g[6], pk1[4];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) g[i] = QS_EL(S.g, k * 6 + i, b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pk1[i] = QS_EL(S.pi, k * 4 + i, b);
+        double a3[4], a4[4], b1[4], b2[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a3[i] = QS_EL(S.A, k * 8 + i, b); a4[i] = QS_EL(S.A, k * 8 + 4 + i, b); b1[i] = QS_EL(S.Bm, k * 8 + i, b); b2[i] = QS_EL(S.Bm, k * 8 + 4 + i, b); }
+        g[0] += dot4(b1, pk1); g[1] += dot4(b2, pk1);
+        g[2] += pk1[0]; g[3] += pk1[1]; g[4] += dot4(a3, pk1); g[5] += dot4(a4, pk1);
+        if (k > 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) g[2 + i] -= QS_EL(S.pi, (k - 1) * 4 + i, b);
+        }
+        const double h[3] = {QS_EL(S.x, k * 4 + 3, b), QS_EL(S.u, k * 2, b), QS_EL(S.u, k * 2 + 1, b)};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (k == 0 && c == 0) continue;
+            const double ll = QS_EL(S.lam, k * 6 + c, b), lu = QS_EL(S.lam, k * 6 + 3 + c, b);
+            g[cidx(c)] += lu - ll;
+            const double sl = h[c] - S.lh[c], su = S.uh[c] - h[c];
+            r_in = fmax(r_in, fmax(fmax(-sl, 0.0), fmax(-su, 0.0)));
+            r_cp = fmax(r_cp, fmax(fabs(ll * sl), fabs(lu * su)));
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { if (k == 0 && i >= 2) continue; r_stat = fmax(r_stat, fabs(g[i])); }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r_eq = fmax(r_eq, fabs(QS_EL(S.b, k * 4 + i, b)));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r_stat = fmax(r_stat, fabs(QS_EL(S.qN, i, b) - QS_EL(S.pi, (N - 1) * 4 + i, b)));
+    QS_EL(S.res, 0, b) = r_stat; QS_EL(S.res, 1, b) = r_eq; QS_EL(S.res, 2, b) = r_in; QS_EL(S.res, 3, b) = r_cp;
+    const bool nan = !(r_stat == r_stat) || !(r_eq == r_eq) || !(r_in == r_in) || !(r_cp == r_cp);
+    int fin = -1;
+    if (nan) fin = 1;
+    else if (r_stat < o.tol[0] && r_eq < o.tol[1] && r_in < o.tol[2] && r_cp < o.tol[3]) fin = 0;
+    else if (it >= o.max_iter) fin = 2;
+    if (fin >= 0) { S.status[b] = fin; S.done[b] = 1; S.sqp_iter[b] = it; return 1; }
+    return 0;
+}
+
+QS_HD double merit_at(const SolverDev& S, const double* M, int b, double alpha) {
+    // L1 merit of the trial point w + alpha*dw (dw in S.z), SURVEY A2.5
+    const int N = S.N;
+    double mval = 0.0;
+    double x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        x[i] = fma(alpha, QS_EL(S.z, 2 + i, b), QS_EL(S.x, i, b));
+        mval += QS_EL(S.wx0, i, b) * fabs(QS_EL(S.x0, i, b) - x[i]);
+    }
+    for (int k = 0; k < N; ++k) {
+        const double un = fma(alpha, QS_EL(S.z, k * 6 + 0, b), QS_EL(S.u, k * 2 + 0, b));
+        const double ut = fma(alpha, QS_EL(S.z, k * 6 + 1, b), QS_EL(S.u, k * 2 + 1, b));
+        double xn[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xn[i] = fma(alpha, QS_EL(S.z, (k + 1) * 6 + 2 + i, b), QS_EL(S.x, (k + 1) * 4 + i, b));
+        // stage cost
+        double r[6];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[i] = x[i] - QS_EL(S.yref, k * 6 + i, b);
+        r[4] = un - QS_EL(S.yref, k * 6 + 4, b); r[5] = ut - QS_EL(S.yref, k * 6 + 5, b);
+        const double* W = S.Wdt + (size_t)k * 36;
+        double q = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double a = 0.0;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) a = fma(W[i + 6 * j], r[j], a);
+            q = fma(r[i], a, q);
+        }
+        mval += 0.5 * q;
+        double Phi[4];
+        erk4_plain(M, x, un, ut, S.dt, Phi);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mval += QS_EL(S.wpi, k * 4 + i, b) * fabs(Phi[i] - xn[i]);
+        const double h[3] = {x[3], un, ut};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (k == 0 && c == 0) continue;
+            mval += QS_EL(S.wlam, k * 6 + c, b) * fmax(0.0, S.lh[c] - h[c]);
+            mval += QS_EL(S.wlam, k * 6 + 3 + c, b) * fmax(0.0, h[c] - S.uh[c]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = xn[i];
+    }
+    double r[4], q = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = x[i] - QS_EL(S.yref_e, i, b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double a = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a = fma(S.We[i + 4 * j], r[j], a);
+        q = fma(r[i], a, q);
+    }
+    return mval + 0.5 * q;
+}
+
+// merit-function backtracking line search and iterate update of one SQP iteration;
+// returns 1 when problem b finishes (QP failure)
+QS_HD int linesearch_one(const SolverDev& S, const SqpOpts& o, const double* __restrict__ Mall, int it, int b) {
+    const int N = S.N;
+    if (S.qpstat[b] == 2) { S.status[b] = 4; S.done[b] = 1; S.sqp_iter[b] = it + 1; return 1; }
+    const double* M = Mall + (size_t)S.objid[b] * MODEL_DOUBLES;
+    double alpha = 1.0;
+    if (o.globalization == 1) {
+        // merit weights: |multipliers_qp| first, then max(|m|, (w + |m|)/2); directional derivative
+        double dcost = 0.0, dinf = 0.0;
+        for (int k = 0; k < N; ++k) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double a = fabs(QS_EL(S.piq, k * 4 + i, b));
+                const double w = (it == 0) ? a : fmax(a, 0.5 * (QS_EL(S.wpi, k * 4 + i, b) + a));
+                QS_EL(S.wpi, k * 4 + i, b) = w;
+                dinf += w * fabs(QS_EL(S.b, k * 4 + i, b));
+            }
+            const double h[3] = {QS_EL(S.x, k * 4 + 3, b), QS_EL(S.u, k * 2, b), QS_EL(S.u, k * 2 + 1, b)};
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const double a = fabs(QS_EL(S.lamq, k * 6 + c, b));
+                const double w = (it == 0) ? a : fmax(a, 0.5 * (QS_EL(S.wlam, k * 6 + c, b) + a));
+                QS_EL(S.wlam, k * 6 + c, b) = w;
+                if (k == 0 && (c % 3) == 0) continue;
+                const int cc = c % 3;
+                dinf += w * (c < 3 ? fmax(0.0, S.lh[cc] - h[cc]) : fmax(0.0, h[cc] - S.uh[cc]));
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) dcost = fma(QS_EL(S.g, k * 6 + i, b), QS_EL(S.z, k * 6 + i, b), dcost);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dcost = fma(QS_EL(S.qN, i, b), QS_EL(S.z, N * 6 + 2 + i, b), dcost);
+        {   // multiplier of the x0 equality = stage-0 costate of the QP
+            double z0[6], m[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) z0[i] = QS_EL(S.z, i, b);
+            double pk1[4], a3[4], a4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { pk1[i] = QS_EL(S.piq, i, b); a3[i] = QS_EL(S.A, i, b); a4[i] = QS_EL(S.A, 4 + i, b); }
+#pragma unroll
+            for (int i = 2; i < 6; ++i) {
+                double a = QS_EL(S.g, i, b);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) a = fma(S.H[LT(i, j)], z0[j], a);
+                m[i] = a;
+            }
+            m[2] += pk1[0]; m[3] += pk1[1]; m[4] += dot4(a3, pk1); m[5] += dot4(a4, pk1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double a = fabs(m[2 + i]);
+                const double w = (it == 0) ? a : fmax(a, 0.5 * (QS_EL(S.wx0, i, b) + a));
+                QS_EL(S.wx0, i, b) = w;
+                dinf += w * fabs(QS_EL(S.dx0, i, b));
+            }
+        }
+        const double dmerit = dcost - dinf;
+        const double m0 = merit_at(S, M, b, 0.0);
+        for (;;) {
+            const double m1 = merit_at(S, M, b, alpha);
+            if (m1 <= m0 + o.eps_sd * alpha * dmerit) break;
+            alpha *= o.alpha_red;
+            if (alpha < o.alpha_min) { alpha = o.alpha_min; break; }
+        }
+    }
+    // update: w += alpha dw ; pi <- (1-alpha) pi + alpha pi_qp ; lam likewise
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) QS_EL(S.u, k * 2 + i, b) = fma(alpha, QS_EL(S.z, k * 6 + i, b), QS_EL(S.u, k * 2 + i, b));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            QS_EL(S.x, k * 4 + i, b) = fma(alpha, QS_EL(S.z, k * 6 + 2 + i, b), QS_EL(S.x, k * 4 + i, b));
+            const double po = QS_EL(S.pi, k * 4 + i, b);
+            QS_EL(S.pi, k * 4 + i, b) = (1.0 - alpha) * po + alpha * QS_EL(S.piq, k * 4 + i, b);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const double lo = QS_EL(S.lam, k * 6 + i, b);
+            QS_EL(S.lam, k * 6 + i, b) = (1.0 - alpha) * lo + alpha * QS_EL(S.lamq, k * 6 + i, b);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) QS_EL(S.x, N * 4 + i, b) = fma(alpha, QS_EL(S.z, N * 6 + 2 + i, b), QS_EL(S.x, N * 4 + i, b));
+    S.alpha[b] = alpha;
+    return 0;
+}
+
+QS_HD void cost_one(const SolverDev& S, int b) {
+    double c = 0.0;
+    for (int k = 0; k < S.N; ++k) c += stage_cost(S, k, b);
+    S.cost[b] = c + terminal_cost(S, b);
+}
+
+// post-processing shift (NMPC_controller.m:397-399) of component c of problem b:
+// c = 0..3 x, 4..5 u, 6..9 pi, 10..15 lam
+QS_HD void shift_one(const SolverDev& S, int c, int b) {
+    const int N = S.N;
+    if (c < 4) { for (int k = 0; k < N; ++k) QS_EL(S.x, k * 4 + c, b) = QS_EL(S.x, (k + 1) * 4 + c, b); }
+    else if (c < 6) { const int i = c - 4; for (int k = 0; k + 1 < N; ++k) QS_EL(S.u, k * 2 + i, b) = QS_EL(S.u, (k + 1) * 2 + i, b); }
+    else if (c < 10) { const int i = c - 6; for (int k = 0; k + 1 < N; ++k) QS_EL(S.pi, k * 4 + i, b) = QS_EL(S.pi, (k + 1) * 4 + i, b); }
+    else { const int i = c - 10; for (int k = 0; k + 1 < N; ++k) QS_EL(S.lam, k * 6 + i, b) = QS_EL(S.lam, (k + 1) * 6 + i, b); }
+}
+
+}  // namespace qs

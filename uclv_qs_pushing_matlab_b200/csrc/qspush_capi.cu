@@ -1,0 +1,637 @@
+// qspush_capi.cu — C-ABI (include/qspush.h) over the sm_100a kernels.  No CPU compute path:
+// every compute entry point requires a CUDA device and fails with QSPUSH_ERR_NO_DEVICE otherwise.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/qspush.h"
+#include "qs_kernels.cuh"
+#include "qs_model.hpp"
+
+using namespace qs;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail(QSPUSH_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));       \
+    } while (0)
+
+struct qspush_model {
+    HostModel hm;
+    std::mutex mu;
+    std::vector<double*> d_blob;   // lazily uploaded copy per device
+};
+
+struct qspush_solver {
+    int device = 0, B = 0, Bp = 0, N = 0, nmodels = 0;
+    double dt = 0.0;
+    qspush_opts opts;
+    qspush_ctrl ctrl;
+    cudaStream_t stream = nullptr;
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+    SolverDev dev;
+    double *d_Wdt = nullptr, *d_We = nullptr, *d_H = nullptr, *d_QN = nullptr, *d_models = nullptr;
+    double* d_stage = nullptr;
+    int* d_istage = nullptr;
+    size_t stage_doubles = 0;
+    int* h_ndone = nullptr;        // pinned
+    std::vector<double> W, We;     // host copies: N x 36 (y order, column-major), 16
+    bool cost_dirty = true;
+    cudaEvent_t ev[6];
+    double t_tot = 0, t_lin = 0, t_qp = 0, t_prep = 0;
+    long long launches = 0;
+    bool smem_attr_set = false;
+};
+
+extern "C" {
+
+const char* qspush_last_error(void) { return g_err.c_str(); }
+const char* qspush_version(void) { return "qspush-b200 0.1 (sm_100a)"; }
+int qspush_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------ model
+int qspush_model_create(const double* knots, int nknots, const double* ctrl_xy, int n, int degree,
+                        double mu_sp, double c_ellipse, int single_coeffs, qspush_model** out) {
+    if (!out) return fail(QSPUSH_ERR_ARG, "out is NULL");
+    qspush_model* m = new qspush_model();
+    std::string e = model_from_tables(knots, nknots, ctrl_xy, n, degree, mu_sp, c_ellipse, single_coeffs != 0, m->hm);
+    if (!e.empty()) { delete m; return fail(QSPUSH_ERR_ARG, e); }
+    *out = m;
+    return QSPUSH_OK;
+}
+
+int qspush_model_create_from_ply(const char* ply_path, int flip_order, int degree, double mu_sg,
+                                 double mu_sp, double mass, double tau_max, qspush_model** out) {
+    if (!out || !ply_path) return fail(QSPUSH_ERR_ARG, "NULL argument");
+    qspush_model* m = new qspush_model();
+    std::string e = model_from_ply(ply_path, flip_order != 0, degree, mu_sg, mu_sp, mass, tau_max, m->hm);
+    if (!e.empty()) { delete m; return fail(QSPUSH_ERR_IO, e); }
+    *out = m;
+    return QSPUSH_OK;
+}
+
+void qspush_model_free(qspush_model* m) {
+    if (!m) return;
+    for (size_t d = 0; d < m->d_blob.size(); ++d)
+        if (m->d_blob[d]) { cudaSetDevice((int)d); cudaFree(m->d_blob[d]); }
+    delete m;
+}
+
+int qspush_model_info(const qspush_model* m, int* n, int* nknots, double* b, double* c_ellipse, double* mu_sp) {
+    if (!m) return fail(QSPUSH_ERR_ARG, "model is NULL");
+    if (n) *n = m->hm.n;
+    if (nknots) *nknots = (int)m->hm.S.size();
+    if (b) *b = m->hm.b;
+    if (c_ellipse) *c_ellipse = m->hm.c_ellipse;
+    if (mu_sp) *mu_sp = m->hm.mu_sp;
+    return QSPUSH_OK;
+}
+int qspush_model_tables(const qspush_model* m, double* knots, double* ctrl_xy, double* c1, double* c2) {
+    if (!m) return fail(QSPUSH_ERR_ARG, "model is NULL");
+    if (knots) std::memcpy(knots, m->hm.S.data(), m->hm.S.size() * 8);
+    if (ctrl_xy) std::memcpy(ctrl_xy, m->hm.P.data(), m->hm.P.size() * 8);
+    if (c1) std::memcpy(c1, m->hm.c1.data(), m->hm.c1.size() * 8);
+    if (c2) std::memcpy(c2, m->hm.c2.data(), m->hm.c2.size() * 8);
+    return QSPUSH_OK;
+}
+}  // extern "C"
+
+static int need_device(int device) {
+    const int n = qspush_device_count();
+    if (n <= 0) return fail(QSPUSH_ERR_NO_DEVICE, "no CUDA device visible: qspush has no CPU path");
+    if (device < 0 || device >= n) return fail(QSPUSH_ERR_ARG, "device index out of range");
+    return QSPUSH_OK;
+}
+
+static int model_on_device(const qspush_model* cm, int device, const double** out) {
+    qspush_model* m = const_cast<qspush_model*>(cm);
+    std::lock_guard<std::mutex> lk(m->mu);
+    if ((int)m->d_blob.size() <= device) m->d_blob.resize(device + 1, nullptr);
+    if (!m->d_blob[device]) {
+        CK(cudaSetDevice(device));
+        double* p = nullptr;
+        CK(cudaMalloc(&p, MODEL_DOUBLES * 8));
+        CK(cudaMemcpy(p, m->hm.blob.data(), MODEL_DOUBLES * 8, cudaMemcpyHostToDevice));
+        m->d_blob[device] = p;
+    }
+    *out = m->d_blob[device];
+    return QSPUSH_OK;
+}
+
+// Temporary device mirrors for the stateless HOST entry points.
+struct TmpBuf {
+    std::vector<void*> ptrs;
+    ~TmpBuf() { for (void* p : ptrs) cudaFree(p); }
+    int in(const double* h, size_t n, qspush_mem mem, const double** d) {
+        if (!h) { *d = nullptr; return QSPUSH_OK; }
+        if (mem == QSPUSH_MEM_DEVICE) { *d = h; return QSPUSH_OK; }
+        double* p = nullptr;
+        CK(cudaMalloc(&p, n * 8)); ptrs.push_back(p);
+        CK(cudaMemcpy(p, h, n * 8, cudaMemcpyHostToDevice));
+        *d = p; return QSPUSH_OK;
+    }
+    int out(double* h, size_t n, qspush_mem mem, double** d) {
+        if (!h) { *d = nullptr; return QSPUSH_OK; }
+        if (mem == QSPUSH_MEM_DEVICE) { *d = h; return QSPUSH_OK; }
+        double* p = nullptr;
+        CK(cudaMalloc(&p, n * 8)); ptrs.push_back(p);
+        *d = p; return QSPUSH_OK;
+    }
+    static int back(double* h, const double* d, size_t n, qspush_mem mem) {
+        if (!h || mem == QSPUSH_MEM_DEVICE) return QSPUSH_OK;
+        CK(cudaMemcpy(h, d, n * 8, cudaMemcpyDeviceToHost));
+        return QSPUSH_OK;
+    }
+};
+#define RET(call) do { int r__ = (call); if (r__ != QSPUSH_OK) return r__; } while (0)
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------------ stateless eval
+int qspush_eval_spline(const qspush_model* m, int device, qspush_mem mem, int cnt, const double* s, int wrap,
+                       double* C, double* Cd, double* Cdd, double* tvers, double* nvers, double* kappa) {
+    if (!m || !s || cnt < 0) return fail(QSPUSH_ERR_ARG, "bad argument");
+    RET(need_device(device));
+    CK(cudaSetDevice(device));
+    if (cnt == 0) return QSPUSH_OK;
+    const double* dm; RET(model_on_device(m, device, &dm));
+    TmpBuf tb; const double* ds; double *dC, *dCd, *dCdd, *dt_, *dn, *dk;
+    RET(tb.in(s, cnt, mem, &ds));
+    RET(tb.out(C, 2 * (size_t)cnt, mem, &dC)); RET(tb.out(Cd, 2 * (size_t)cnt, mem, &dCd)); RET(tb.out(Cdd, 2 * (size_t)cnt, mem, &dCdd));
+    RET(tb.out(tvers, 2 * (size_t)cnt, mem, &dt_)); RET(tb.out(nvers, 2 * (size_t)cnt, mem, &dn)); RET(tb.out(kappa, cnt, mem, &dk));
+    k_eval_spline<<<(cnt + 255) / 256, 256, model_smem_bytes(1)>>>(dm, cnt, ds, wrap, m->hm.single_coeffs ? 1 : 0, dC, dCd, dCdd, dt_, dn, dk);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    RET(TmpBuf::back(C, dC, 2 * (size_t)cnt, mem)); RET(TmpBuf::back(Cd, dCd, 2 * (size_t)cnt, mem)); RET(TmpBuf::back(Cdd, dCdd, 2 * (size_t)cnt, mem));
+    RET(TmpBuf::back(tvers, dt_, 2 * (size_t)cnt, mem)); RET(TmpBuf::back(nvers, dn, 2 * (size_t)cnt, mem)); RET(TmpBuf::back(kappa, dk, cnt, mem));
+    return QSPUSH_OK;
+}
+
+int qspush_eval_dynamics(const qspush_model* m, int device, qspush_mem mem, int cnt, const double* x, const double* u,
+                         double* f, double* Jx, double* Ju) {
+    if (!m || !x || !u || !f || cnt < 0) return fail(QSPUSH_ERR_ARG, "bad argument");
+    RET(need_device(device));
+    CK(cudaSetDevice(device));
+    if (cnt == 0) return QSPUSH_OK;
+    const double* dm; RET(model_on_device(m, device, &dm));
+    TmpBuf tb; const double *dx, *du; double *df, *dJx, *dJu;
+    RET(tb.in(x, 4 * (size_t)cnt, mem, &dx)); RET(tb.in(u, 2 * (size_t)cnt, mem, &du));
+    RET(tb.out(f, 4 * (size_t)cnt, mem, &df)); RET(tb.out(Jx, 16 * (size_t)cnt, mem, &dJx)); RET(tb.out(Ju, 8 * (size_t)cnt, mem, &dJu));
+    k_eval_dynamics<<<(cnt + 255) / 256, 256, model_smem_bytes(1)>>>(dm, cnt, dx, du, df, dJx, dJu);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    RET(TmpBuf::back(f, df, 4 * (size_t)cnt, mem)); RET(TmpBuf::back(Jx, dJx, 16 * (size_t)cnt, mem)); RET(TmpBuf::back(Ju, dJu, 8 * (size_t)cnt, mem));
+    return QSPUSH_OK;
+}
+
+int qspush_eval_erk4_sens(const qspush_model* m, int device, qspush_mem mem, int cnt, const double* x, const double* u,
+                          double dt, double* Phi, double* A, double* B) {
+    if (!m || !x || !u || !Phi || cnt < 0) return fail(QSPUSH_ERR_ARG, "bad argument");
+    RET(need_device(device));
+    CK(cudaSetDevice(device));
+    if (cnt == 0) return QSPUSH_OK;
+    const double* dm; RET(model_on_device(m, device, &dm));
+    TmpBuf tb; const double *dx, *du; double *dP, *dA, *dB;
+    RET(tb.in(x, 4 * (size_t)cnt, mem, &dx)); RET(tb.in(u, 2 * (size_t)cnt, mem, &du));
+    RET(tb.out(Phi, 4 * (size_t)cnt, mem, &dP)); RET(tb.out(A, 16 * (size_t)cnt, mem, &dA)); RET(tb.out(B, 8 * (size_t)cnt, mem, &dB));
+    k_eval_erk4<<<(cnt + 127) / 128, 128, model_smem_bytes(1)>>>(dm, cnt, dx, du, dt, dP, dA, dB);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    RET(TmpBuf::back(Phi, dP, 4 * (size_t)cnt, mem)); RET(TmpBuf::back(A, dA, 16 * (size_t)cnt, mem)); RET(TmpBuf::back(B, dB, 8 * (size_t)cnt, mem));
+    return QSPUSH_OK;
+}
+
+void qspush_ctrl_default(qspush_ctrl* c) {
+    if (!c) return;
+    c->v_alpha = 1.0; c->d_v_bound = 0.0; c->t_angle0 = 3.0;   // NMPC_controller.m:98-100
+    c->u_t_ub = 0.05; c->u_n_lb = 0.0;                        // :24-25
+}
+
+int qspush_eval_v_bound(const qspush_model* m, int device, qspush_mem mem, int cnt, const double* s,
+                        const qspush_ctrl* ctrl, int single_quirk, double* v_bound, double* t_angle) {
+    if (!m || !s || cnt < 0) return fail(QSPUSH_ERR_ARG, "bad argument");
+    RET(need_device(device));
+    CK(cudaSetDevice(device));
+    if (cnt == 0) return QSPUSH_OK;
+    qspush_ctrl c; if (ctrl) c = *ctrl; else qspush_ctrl_default(&c);
+    CtrlDev cd{c.v_alpha, c.d_v_bound, c.t_angle0, c.u_t_ub, c.u_n_lb, single_quirk};
+    const double* dm; RET(model_on_device(m, device, &dm));
+    TmpBuf tb; const double* ds; double *dv, *da;
+    RET(tb.in(s, cnt, mem, &ds)); RET(tb.out(v_bound, cnt, mem, &dv)); RET(tb.out(t_angle, cnt, mem, &da));
+    k_eval_vbound<<<(cnt + 255) / 256, 256, model_smem_bytes(1)>>>(dm, cnt, ds, cd, dv, da);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    RET(TmpBuf::back(v_bound, dv, cnt, mem)); RET(TmpBuf::back(t_angle, da, cnt, mem));
+    return QSPUSH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ solver
+void qspush_opts_default(qspush_opts* o) {
+    if (!o) return;
+    std::memset(o, 0, sizeof *o);
+    o->mode = QSPUSH_MODE_RTI;
+    o->max_sqp_iter = 30;                                      // NMPC_controller.m:276
+    o->tol_stat = o->tol_eq = o->tol_ineq = o->tol_comp = 1e-6;
+    o->qp_max_iter = 50;
+    o->qp_tol = 1e-8; o->qp_mu0 = 1.0; o->qp_thr = 1e-3; o->qp_tau = 0.995;
+    o->globalization = 1;                                      // merit_backtracking, :272
+    o->alpha_min = 0.05; o->alpha_reduction = 0.7; o->eps_sufficient_descent = 1e-4;
+    o->matlab_single_quirk = 1;
+    o->problems_per_warp = 0;
+}
+
+static size_t al(size_t doubles) { return (doubles + 31) / 32 * 32; }   // 256-byte granules
+
+int qspush_solver_create(const qspush_model* const* models, int nmodels, int N, double dt, int batch,
+                         int device, const qspush_opts* opts, qspush_solver** out) {
+    if (!models || !out || nmodels < 1 || nmodels > MAX_MODELS) return fail(QSPUSH_ERR_ARG, "need 1..8 models");
+    if (N < 1 || N > 4096 || batch < 1 || !(dt > 0.0)) return fail(QSPUSH_ERR_ARG, "bad N / batch / dt");
+    for (int i = 0; i < nmodels; ++i) if (!models[i]) return fail(QSPUSH_ERR_ARG, "NULL model");
+    RET(need_device(device));
+    CK(cudaSetDevice(device));
+    qspush_solver* s = new qspush_solver();
+    s->device = device; s->B = batch; s->Bp = (batch + 31) / 32 * 32; s->N = N; s->nmodels = nmodels; s->dt = dt;
+    if (opts) s->opts = *opts; else qspush_opts_default(&s->opts);
+    qspush_ctrl_default(&s->ctrl);
+    CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (auto& e : s->ev) CK(cudaEventCreate(&e));
+    CK(cudaMallocHost(&s->h_ndone, sizeof(int)));
+    const size_t Bp = (size_t)s->Bp;
+    // rows of every slab
+    struct Slab { double** p; size_t rows; };
+    SolverDev& D = s->dev;
+    std::memset(&D, 0, sizeof D);
+    std::vector<Slab> slabs = {
+        {&D.x, (size_t)(N + 1) * 4}, {&D.u, (size_t)N * 2}, {&D.pi, (size_t)N * 4}, {&D.lam, (size_t)N * 6},
+        {&D.x0, 4}, {&D.yref, (size_t)N * 6}, {&D.yref_e, 4},
+        {&D.A, (size_t)N * 8}, {&D.Bm, (size_t)N * 8}, {&D.b, (size_t)N * 4}, {&D.g, (size_t)N * 6}, {&D.qN, 4}, {&D.dx0, 4},
+        {&D.z, (size_t)(N + 1) * 6}, {&D.zp, (size_t)(N + 1) * 6}, {&D.zc, (size_t)N * 3}, {&D.lamq, (size_t)N * 6}, {&D.t, (size_t)N * 6},
+        {&D.K, (size_t)N * 8}, {&D.Li, (size_t)N * 3}, {&D.Pb, (size_t)N * 4}, {&D.kff, (size_t)N * 2}, {&D.piq, (size_t)N * 4},
+        {&D.rg, (size_t)(N + 1) * 6}, {&D.rb, (size_t)N * 4}, {&D.rgs, (size_t)N},
+        {&D.cost, 1}, {&D.res, 4}, {&D.alpha, 1},
+        {&D.wpi, (size_t)N * 4}, {&D.wlam, (size_t)N * 6}, {&D.wx0, 4},
+    };
+    size_t total = 0;
+    for (auto& sl : slabs) total += al(sl.rows * Bp);
+    const size_t n_const = al((size_t)N * 36) + al(16) + al((size_t)N * 21) + al(10) + al((size_t)nmodels * MODEL_DOUBLES);
+    s->stage_doubles = (size_t)(N + 1) * 6 * Bp;                 // largest AoS field (x: (N+1)*4, lam: N*6)
+    const size_t n_int = 8 * Bp + 32;
+    s->arena_bytes = (total + n_const + al(s->stage_doubles)) * 8 + (n_int + Bp) * sizeof(int) + 1024;
+    CK(cudaMalloc(&s->arena, s->arena_bytes));
+    CK(cudaMemsetAsync(s->arena, 0, s->arena_bytes, s->stream));
+    double* cur = (double*)s->arena;
+    for (auto& sl : slabs) { *sl.p = cur; cur += al(sl.rows * Bp); }
+    s->d_Wdt = cur; cur += al((size_t)N * 36);
+    s->d_We = cur; cur += al(16);
+    s->d_H = cur; cur += al((size_t)N * 21);
+    s->d_QN = cur; cur += al(10);
+    s->d_models = cur; cur += al((size_t)nmodels * MODEL_DOUBLES);
+    s->d_stage = cur; cur += al(s->stage_doubles);
+    int* icur = (int*)cur;
+    int** ints[] = {&D.status, &D.sqp_iter, &D.qp_iter, &D.cold, &D.done, &D.qpstat};
+    for (int** ip : ints) { *ip = icur; icur += Bp; }
+    int* objid = icur; icur += Bp;
+    s->d_istage = icur; icur += Bp;
+    D.ndone = icur; icur += 32;
+    D.objid = objid;
+    D.B = batch; D.Bp = s->Bp; D.N = N; D.nmodels = nmodels; D.dt = dt;
+    D.models = s->d_models; D.Wdt = s->d_Wdt; D.We = s->d_We; D.H = s->d_H; D.QN = s->d_QN;
+    for (int i = 0; i < nmodels; ++i)
+        CK(cudaMemcpyAsync(s->d_models + (size_t)i * MODEL_DOUBLES, models[i]->hm.blob.data(), MODEL_DOUBLES * 8,
+                           cudaMemcpyHostToDevice, s->stream));
+    k_fill_int<<<(s->Bp + 255) / 256, 256, 0, s->stream>>>(D.cold, s->Bp, 1);
+    s->launches++;
+    // defaults of NMPC_controller.m:16-18 and :251-252 (with :23-26, 83-84)
+    s->W.assign((size_t)N * 36, 0.0); s->We.assign(16, 0.0);
+    const double wx[4] = {1.0, 1.0, 1e-3, 0.0}, wu[2] = {1e-3, 1e-3}, we[4] = {2e5, 2e5, 20.0, 0.0};
+    for (int k = 0; k < N; ++k) {
+        for (int i = 0; i < 4; ++i) s->W[(size_t)k * 36 + 7 * i] = wx[i];
+        for (int i = 0; i < 2; ++i) s->W[(size_t)k * 36 + 7 * (4 + i)] = wu[i];
+    }
+    for (int i = 0; i < 4; ++i) s->We[5 * i] = we[i];
+    const double lh[3] = {-0.06, 0.0, -0.05}, uh[3] = {0.011, 0.03, 0.05};
+    for (int i = 0; i < 3; ++i) { D.lh[i] = lh[i]; D.uh[i] = uh[i]; }
+    s->cost_dirty = true;
+    // dynamic shared memory for the model tables
+    const int smem = (int)model_smem_bytes(nmodels);
+    CK(cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_linearise, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_linesearch, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_plant_step, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaStreamSynchronize(s->stream));
+    *out = s;
+    return QSPUSH_OK;
+}
+
+void qspush_solver_free(qspush_solver* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+    if (s->arena) cudaFree(s->arena);
+    if (s->h_ndone) cudaFreeHost(s->h_ndone);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int qspush_solver_set_opts(qspush_solver* s, const qspush_opts* o) {
+    if (!s || !o) return fail(QSPUSH_ERR_ARG, "NULL argument");
+    s->opts = *o; return QSPUSH_OK;
+}
+int qspush_solver_set_ctrl(qspush_solver* s, const qspush_ctrl* c) {
+    if (!s || !c) return fail(QSPUSH_ERR_ARG, "NULL argument");
+    s->ctrl = *c; return QSPUSH_OK;
+}
+}  // extern "C"
+
+// upload dt*W, W_e and the packed z-order Hessians
+static int flush_cost(qspush_solver* s) {
+    if (!s->cost_dirty) return QSPUSH_OK;
+    const int N = s->N;
+    std::vector<double> Wdt((size_t)N * 36), H((size_t)N * 21), QN(10);
+    auto perm = [](int zi) { return zi < 2 ? 4 + zi : zi - 2; };   // z index -> y index
+    for (int k = 0; k < N; ++k) {
+        for (int i = 0; i < 36; ++i) Wdt[(size_t)k * 36 + i] = s->dt * s->W[(size_t)k * 36 + i];
+        for (int i = 0; i < 6; ++i)
+            for (int j = 0; j <= i; ++j) {
+                // symmetrise: the reference passes symmetric W; average guards against round-off asymmetry
+                const double a = s->W[(size_t)k * 36 + perm(i) + 6 * perm(j)], b = s->W[(size_t)k * 36 + perm(j) + 6 * perm(i)];
+                H[(size_t)k * 21 + LT(i, j)] = s->dt * 0.5 * (a + b);
+            }
+    }
+    for (int i = 0; i < 4; ++i) for (int j = 0; j <= i; ++j) QN[LT(i, j)] = 0.5 * (s->We[i + 4 * j] + s->We[j + 4 * i]);
+    CK(cudaMemcpyAsync(s->d_Wdt, Wdt.data(), Wdt.size() * 8, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->d_H, H.data(), H.size() * 8, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->d_QN, QN.data(), QN.size() * 8, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->d_We, s->We.data(), 16 * 8, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));   // the host vectors die here
+    s->cost_dirty = false;
+    return QSPUSH_OK;
+}
+
+struct FieldInfo { double* base; int dim; int nst; bool settable; };
+static bool field_info(qspush_solver* s, qspush_field f, FieldInfo& fi) {
+    SolverDev& D = s->dev; const int N = s->N;
+    switch (f) {
+        case QSPUSH_X0: fi = {D.x0, 4, 1, true}; return true;
+        case QSPUSH_YREF: fi = {D.yref, 6, N, true}; return true;
+        case QSPUSH_YREF_E: fi = {D.yref_e, 4, 1, true}; return true;
+        case QSPUSH_X: fi = {D.x, 4, N + 1, true}; return true;
+        case QSPUSH_U: fi = {D.u, 2, N, true}; return true;
+        case QSPUSH_PI: fi = {D.pi, 4, N, true}; return true;
+        case QSPUSH_LAM: fi = {D.lam, 6, N, true}; return true;
+        case QSPUSH_COST: fi = {D.cost, 1, 1, false}; return true;
+        case QSPUSH_RES: fi = {D.res, 4, 1, false}; return true;
+        default: return false;
+    }
+}
+
+extern "C" {
+
+int qspush_set(qspush_solver* s, qspush_field f, int stage, int lo, int hi, const double* data, qspush_mem mem) {
+    if (!s || !data) return fail(QSPUSH_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(s->device));
+    const int N = s->N;
+    if (f == QSPUSH_W) {
+        if (mem != QSPUSH_MEM_HOST) return fail(QSPUSH_ERR_ARG, "cost_W must be passed from host memory");
+        if (stage == N) std::memcpy(s->We.data(), data, 16 * 8);                       // NMPC_controller.m:154
+        else if (stage >= 0 && stage < N) std::memcpy(&s->W[(size_t)stage * 36], data, 36 * 8);   // :157
+        else if (stage == -1) for (int k = 0; k < N; ++k) std::memcpy(&s->W[(size_t)k * 36], data, 36 * 8);
+        else return fail(QSPUSH_ERR_ARG, "cost_W: stage out of range");
+        s->cost_dirty = true;
+        return QSPUSH_OK;
+    }
+    if (f == QSPUSH_LH || f == QSPUSH_UH) {
+        if (mem != QSPUSH_MEM_HOST) return fail(QSPUSH_ERR_ARG, "bounds must be passed from host memory");
+        for (int i = 0; i < 3; ++i) (f == QSPUSH_LH ? s->dev.lh : s->dev.uh)[i] = data[i];
+        return QSPUSH_OK;
+    }
+    FieldInfo fi;
+    if (!field_info(s, f, fi) || !fi.settable) return fail(QSPUSH_ERR_ARG, "field cannot be set");
+    if (lo < 0 || hi > s->B || lo >= hi) return fail(QSPUSH_ERR_ARG, "batch range out of bounds");
+    if (stage < -1 || stage >= fi.nst) return fail(QSPUSH_ERR_ARG, "stage out of range");
+    const int nb = hi - lo;
+    const int R = (stage < 0) ? fi.nst * fi.dim : fi.dim;
+    const int row0 = (stage < 0) ? 0 : stage * fi.dim;
+    const double* src = data;
+    if (mem == QSPUSH_MEM_HOST) {
+        CK(cudaMemcpyAsync(s->d_stage, data, (size_t)nb * R * 8, cudaMemcpyHostToDevice, s->stream));
+        src = s->d_stage;
+    }
+    dim3 grid((nb + 31) / 32, (R + 31) / 32), block(32, 8);
+    k_aos_to_soa<<<grid, block, 0, s->stream>>>(src, fi.base, nb, R, row0, lo, s->Bp);
+    CK(cudaGetLastError());
+    s->launches++;
+    return QSPUSH_OK;
+}
+
+int qspush_get(qspush_solver* s, qspush_field f, int stage, int lo, int hi, double* out, qspush_mem mem) {
+    if (!s || !out) return fail(QSPUSH_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(s->device));
+    const int N = s->N;
+    if (f == QSPUSH_W) {
+        if (stage == N) std::memcpy(out, s->We.data(), 16 * 8);
+        else if (stage >= 0 && stage < N) std::memcpy(out, &s->W[(size_t)stage * 36], 36 * 8);
+        else return fail(QSPUSH_ERR_ARG, "cost_W: stage out of range");
+        return QSPUSH_OK;
+    }
+    if (f == QSPUSH_LH || f == QSPUSH_UH) { for (int i = 0; i < 3; ++i) out[i] = (f == QSPUSH_LH ? s->dev.lh : s->dev.uh)[i]; return QSPUSH_OK; }
+    FieldInfo fi;
+    if (!field_info(s, f, fi)) return fail(QSPUSH_ERR_ARG, "unknown field");
+    if (lo < 0 || hi > s->B || lo >= hi) return fail(QSPUSH_ERR_ARG, "batch range out of bounds");
+    if (stage < -1 || stage >= fi.nst) return fail(QSPUSH_ERR_ARG, "stage out of range");
+    const int nb = hi - lo;
+    const int R = (stage < 0) ? fi.nst * fi.dim : fi.dim;
+    const int row0 = (stage < 0) ? 0 : stage * fi.dim;
+    double* dst = (mem == QSPUSH_MEM_HOST) ? s->d_stage : out;
+    dim3 grid((nb + 31) / 32, (R + 31) / 32), block(32, 8);
+    k_soa_to_aos<<<grid, block, 0, s->stream>>>(fi.base, dst, nb, R, row0, lo, s->Bp);
+    CK(cudaGetLastError());
+    s->launches++;
+    if (mem == QSPUSH_MEM_HOST) {
+        CK(cudaMemcpyAsync(out, s->d_stage, (size_t)nb * R * 8, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+    }
+    return QSPUSH_OK;
+}
+
+static int* int_field(qspush_solver* s, qspush_field f, bool& settable) {
+    settable = false;
+    switch (f) {
+        case QSPUSH_STATUS: return s->dev.status;
+        case QSPUSH_SQP_ITER: return s->dev.sqp_iter;
+        case QSPUSH_QP_ITER: return s->dev.qp_iter;
+        case QSPUSH_OBJECT_ID: settable = true; return const_cast<int*>(s->dev.objid);
+        case QSPUSH_COLD: settable = true; return s->dev.cold;
+        default: return nullptr;
+    }
+}
+
+int qspush_set_int(qspush_solver* s, qspush_field f, int lo, int hi, const int* data, qspush_mem mem) {
+    if (!s || !data) return fail(QSPUSH_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(s->device));
+    bool settable; int* p = int_field(s, f, settable);
+    if (!p || !settable) return fail(QSPUSH_ERR_ARG, "int field cannot be set");
+    if (lo < 0 || hi > s->B || lo >= hi) return fail(QSPUSH_ERR_ARG, "batch range out of bounds");
+    if (f == QSPUSH_OBJECT_ID && mem == QSPUSH_MEM_HOST)
+        for (int i = 0; i < hi - lo; ++i) if (data[i] < 0 || data[i] >= s->nmodels) return fail(QSPUSH_ERR_ARG, "object id out of range");
+    CK(cudaMemcpyAsync(p + lo, data, (size_t)(hi - lo) * sizeof(int),
+                       mem == QSPUSH_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s->stream));
+    if (mem == QSPUSH_MEM_HOST) CK(cudaStreamSynchronize(s->stream));
+    return QSPUSH_OK;
+}
+int qspush_get_int(qspush_solver* s, qspush_field f, int lo, int hi, int* out, qspush_mem mem) {
+    if (!s || !out) return fail(QSPUSH_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(s->device));
+    bool settable; int* p = int_field(s, f, settable);
+    if (!p) return fail(QSPUSH_ERR_ARG, "unknown int field");
+    if (lo < 0 || hi > s->B || lo >= hi) return fail(QSPUSH_ERR_ARG, "batch range out of bounds");
+    CK(cudaMemcpyAsync(out, p + lo, (size_t)(hi - lo) * sizeof(int),
+                       mem == QSPUSH_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s->stream));
+    if (mem == QSPUSH_MEM_HOST) CK(cudaStreamSynchronize(s->stream));
+    return QSPUSH_OK;
+}
+
+static CtrlDev ctrl_dev(const qspush_solver* s) {
+    return CtrlDev{s->ctrl.v_alpha, s->ctrl.d_v_bound, s->ctrl.t_angle0, s->ctrl.u_t_ub, s->ctrl.u_n_lb, s->opts.matlab_single_quirk};
+}
+
+int qspush_prepare(qspush_solver* s) {
+    if (!s) return fail(QSPUSH_ERR_ARG, "NULL solver");
+    CK(cudaSetDevice(s->device));
+    CK(cudaEventRecord(s->ev[4], s->stream));
+    k_prepare<<<(s->B + 127) / 128, 128, model_smem_bytes(s->nmodels), s->stream>>>(s->dev, ctrl_dev(s));
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(s->ev[5], s->stream));
+    s->launches++;
+    return QSPUSH_OK;
+}
+
+static int pick_ppw(const qspush_solver* s) {
+    int p = s->opts.problems_per_warp;
+    if (p == 32 || p == 16 || p == 8 || p == 4) return p;
+    // auto: keep at least ~4 warps per SM in flight (148 SMs) before packing warps fully
+    if (s->B >= 32 * 148 * 4) return 32;
+    if (s->B >= 16 * 148 * 4) return 16;
+    return 8;
+}
+
+int qspush_solve(qspush_solver* s) {
+    if (!s) return fail(QSPUSH_ERR_ARG, "NULL solver");
+    CK(cudaSetDevice(s->device));
+    RET(flush_cost(s));
+    const qspush_opts& o = s->opts;
+    IpmOpts io{o.qp_max_iter, o.qp_tol, o.qp_mu0, o.qp_thr, o.qp_tau};
+    const int ppw = pick_ppw(s);
+    const size_t smem = model_smem_bytes(s->nmodels);
+    const size_t nlin = (size_t)(s->N + 1) * s->Bp;
+    const unsigned lin_blocks = (unsigned)((nlin + 127) / 128);
+    const unsigned qp_blocks = (unsigned)((s->B + ppw - 1) / ppw);
+    CK(cudaEventRecord(s->ev[0], s->stream));
+    if (o.mode == QSPUSH_MODE_RTI) {
+        SolverDev D = s->dev; D.done = nullptr;
+        k_linearise<<<lin_blocks, 128, smem, s->stream>>>(D);
+        CK(cudaEventRecord(s->ev[1], s->stream));
+        k_qp<<<qp_blocks, 32, 0, s->stream>>>(D, io, ppw, 1);
+        CK(cudaEventRecord(s->ev[2], s->stream));
+        CK(cudaGetLastError());
+        s->launches += 2;
+        CK(cudaEventRecord(s->ev[3], s->stream));
+        return QSPUSH_OK;
+    }
+    // ---- full SQP (NMPC_controller.m:271-276): host-driven loop, per-problem convergence on the device
+    SqpOpts so{o.max_sqp_iter, {o.tol_stat, o.tol_eq, o.tol_ineq, o.tol_comp}, o.globalization, o.alpha_min, o.alpha_reduction, o.eps_sufficient_descent};
+    SolverDev D = s->dev;
+    CK(cudaMemsetAsync(D.done, 0, s->Bp * sizeof(int), s->stream));
+    CK(cudaMemsetAsync(D.qp_iter, 0, s->Bp * sizeof(int), s->stream));
+    CK(cudaMemsetAsync(D.ndone, 0, sizeof(int), s->stream));
+    const unsigned pb = (unsigned)((s->B + 63) / 64);
+    for (int it = 0; it <= o.max_sqp_iter; ++it) {
+        k_linearise<<<lin_blocks, 128, smem, s->stream>>>(D);
+        k_nlp_res<<<pb, 64, 0, s->stream>>>(D, so, it);
+        s->launches += 2;
+        CK(cudaMemcpyAsync(s->h_ndone, D.ndone, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        if (*s->h_ndone >= s->B || it == o.max_sqp_iter) break;
+        k_qp<<<qp_blocks, 32, 0, s->stream>>>(D, io, ppw, 0);
+        k_linesearch<<<pb, 64, smem, s->stream>>>(D, so, it);
+        s->launches += 2;
+    }
+    CK(cudaEventRecord(s->ev[1], s->stream));
+    CK(cudaEventRecord(s->ev[2], s->stream));
+    k_cost<<<(s->B + 127) / 128, 128, 0, s->stream>>>(D);
+    CK(cudaGetLastError());
+    s->launches++;
+    CK(cudaEventRecord(s->ev[3], s->stream));
+    return QSPUSH_OK;
+}
+
+int qspush_shift(qspush_solver* s) {
+    if (!s) return fail(QSPUSH_ERR_ARG, "NULL solver");
+    CK(cudaSetDevice(s->device));
+    dim3 grid((s->B + 127) / 128, 16);
+    k_shift<<<grid, 128, 0, s->stream>>>(s->dev);
+    CK(cudaGetLastError());
+    s->launches++;
+    return QSPUSH_OK;
+}
+
+int qspush_plant_step(qspush_solver* s, double* x, const double* u, qspush_mem mem) {
+    if (!s || !x || !u) return fail(QSPUSH_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(s->device));
+    double* dx = x; const double* du = u;
+    if (mem == QSPUSH_MEM_HOST) {
+        dx = s->d_stage; du = s->d_stage + (size_t)4 * s->Bp;
+        CK(cudaMemcpyAsync(dx, x, (size_t)s->B * 4 * 8, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync((void*)du, u, (size_t)s->B * 2 * 8, cudaMemcpyHostToDevice, s->stream));
+    }
+    k_plant_step<<<(s->B + 127) / 128, 128, model_smem_bytes(s->nmodels), s->stream>>>(s->dev, dx, du);
+    CK(cudaGetLastError());
+    s->launches++;
+    if (mem == QSPUSH_MEM_HOST) {
+        CK(cudaMemcpyAsync(x, dx, (size_t)s->B * 4 * 8, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+    }
+    return QSPUSH_OK;
+}
+
+int qspush_sync(qspush_solver* s) {
+    if (!s) return fail(QSPUSH_ERR_ARG, "NULL solver");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    return QSPUSH_OK;
+}
+void* qspush_stream(qspush_solver* s) { return s ? (void*)s->stream : nullptr; }
+
+int qspush_get_stat(qspush_solver* s, qspush_stat which, double* out) {
+    if (!s || !out) return fail(QSPUSH_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    float ms = 0.f;
+    cudaError_t e = cudaSuccess;
+    switch (which) {
+        case QSPUSH_TIME_TOT: e = cudaEventElapsedTime(&ms, s->ev[0], s->ev[3]); break;
+        case QSPUSH_TIME_LIN: e = cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]); break;
+        case QSPUSH_TIME_QP: e = cudaEventElapsedTime(&ms, s->ev[1], s->ev[2]); break;
+        case QSPUSH_TIME_PREP: e = cudaEventElapsedTime(&ms, s->ev[4], s->ev[5]); break;
+        default: return fail(QSPUSH_ERR_ARG, "unknown stat");
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); ms = 0.f; }   // events not recorded yet
+    *out = (double)ms * 1e-3;
+    return QSPUSH_OK;
+}
+long long qspush_launch_count(const qspush_solver* s) { return s ? s->launches : 0; }
+
+}  // extern "C"
