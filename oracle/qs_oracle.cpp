@@ -511,7 +511,8 @@ static void qp_solve_ipm(const QP& qp, const OcpOpts& o, QPSol& sol) {
     std::vector<double> dz, dxN, dpi, dlam(nc), dt_(nc), dz2, dxN2, dpi2;
     RiccatiFactor F;
     sol.status = 1;
-    int it = 0;
+    int it = 0, stall = 0;
+    double rmax_prev = 1e300;
     for (;; ++it) {
         // ---- residuals
         for (int k = 0; k < N; ++k) {
@@ -557,6 +558,11 @@ static void qp_solve_ipm(const QP& qp, const OcpOpts& o, QPSol& sol) {
         sol.res[0] = r_stat; sol.res[1] = r_eq; sol.res[2] = r_in; sol.res[3] = r_cp;
         if (!(r_stat == r_stat) || !(r_eq == r_eq) || !(mu == mu)) { sol.status = 2; break; }
         if (r_stat < o.qp_tol && r_eq < o.qp_tol && r_in < o.qp_tol && r_cp < o.qp_tol) { sol.status = 0; break; }
+        {   // stall exit (weakly active pairs): residuals stopped moving below the reference's QP tolerance 1e-6
+            const double rmax = std::max(std::max(r_stat, r_eq), std::max(r_in, r_cp));
+            if (rmax < 0.5 * rmax_prev) { rmax_prev = rmax; stall = 0; } else ++stall;   // rmax_prev = best so far
+            if (stall >= 5 && rmax < 1e-6) { sol.status = 0; break; }
+        }
         if (it >= o.qp_max_iter) { sol.status = 1; break; }
         // ---- factorise with barrier diagonal
         std::fill(Hb.begin(), Hb.end(), 0.0);
@@ -597,7 +603,8 @@ static void qp_solve_ipm(const QP& qp, const OcpOpts& o, QPSol& sol) {
         mu_aff = m_on ? mu_aff / m_on : 0.0;
         double sigma = (mu > 0.0) ? (mu_aff / mu) : 0.0; sigma = sigma * sigma * sigma;
         // ---- corrector
-        for (size_t i = 0; i < nc; ++i) rm[i] = on[i] ? (lam[i] * t[i] + dlam[i] * dt_[i] - sigma * mu) : 0.0;
+        const double smu = std::max(sigma * mu, 0.1 * o.qp_tol);   // centering target floor (keeps lam/t bounded at the end)
+        for (size_t i = 0; i < nc; ++i) rm[i] = on[i] ? (lam[i] * t[i] + dlam[i] * dt_[i] - smu) : 0.0;
         solve_with(rm, dz, dxN, dpi);
         double alpha = std::min(1.0, o.qp_tau * max_step());
         if (m_on == 0) alpha = 1.0;

@@ -108,7 +108,7 @@ struct OcpOpts {
     int    max_sqp_iter = 30;          // NMPC_controller.m:276
     double tol_stat = 1e-6, tol_eq = 1e-6, tol_ineq = 1e-6, tol_comp = 1e-6;  // :276
     int    qp_max_iter = 50;           // acados default qp_solver_iter_max
-    double qp_tol = 1e-8;              // QP residual tolerance (all four)
+    double qp_tol = 1e-12;              // QP residual tolerance (all four)
     double qp_mu0 = 1.0;               // initial barrier parameter
     double qp_thr = 1e-3;              // lower clamp on initial slacks
     double qp_tau = 0.995;             // fraction to the boundary

@@ -1,0 +1,220 @@
+"""GPU parity (through the C-ABI) of the batched OCP solver: prepare (K6), linearise (K2+K3), QP (K4), RTI step
+(K5), full SQP, shift, plant step, the acados_ocp / NMPC_controller mirror and the closed loop, vs the CPU
+oracle and the golden fixtures; plus size-independent properties at BASELINE.json's config-3 size."""
+import os
+
+import numpy as np
+import pytest
+
+import uclv_qs_pushing_matlab_b200 as q
+from oracle import oracle as orc
+from tests.test_hostsim_parity import REL, rel_err
+from tests.workloads import OBJECT_ORDER, make_rti_workload, packaged_model_pair, gpu_model, oracle_model
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(s, wl, cold=0):
+    B = wl["x0"].shape[0]
+    s.set("x0", wl["x0"]); s.set("yref", wl["yref"]); s.set("yref_e", wl["yref_e"]); s.set("u", wl["u_init"])
+    s.set_int("cold", np.full(B, cold, dtype=np.int32))
+    if "object_id" in wl:
+        s.set_int("object_id", wl["object_id"])
+
+
+def _oracle_prepared(om, wl, N, **opts):
+    B = wl["x0"].shape[0]
+    ocp = orc.Ocp(om, N, 0.05, **opts)
+    return ocp, ocp.prepare(wl["x0"], np.zeros(B, dtype=np.int32), np.zeros((B, N + 1, 4)), wl["u_init"])
+
+
+def test_set_get_roundtrip_and_errors():
+    gm = gpu_model("santal")
+    B, N = 37, 7                                                  # ragged: batch not a multiple of 32
+    s = q.Solver([gm], N, 0.05, B)
+    rng = np.random.default_rng(0)
+    for f, dim, nst in (("x", 4, N + 1), ("u", 2, N), ("pi", 4, N), ("lam", 6, N), ("yref", 6, N)):
+        a = rng.standard_normal((B, nst, dim))
+        s.set(f, a)
+        assert np.array_equal(s.get(f), a)
+        b = rng.standard_normal((5, dim))
+        s.set(f, b, stage=nst - 1, lo=3, hi=8)                     # one stage of a batch slice
+        a[3:8, nst - 1] = b
+        assert np.array_equal(s.get(f), a) and np.array_equal(s.get(f, stage=nst - 1, lo=3, hi=8), b)
+    for f in ("x0", "yref_e"):
+        a = rng.standard_normal((B, 4)); s.set(f, a); assert np.array_equal(s.get(f), a)
+    ids = np.zeros(B, dtype=np.int32); s.set_int("object_id", ids); assert np.array_equal(s.get_int("object_id"), ids)
+    W = np.diag([2.0, 3, 4, 5, 6, 7]); s.set("W", W, stage=2)
+    out = np.zeros(36); q._lib.check(q._lib.lib().qspush_get(s._h, q._lib.W, 2, 0, 0, out.ctypes.data, 0)); assert np.array_equal(out.reshape(6, 6), W)
+    with pytest.raises(q.QspushError):
+        s.set("x0", np.zeros((B, 4)), lo=0, hi=B + 1)              # batch range out of bounds
+    with pytest.raises(q.QspushError):
+        s.set("u", np.zeros((B, 2)), stage=N)                      # stage out of range
+    with pytest.raises(q.QspushError):
+        s.set("cost", np.zeros(B))                                # read-only field
+    with pytest.raises(q.QspushError):
+        s.set_int("object_id", np.full(B, 3, dtype=np.int32))      # only one model registered
+    with pytest.raises(q.QspushError):
+        q.Solver([gm], 0, 0.05, 4)
+    import torch
+    t = torch.randn(B, N, 2, dtype=torch.float64, device="cuda:0")
+    s.set("u", t); out = torch.empty_like(t); s.get("u", out=out); s.sync()
+    assert torch.equal(out, t)                                    # device-pointer path, no host copies
+
+
+@pytest.mark.parametrize("name,N", [("santal", 40), ("montana", 10), ("balea", 100)])
+def test_prepare_qp_rti_vs_oracle(name, N):
+    gm, om = packaged_model_pair(name)
+    B = 256
+    wl = make_rti_workload(None, batch=B, N=N, seed=2)
+    ocp, pr = _oracle_prepared(om, wl, N)
+    s = q.Solver([gm], N, 0.05, B)
+    _load(s, wl); s.prepare()
+    assert np.array_equal(s.get("x0"), pr["x0"])
+    assert rel_err(s.get("x"), pr["x"]) < REL and rel_err(s.get("u"), pr["u"]) < REL
+    s.solve()
+    ro = ocp.solve("rti", pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"], nthreads=8)
+    u, x, pi, lam = s.get("u"), s.get("x"), s.get("pi"), s.get("lam")
+    it = s.get_int("qp_iter")
+    assert (s.get_int("status") == 0).all() and (s.get_int("sqp_iter") == 1).all()
+    assert np.abs(it - ro["qp_iter"]).max() <= 1 and (it == ro["qp_iter"]).mean() > 0.8
+    same = it == ro["qp_iter"]
+    u0err = np.abs(u[:, 0] - ro["u"][:, 0]).max(1)
+    assert u0err[same].max() < 1e-6 and (u0err < 1e-6).mean() >= 0.95 and u0err.max() < 2e-5     # north_star: u0 within 1e-6
+    assert np.abs(u[same] - ro["u"][same]).max() < 1e-6 and np.abs(x[same] - ro["x"][same]).max() < 1e-6
+    assert np.abs(u - ro["u"]).max() < 2e-5 and np.abs(x - ro["x"]).max() < 2e-5                 # FP64 conditioning floor, DESIGN.md
+    assert rel_err(pi[same], ro["pi"][same]) < 1e-5 and np.abs(lam[same] - ro["lam"][same]).max() < 1e-5 * max(1.0, np.abs(ro["lam"]).max())
+    assert rel_err(s.get("cost"), ro["cost"]) < 1e-8
+    assert s.get("res").max() < 1e-11                             # true KKT residuals of every returned QP point
+    assert s.stat("time_tot") > 0 and s.stat("time_qp_sol") > 0 and s.launches > 0
+
+
+def test_rti_vs_golden_fixture():
+    g = np.load(os.path.join(GOLD, "rti_santal_N40.npz"))
+    gm = gpu_model("santal")
+    B, N = g["x0"].shape[0], 40
+    s = q.Solver([gm], N, 0.05, B)
+    _load(s, {k: g[k] for k in ("x0", "yref", "yref_e", "u_init")}); s.prepare()
+    assert np.array_equal(s.get("x0"), g["x0_wrapped"]) and rel_err(s.get("x"), g["x_prep"]) < REL
+    s.solve()
+    assert np.abs(s.get("u") - g["u"]).max() < 1e-6 and np.abs(s.get("x") - g["x"]).max() < 1e-6
+    assert rel_err(s.get("cost"), g["cost"]) < 1e-8
+
+
+def test_multi_object_batch_shift_and_warm_start():
+    names = list(OBJECT_ORDER)
+    gms, oms = [gpu_model(n) for n in names], [oracle_model(n) for n in names]
+    B, N = 128, 20
+    wl = make_rti_workload(None, batch=B, N=N, seed=3, n_objects=4)
+    s = q.Solver(gms, N, 0.05, B)
+    _load(s, wl); s.prepare(); s.solve(); s.shift()
+    u, x, pi = s.get("u"), s.get("x"), s.get("pi")
+    s.prepare(); s.solve()                                       # second RTI iteration from the shifted warm start
+    u2 = s.get("u")
+    for o in range(4):
+        idx = np.where(wl["object_id"] == o)[0]
+        sub = {k: v[idx] for k, v in wl.items()}
+        ocp, pr = _oracle_prepared(oms[o], sub, N)
+        ro = ocp.solve("rti", pr["x0"], sub["yref"], sub["yref_e"], pr["x"], pr["u"], nthreads=4)
+        sh = ocp.shift(ro["x"], ro["u"], ro["pi"], ro["lam"])
+        assert np.abs(u[idx] - sh["u"]).max() < 1e-5 and np.abs(x[idx] - sh["x"]).max() < 1e-5 and (np.abs(u[idx] - sh["u"]).max(axis=(1, 2)) < 1e-6).mean() > 0.9
+        pr2 = ocp.prepare(pr["x0"], np.zeros(len(idx), dtype=np.int32), sh["x"], sh["u"], sh["pi"], sh["lam"])
+        r2 = ocp.solve("rti", pr2["x0"], sub["yref"], sub["yref_e"], pr2["x"], pr2["u"], pr2["pi"], pr2["lam"], nthreads=4)
+        assert (np.abs(u2[idx] - r2["u"]).max(axis=(1, 2)) < 1e-5).mean() > 0.9
+
+
+def test_cold_start_and_plant_step():
+    gm, om = packaged_model_pair("santal")
+    B, N = 64, 10
+    wl = make_rti_workload(None, batch=B, N=N, seed=5)
+    s = q.Solver([gm], N, 0.05, B)
+    wl2 = dict(wl); wl2["u_init"] = np.full((B, N, 2), 9.9)         # must be ignored by a cold start
+    _load(s, wl2, cold=1); s.prepare()
+    assert (s.get_int("cold") == 0).all() and np.all(s.get("u") == 0) and np.allclose(s.get("x"), s.get("x0")[:, None, :])
+    s.solve()
+    ocp = orc.Ocp(om, N, 0.05)
+    pr = ocp.prepare(wl["x0"], np.ones(B, dtype=np.int32), np.zeros((B, N + 1, 4)), np.zeros((B, N, 2)))
+    ro = ocp.solve("rti", pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"])
+    assert np.abs(s.get("u") - ro["u"]).max() < 1e-6
+    x = wl["x0"].copy(); u = s.get("u", stage=0)
+    xn = s.plant_step(x.copy(), u)
+    assert rel_err(xn, x + 0.05 * om.dynamics(x, u)) < REL          # helper.m:294,307
+
+
+def test_full_sqp_vs_oracle_and_golden():
+    gm, om = packaged_model_pair("santal")
+    B, N = 16, 10
+    wl = make_rti_workload(None, batch=B, N=N, seed=4)
+    for iters in (1, 3):
+        ocp, pr = _oracle_prepared(om, wl, N, max_sqp_iter=iters)
+        so = ocp.solve("sqp", pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"])
+        s = q.Solver([gm], N, 0.05, B, mode=1, max_sqp_iter=iters)
+        _load(s, wl); s.prepare(); s.solve()
+        assert np.array_equal(s.get_int("status"), so["status"]) and np.array_equal(s.get_int("sqp_iter"), so["sqp_iter"])
+        assert np.abs(s.get("u") - so["u"]).max() < 1e-6 and np.abs(s.get("x") - so["x"]).max() < 1e-6
+        assert rel_err(s.get("cost"), so["cost"]) < 1e-8 and rel_err(s.get("res"), so["res"]) < 1e-4
+    g = np.load(os.path.join(GOLD, "sqp_santal_N10.npz"))
+    s = q.Solver([gm], N, 0.05, g["x0"].shape[0], mode=1)
+    _load(s, {k: g[k] for k in ("x0", "yref", "yref_e", "u_init")}); s.prepare(); s.solve()
+    st = s.get_int("status")
+    conv = (st == 0) & (g["status"] == 0)
+    assert conv.sum() >= 1 and (st == g["status"]).mean() >= 0.75
+    assert np.abs(s.get("u")[conv] - g["u"][conv]).max() < 1e-5
+
+
+def test_config3_full_size_properties():
+    """4096 instances, N = 40, santal (BASELINE config 3): properties that do not need the oracle at full size,
+    plus the oracle on a strided subset."""
+    gm, om = packaged_model_pair("santal")
+    B, N = 4096, 40
+    wl = make_rti_workload(None, batch=B, N=N, seed=2)
+    s = q.Solver([gm], N, 0.05, B)
+    _load(s, wl); s.prepare(); s.solve()
+    st, it, res, u, x = s.get_int("status"), s.get_int("qp_iter"), s.get("res"), s.get("u"), s.get("x")
+    assert (st == 0).all() and it.max() <= 30 and 8 < it.mean() < 16
+    assert res.max() < 1e-11                                       # KKT certificate of all 4096 QPs
+    assert u[:, :, 0].min() > -1e-9 and u[:, :, 0].max() < 0.03 + 1e-9 and np.abs(u[:, :, 1]).max() < 0.05 + 1e-9
+    assert x[:, 1:, 3].min() > -0.06 - 1e-9 and x[:, 1:, 3].max() < 0.011 + 1e-9
+    assert np.array_equal(x[:, 0], s.get("x0"))                     # x_0 + dx_0 = x0bar exactly
+    idx = np.arange(0, B, 64)
+    sub = {k: v[idx] for k, v in wl.items()}
+    ocp, pr = _oracle_prepared(om, sub, N)
+    ro = ocp.solve("rti", pr["x0"], sub["yref"], sub["yref_e"], pr["x"], pr["u"], nthreads=8)
+    e = np.abs(u[idx][:, 0] - ro["u"][:, 0]).max(1)
+    assert (e < 1e-6).mean() >= 0.95 and e.max() < 2e-5
+
+
+def test_nmpc_controller_closed_loop_config1():
+    """main.m acceptance (config 1) through the MATLAB-shaped mirror: santal, x0 = 0, Hp = 10, dt = 0.05,
+    straight-line reference; RTI mode is compared step by step with the oracle closed loop."""
+    sel = q.object_selection("santal")
+    p = q.PusherSliderModel("real_plant", sel, 0, sel.cad_model_path, 3, sel.pcl_path, "santal")
+    p.symbolic_model_variable_shape()
+    steps, Hp, dt = 40, 10, 0.05
+    T = 201
+    t = np.arange(T) * dt
+    traj = np.zeros((6, T)); traj[0] = np.minimum(0.01 * t, 0.10)
+    om = oracle_model("santal")
+    for nlp in ("sqp_rti", "sqp"):
+        c = q.NMPC_controller("NMPC", p, dt, Hp, nlp_solver=nlp)
+        c.create_ocp_solver()
+        c.set_delay_comp(0.0)
+        c.initial_condition_update(np.zeros(4))
+        c.update_cost_function(0.01 * np.diag([100, 100, 0.1, 0]), np.diag([1e-3, 1e-3]), 200 * np.diag([1000, 1000, 0.1, 0]), 0, Hp - 1)
+        c.set_reference_trajectory(traj)
+        out = q.helper.closed_loop_matlab(p, c, np.zeros(4), (steps - 1) * dt)
+        x_s, u_n, u_t, found = out[0], out[6], out[7], out[10]
+        cl = orc.Ocp(om, Hp, dt).closed_loop("rti" if nlp == "sqp_rti" else "sqp", np.zeros(4), traj.T, steps)
+        assert abs(x_s[-1] - 0.01 * (steps - 1) * dt) < 2e-3          # the slider tracks the 0.01 m/s reference
+        if nlp == "sqp_rti":
+            assert found.all()
+            assert np.abs(np.stack([u_n, u_t], 1) - cl["u"]).max() < 1e-5 and np.abs(x_s - cl["x"][:-1, 0]).max() < 1e-6
+        else:
+            assert (found == (cl["status"] == 0)).mean() > 0.7
+    vb, ta = c.update_tangential_velocity_bounds(-0.01)
+    vo = om.v_bound(-0.01)
+    assert abs(vb - vo[0]) < 1e-12 and abs(ta - vo[1]) < 1e-9
+    assert abs(p.SP.getMaxCurvature() - om.get_curvatures(np.arange(0, om.b + 1e-12, 0.001)).max()) < 1e-6
+    assert rel_err(p.SP.evalSpline(p.SP.FC, [-0.01, 0.3]), om.eval_spline([-0.01, 0.3], wrap=1)["C"]) < REL
+    assert rel_err(p.evalModelVariableShape(np.array([0, 0, 0.1, -0.01]), np.array([0.01, 0.002])), om.dynamics([[0, 0, 0.1, -0.01]], [[0.01, 0.002]])[0]) < REL
