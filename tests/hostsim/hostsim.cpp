@@ -6,6 +6,7 @@
 // (`pytest -m "not gpu"`).  It is never part of the product: libqspush.so does not contain it and
 // the package never loads it.
 #include <algorithm>
+#include <cstdint>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -16,6 +17,138 @@
 using namespace qs;
 
 static std::string g_err;
+
+
+// ------------------------------------------------------------------------------------------------
+// Warp emulator: the 32 lanes of a warp run as cooperative fibers (hand-rolled x86-64 context switch);
+// every warp collective (shfl, reductions) is a yield point, values are exchanged through a
+// double-buffered array — the lanes advance in lockstep exactly like *_sync collectives demand.
+// ------------------------------------------------------------------------------------------------
+#if !defined(__x86_64__)
+#error "the hostsim warp emulator needs x86-64"
+#endif
+extern "C" void qs_ctx_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.globl qs_ctx_switch
+.type qs_ctx_switch,@function
+qs_ctx_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size qs_ctx_switch, .-qs_ctx_switch
+)");
+
+struct WarpEmu {
+    static constexpr int W = 32;
+    static constexpr size_t STACK = 512 * 1024;
+    double xbuf[2][W];
+    int count[W];
+    void* sp[W];
+    void* main_sp = nullptr;
+    bool done[W];
+    int cur = 0;
+    std::vector<char> stacks;
+    void (*body)(int lane, void* arg) = nullptr;
+    void* arg = nullptr;
+};
+static thread_local WarpEmu* g_emu = nullptr;
+
+static void emu_fiber_entry() {
+    WarpEmu* e = g_emu;
+    const int lane = e->cur;
+    e->body(lane, e->arg);
+    e->done[lane] = true;
+    qs_ctx_switch(&e->sp[lane], e->main_sp);     // never resumed
+    __builtin_trap();
+}
+
+static void emu_run(void (*body)(int, void*), void* arg) {
+    WarpEmu e;
+    e.body = body; e.arg = arg;
+    e.stacks.assign(WarpEmu::W * WarpEmu::STACK, 0);
+    for (int l = 0; l < WarpEmu::W; ++l) {
+        e.done[l] = false; e.count[l] = 0;
+        char* top = e.stacks.data() + (size_t)(l + 1) * WarpEmu::STACK;
+        top = (char*)((uintptr_t)top & ~(uintptr_t)15);
+        void** p = (void**)top;
+        *(--p) = nullptr;                          // fake return address of the entry function
+        *(--p) = (void*)&emu_fiber_entry;          // `ret` target of the first switch
+        for (int i = 0; i < 6; ++i) *(--p) = nullptr;   // rbp rbx r12 r13 r14 r15
+        e.sp[l] = p;
+    }
+    g_emu = &e;
+    for (;;) {
+        bool any = false;
+        for (int l = 0; l < WarpEmu::W; ++l) {
+            if (e.done[l]) continue;
+            any = true; e.cur = l;
+            qs_ctx_switch(&e.main_sp, e.sp[l]);
+        }
+        if (!any) break;
+    }
+    g_emu = nullptr;
+}
+
+struct WarpCtxHost {
+    int lane_;
+    int lane() const { return lane_; }
+    // deposit v, yield until every lane has deposited, return the buffer of this collective
+    const double* exchange(double v) const {
+        WarpEmu* e = g_emu;
+        const int p = e->count[lane_] & 1;
+        e->xbuf[p][lane_] = v;
+        e->count[lane_]++;
+        qs_ctx_switch(&e->sp[lane_], e->main_sp);
+        return e->xbuf[p];
+    }
+    double shfl(double v, int src) const { return exchange(v)[src & 31]; }
+    template <class F> double butterfly(double v, F f) const {
+        const double* b = exchange(v);
+        double t[32], u[32];
+        for (int i = 0; i < 32; ++i) t[i] = b[i];
+        for (int o = 16; o > 0; o >>= 1) { for (int i = 0; i < 32; ++i) u[i] = f(t[i], t[i ^ o]); for (int i = 0; i < 32; ++i) t[i] = u[i]; }
+        return t[lane_];
+    }
+    double wmax(double v) const { return butterfly(v, [](double a, double b) { return fmax(a, b); }); }
+    double wmin(double v) const { return butterfly(v, [](double a, double b) { return fmin(a, b); }); }
+    double wsum(double v) const { return butterfly(v, [](double a, double b) { return a + b; }); }
+    int wany(int p) const { const double* b = exchange(p ? 1.0 : 0.0); for (int i = 0; i < 32; ++i) if (b[i] != 0.0) return 1; return 0; }
+    void sync() const { exchange(0.0); }
+    bool cta_all(bool pred) const { return pred; }      // one emulated warp per CTA
+};
+
+struct WarpJob { const SolverDev* S; const IpmOpts* io; int b; int apply; double* sm; int C; };
+static void warp_job_body(int lane, void* arg) {
+    WarpJob* j = (WarpJob*)arg;
+    WarpCtxHost w{lane};
+    switch (j->C) {
+        case 1: qp_one_warp<WarpCtxHost, 1>(w, j->sm, *j->S, *j->io, j->b, j->apply); break;
+        case 2: qp_one_warp<WarpCtxHost, 2>(w, j->sm, *j->S, *j->io, j->b, j->apply); break;
+        case 3: qp_one_warp<WarpCtxHost, 3>(w, j->sm, *j->S, *j->io, j->b, j->apply); break;
+        default: qp_one_warp<WarpCtxHost, 4>(w, j->sm, *j->S, *j->io, j->b, j->apply); break;
+    }
+}
+// mirrors k_qp_warp: one emulated warp per problem
+static void qp_warp_host(const SolverDev& S, const IpmOpts& io, int b, int apply) {
+    std::vector<double> sm(qp_warp_smem_doubles(S.N), 0.0);
+    WarpJob j{&S, &io, b, apply, sm.data(), qp_warp_chunk(S.N)};
+    emu_run(warp_job_body, &j);
+}
+
+// test hook: suffix scan of stage elements vs nothing else — returns P_k of every stage from the scan path
 
 extern "C" {
 
@@ -102,7 +235,7 @@ void hs_eval_vbound(void* m_, int cnt, const double* s, const double* ctrl5, int
 
 // Whole solver pipeline in kernel order on host slabs.
 //   opts_d: [qp_tol, qp_mu0, qp_thr, qp_tau, tol_stat, tol_eq, tol_ineq, tol_comp, alpha_min, alpha_red, eps_sd]
-//   opts_i: [mode(0 rti,1 sqp,2 qp-only), qp_max_iter, max_sqp_iter, globalization, single_quirk, do_prepare, do_shift]
+//   opts_i: [mode(0 rti,1 sqp,2 qp-only), qp_max_iter, max_sqp_iter, globalization, single_quirk, do_prepare, do_shift, qp_kernel(0 thread,1 warp)]
 //   ctrl5 : [v_alpha, d_v_bound, t_angle0, u_t_ub, u_n_lb]
 // AoS in/out: x0 [nb][4] (in/out: wrapped by prepare), yref [nb][N][6], yref_e [nb][4], x [nb][N+1][4], u [nb][N][2],
 //             pi [nb][N][4], lam [nb][N][6], cold [nb]
@@ -162,14 +295,14 @@ int hs_solve(void* const* models, int nmodels, int N, double dt, int nb, const i
     auto linearise_all = [&]() { for (int k = 0; k <= N; ++k) for (int b = 0; b < nb; ++b) if (!S.done[b]) linearise_one(S, Mall, k, b); };
     if (mode == 0 || mode == 2) {
         linearise_all();
-        for (int b = 0; b < nb; ++b) qp_one(S, io, b, mode == 0 ? 1 : 0);
+        for (int b = 0; b < nb; ++b) { if (opts_i[7] && qp_warp_chunk(N) <= 4) qp_warp_host(S, io, b, mode == 0 ? 1 : 0); else qp_one(S, io, b, mode == 0 ? 1 : 0); }
     } else {
         for (int it = 0; it <= so.max_iter; ++it) {
             linearise_all();
             int nd = 0;
             for (int b = 0; b < nb; ++b) { if (!S.done[b]) nlp_res_one(S, so, it, b); nd += S.done[b]; }
             if (nd >= nb || it == so.max_iter) break;
-            for (int b = 0; b < nb; ++b) if (!S.done[b]) qp_one(S, io, b, 0);
+            for (int b = 0; b < nb; ++b) if (!S.done[b]) { if (opts_i[7] && qp_warp_chunk(N) <= 4) qp_warp_host(S, io, b, 0); else qp_one(S, io, b, 0); }
             for (int b = 0; b < nb; ++b) if (!S.done[b]) linesearch_one(S, so, Mall, it, b);
         }
         for (int b = 0; b < nb; ++b) cost_one(S, b);

@@ -11,9 +11,9 @@ from tests.workloads import gpu_model
 gm = gpu_model("santal")
 dev = torch.device("cuda:0")
 
-def time_rti(B, N, ppw, tol, reps=5):
+def time_rti(B, N, ppw, tol, reps=5, **kw):
     wl = make_rti_workload(B, N, seed=2)
-    s = q.Solver([gm], N, 0.05, B, qp_tol=tol, problems_per_warp=ppw)
+    s = q.Solver([gm], N, 0.05, B, qp_tol=tol, problems_per_warp=ppw, **kw)
     x0 = torch.from_numpy(wl["x0"]).to(dev); yr = torch.from_numpy(wl["yref"]).to(dev); ye = torch.from_numpy(wl["yref_e"]).to(dev)
     ui = torch.from_numpy(wl["u_init"]).to(dev); cold = torch.zeros(B, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()

@@ -1,0 +1,801 @@
+// qs_qp_warp.cuh — K4, second generation: one WARP per problem, parallel in time.
+//
+// Same QP and the same Mehrotra predictor-corrector IPM in Newton-step form as qs_qp.cuh (true residuals
+// every iteration, centering floor, stall exit), but the horizon is spread over the 32 lanes of a warp:
+// lane l owns the C consecutive stages l*C .. l*C+C-1 (C = ceil((N+1)/32)); the whole IPM state of the
+// problem lives in shared memory (no HBM traffic inside the iteration loop) and every "sweep" of the
+// serial algorithm becomes either lane-local work or a warp scan built from shuffles:
+//
+//   * Riccati matrices P_k: suffix scan of conditional value functions V_{i->j}(x_i, x_j), each an element
+//     (A, C, J) with  V = max_lam 1/2 x'Jx - 1/2 lam'C lam + lam'(x_j - A x_i)  [vector parts omitted]
+//     (Sarkka & Garcia-Fernandez, "Temporal parallelization of dynamic programming and LQ control").
+//     The combination is evaluated in a symmetric, Cholesky-based form that keeps C and J positive
+//     semi-definite by construction:  J2 = L2 L2',  T = C1 L2,  W = I + L2' T = Lw Lw',
+//     Z = Lw^-1 L2' A1,  Y = Lw^-1 T'   =>   A = A2 (A1 - Y'Z),  C = A2 (C1 - Y'Y) A2' + C2,  J = Z'Z + J1.
+//   * with P at the right boundary of its chunk, each lane runs the ordinary Riccati stage (qs_qp.cuh)
+//     over its own C stages: gains K_k, Cholesky factors, P_k;
+//   * the vector recursions p_k = Abar_k' p_{k+1} + d_k (backward) and dx_{k+1} = Abar_k dx_k + bbar_k
+//     (forward), Abar = A - B K, are suffix / prefix scans of affine maps — twice per iteration
+//     (predictor and corrector share the matrix scan);
+//   * residual norms, step lengths and complementarity sums are warp reductions.
+//
+// The code is written against a tiny warp context (lane id, shfl, reductions) so that tests/hostsim can
+// run the identical source on the CPU with a fiber-based warp emulator.
+#pragma once
+#include "qs_qp.cuh"
+
+namespace qs {
+
+#if defined(__CUDACC__)
+struct WarpCtxDev {
+    int lane_;
+    __device__ __forceinline__ int lane() const { return lane_; }
+    __device__ __forceinline__ double shfl(double v, int src) const { return __shfl_sync(0xffffffffu, v, src & 31); }
+    __device__ __forceinline__ double wmax(double v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+    __device__ __forceinline__ double wmin(double v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+    __device__ __forceinline__ double wsum(double v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    __device__ __forceinline__ int wany(int p) const { return __any_sync(0xffffffffu, p); }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    // CTA-wide vote: keeps the warps of a CTA (one problem each) in lockstep, one barrier per IPM iteration,
+    // so that they share instruction fetches; returns true when every warp of the CTA has finished
+    __device__ __forceinline__ bool cta_all(bool pred) const { return __syncthreads_and(pred ? 1 : 0) != 0; }
+};
+#endif
+
+// rows of the per-problem shared-memory state; element (row, j) of lane l sits at sm[((row)*C + j)*L + l]
+enum : int {
+    R_A3 = 0, R_A4 = 4, R_B1 = 8, R_B2 = 12, R_BV = 16, R_G = 20, R_HH = 26,      // linearisation (29)
+    R_Z = 29, R_PIK = 35, R_LAM = 39, R_T = 45,                                    // point (22): z, pi_k, lam, t
+    R_RG = 51, R_RB = 57, R_K = 61, R_LI = 69, R_P = 72, R_PB = 82, R_DZA = 86,    // residuals, factor, P_k, P_{k+1} r_b, affine step
+    R_GT = 89, R_PV = 95, R_KFF = 99,                                              // rhs / step (aliased), p_k, k_ff
+    R_ROWS = 101
+};
+QS_HD constexpr int qp_warp_chunk(int N) { return (N + 1 + 31) / 32; }
+QS_HD constexpr int qp_warp_lanes(int N, int C) { return (N + 1 + C - 1) / C; }
+QS_HD constexpr size_t qp_warp_smem_doubles(int N) { return (size_t)R_ROWS * qp_warp_chunk(N) * qp_warp_lanes(N, qp_warp_chunk(N)); }
+
+// ---- small dense helpers --------------------------------------------------------------------------
+// Cholesky of a packed symmetric positive SEMI-definite 4x4 (lower, LT indexing); non-positive pivots give
+// a zero column.  id[i] = 1/L[i][i] (0 for dropped pivots).
+QS_HD void chol4_psd(const double A[10], double Lo[10], double id[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        double d = A[LT(j, j)];
+#pragma unroll
+        for (int p = 0; p < j; ++p) d = fma(-Lo[LT(j, p)], Lo[LT(j, p)], d);
+        const bool pos = d > 1e-14 * fabs(A[LT(j, j)]) && d > 0.0;
+        const double inv = pos ? qs_rsqrt(d) : 0.0;
+        Lo[LT(j, j)] = pos ? d * inv : 0.0;
+        id[j] = inv;
+#pragma unroll
+        for (int i = j + 1; i < 4; ++i) {
+            double a = A[LT(i, j)];
+#pragma unroll
+            for (int p = 0; p < j; ++p) a = fma(-Lo[LT(i, p)], Lo[LT(j, p)], a);
+            Lo[LT(i, j)] = a * inv;
+        }
+    }
+}
+
+struct Elem { double A[16]; double C[10]; double J[10]; };   // A row-major, C and J packed lower
+
+QS_HD void elem_identity(Elem& e) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) e.A[i] = (i % 5 == 0) ? 1.0 : 0.0;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) { e.C[i] = 0.0; e.J[i] = 0.0; }
+}
+
+// e1 <- e1 (x) e2 : e1 covers the earlier interval (i -> j), (A2, C2, J2) the later one (j -> k).
+QS_HD void elem_combine(Elem& e1, const double A2[16], const double C2[10], const double J2[10]) {
+    double L2[10], i2[4];
+    chol4_psd(J2, L2, i2);
+    // T = C1 L2 (4x4), L2 lower triangular: T[i][j] = sum_{p>=j} C1[i][p] L2[p][j]
+    double T[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double a = 0.0;
+#pragma unroll
+            for (int p = j; p < 4; ++p) a = fma(e1.C[LT(i, p)], L2[LT(p, j)], a);
+            T[4 * i + j] = a;
+        }
+    // W = I + L2' T (symmetric positive definite, eigenvalues >= 1)
+    double W[10], Lw[10], iw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            double a = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+            for (int p = i; p < 4; ++p) a = fma(L2[LT(p, i)], T[4 * p + j], a);
+            W[LT(i, j)] = a;
+        }
+    chol4_psd(W, Lw, iw);
+    // Z = Lw^-1 (L2' A1)   and   Y = Lw^-1 T'   (forward substitutions, column by column)
+    double Z[16], Y[16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double g[4], t[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double a = 0.0;
+#pragma unroll
+            for (int p = i; p < 4; ++p) a = fma(L2[LT(p, i)], e1.A[4 * p + c], a);
+            g[i] = a;
+            t[i] = T[4 * c + i];                               // column c of T' = row c of T
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double a = g[i], b = t[i];
+#pragma unroll
+            for (int p = 0; p < i; ++p) { a = fma(-Lw[LT(i, p)], Z[4 * p + c], a); b = fma(-Lw[LT(i, p)], Y[4 * p + c], b); }
+            Z[4 * i + c] = a * iw[i];
+            Y[4 * i + c] = b * iw[i];
+        }
+    }
+    // FA = A1 - Y'Z ; FC = C1 - Y'Y (sym) ; J = Z'Z + J1
+    double FA[16], FC[10];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double a = e1.A[4 * i + j];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) a = fma(-Y[4 * p + i], Z[4 * p + j], a);
+            FA[4 * i + j] = a;
+        }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            double a = e1.C[LT(i, j)], b = e1.J[LT(i, j)];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) { a = fma(-Y[4 * p + i], Y[4 * p + j], a); b = fma(Z[4 * p + i], Z[4 * p + j], b); }
+            FC[LT(i, j)] = a;
+            e1.J[LT(i, j)] = b;
+        }
+    // A = A2 FA ; C = A2 FC A2' + C2
+    double AF[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) { a = fma(A2[4 * i + p], FA[4 * p + j], a); b = fma(A2[4 * i + p], FC[LT(p, j)], b); }
+            e1.A[4 * i + j] = a;
+            AF[4 * i + j] = b;                                 // A2 FC
+        }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            double a = C2[LT(i, j)];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) a = fma(AF[4 * i + p], A2[4 * j + p], a);
+            e1.C[LT(i, j)] = a;
+        }
+}
+
+// affine maps v -> M v + d ; own <- own o partner  (own is applied AFTER partner)
+QS_HD void aff_compose(double M[16], double d[4], const double Mp[16], const double dp[4]) {
+    double Mn[16], dn[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double a = d[i];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) a = fma(M[4 * i + p], dp[p], a);
+        dn[i] = a;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double b = 0.0;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) b = fma(M[4 * i + p], Mp[4 * p + j], b);
+            Mn[4 * i + j] = b;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) M[i] = Mn[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[i] = dn[i];
+}
+
+// closed-loop transition Abar = A - B K of a stage (row-major), A = [e1 e2 a3 a4]
+QS_HD void closed_loop(const StageLin& L, const double K0[4], const double K1[4], double Ab[16]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double a = (j == 0) ? (i == 0 ? 1.0 : 0.0) : (j == 1) ? (i == 1 ? 1.0 : 0.0) : (j == 2 ? L.a3[i] : L.a4[i]);
+            Ab[4 * i + j] = a - fma(L.b1[i], K0[j], L.b2[i] * K1[j]);
+        }
+}
+
+// Newton step of one two-sided bound pair (lower: t = v - dl, upper: t = du - v), Mehrotra corrector included.
+struct IneqStep { double dtl, dtu, dll, dlu; };
+QS_HD IneqStep ineq_step(double v, double dva, double dv, double ll, double lu, double tl, double tu, double dl, double du, double smu) {
+    const double rdl = v - dl - tl, rdu = du - v - tu;
+    const double dtal = dva + rdl, dtau = -dva + rdu;
+    const double cl = (-ll - ll * dtal / tl) * dtal, cu = (-lu - lu * dtau / tu) * dtau;
+    IneqStep s;
+    s.dtl = dv + rdl; s.dtu = -dv + rdu;
+    s.dll = -(ll * tl - smu + cl + ll * s.dtl) / tl;
+    s.dlu = -(lu * tu - smu + cu + lu * s.dtu) / tu;
+    return s;
+}
+
+#define QW_SM(row, j) sm[((size_t)(row) * C + (j)) * Lw_ + lane]
+
+// One Newton solve with the current factorisation: rhs gt (R_GT rows) and r_b (R_RB) ->
+// step dz (R_GT rows, aliased), costate offsets p_k (R_PV), feed-forward k_ff (R_KFF).
+template <class Ctx, int C>
+QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, const double* __restrict__ QNp) {
+    const int lane = w.lane();
+    const bool act = lane < Lw_;
+    // ---- (a) local: d_k, kff0_k and the chunk's composed backward map  p_start = M p_end + d
+    double M[16], d[4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) M[i] = (i % 5 == 0) ? 1.0 : 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[i] = 0.0;
+    if (act) {
+#pragma unroll 1
+        for (int j = C - 1; j >= 0; --j) {
+            const int k = lane * C + j;
+            if (k > N) continue;
+            if (k == N) {                                       // terminal: p_N = rg_N (constant map)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) M[i] = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { d[i] = QW_SM(R_RG + 2 + i, j); QW_SM(R_PV + i, j) = d[i]; }
+                continue;
+            }
+            StageLin L;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
+            double gt[6], Pb[4], K0[4], K1[4], Li[3], m[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) gt[i] = QW_SM(R_GT + i, j);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { Pb[i] = QW_SM(R_PB + i, j); K0[i] = QW_SM(R_K + i, j); K1[i] = QW_SM(R_K + 4 + i, j); }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) Li[i] = QW_SM(R_LI + i, j);
+            lin_T_mul_add(L, Pb, gt, m);
+            const double y0 = m[0] * Li[0], y1 = (m[1] - Li[1] * y0) * Li[2];
+            const double k1 = y1 * Li[2], k0 = (y0 - Li[1] * k1) * Li[0];
+            QW_SM(R_KFF, j) = k0; QW_SM(R_KFF + 1, j) = k1;
+            double dk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { dk[i] = m[2 + i] - fma(K0[i], m[0], K1[i] * m[1]); QW_SM(R_PV + i, j) = dk[i]; }
+            double Ab[16], At[16];
+            closed_loop(L, K0, K1, Ab);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) At[4 * i + q] = Ab[4 * q + i];
+            // acc <- f_k o acc
+            aff_compose(At, dk, M, d);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) M[i] = At[i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] = dk[i];
+        }
+    }
+    // ---- (b) suffix scan over lanes; afterwards d = p at the first stage of the lane's chunk
+#pragma unroll 1
+    for (int dl = 1; dl < 32; dl <<= 1) {
+        double Mp[16], dp[4];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) Mp[i] = w.shfl(M[i], lane + dl);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dp[i] = w.shfl(d[i], lane + dl);
+        if (act && lane + dl < Lw_) aff_compose(M, d, Mp, dp);
+    }
+    double pe[4];                                              // p at the right boundary of the chunk
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pe[i] = w.shfl(d[i], lane + 1);
+    // ---- (c) local back-substitution: k_ff and p_k
+    if (act) {
+#pragma unroll 1
+        for (int j = C - 1; j >= 0; --j) {
+            const int k = lane * C + j;
+            if (k > N) continue;
+            if (k == N) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) pe[i] = QW_SM(R_PV + i, j);
+                continue;
+            }
+            StageLin L;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
+            double K0[4], K1[4], Li[3];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { K0[i] = QW_SM(R_K + i, j); K1[i] = QW_SM(R_K + 4 + i, j); }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) Li[i] = QW_SM(R_LI + i, j);
+            const double m0 = dot4(L.b1, pe), m1 = dot4(L.b2, pe);
+            const double y0 = m0 * Li[0], y1 = (m1 - Li[1] * y0) * Li[2];
+            const double k1 = y1 * Li[2], k0 = (y0 - Li[1] * k1) * Li[0];
+            QW_SM(R_KFF, j) += k0; QW_SM(R_KFF + 1, j) += k1;
+            // p_k = Abar' p_{k+1} + d_k = A'p - K'(B'p) + d_k
+            double pk[4];
+            pk[0] = QW_SM(R_PV + 0, j) + pe[0] - fma(K0[0], m0, K1[0] * m1);
+            pk[1] = QW_SM(R_PV + 1, j) + pe[1] - fma(K0[1], m0, K1[1] * m1);
+            pk[2] = QW_SM(R_PV + 2, j) + dot4(L.a3, pe) - fma(K0[2], m0, K1[2] * m1);
+            pk[3] = QW_SM(R_PV + 3, j) + dot4(L.a4, pe) - fma(K0[3], m0, K1[3] * m1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { QW_SM(R_PV + i, j) = pk[i]; pe[i] = pk[i]; }
+        }
+    }
+    // ---- (d) forward: chunk's composed map dx_end = M dx_start + d, prefix scan, local rollout
+#pragma unroll
+    for (int i = 0; i < 16; ++i) M[i] = (i % 5 == 0) ? 1.0 : 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[i] = 0.0;
+    if (act) {
+#pragma unroll 1
+        for (int j = 0; j < C; ++j) {
+            const int k = lane * C + j;
+            if (k >= N) continue;
+            StageLin L;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
+            double K0[4], K1[4], Ab[16], bb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { K0[i] = QW_SM(R_K + i, j); K1[i] = QW_SM(R_K + 4 + i, j); }
+            const double f0 = QW_SM(R_KFF, j), f1 = QW_SM(R_KFF + 1, j);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) bb[i] = QW_SM(R_RB + i, j) - fma(L.b1[i], f0, L.b2[i] * f1);
+            closed_loop(L, K0, K1, Ab);
+            aff_compose(Ab, bb, M, d);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) M[i] = Ab[i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] = bb[i];
+        }
+    }
+#pragma unroll 1
+    for (int dl = 1; dl < 32; dl <<= 1) {
+        double Mp[16], dp[4];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) Mp[i] = w.shfl(M[i], lane - dl);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dp[i] = w.shfl(d[i], lane - dl);
+        if (lane - dl >= 0) aff_compose(M, d, Mp, dp);
+    }
+    double x[4];                                               // dx at the first stage of the chunk (dx_0 = 0)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const double v = w.shfl(d[i], lane - 1); x[i] = (lane == 0) ? 0.0 : v; }
+    if (act) {
+#pragma unroll 1
+        for (int j = 0; j < C; ++j) {
+            const int k = lane * C + j;
+            if (k > N) continue;
+            if (k == N) {
+                QW_SM(R_GT + 0, j) = 0.0; QW_SM(R_GT + 1, j) = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) QW_SM(R_GT + 2 + i, j) = x[i];
+                continue;
+            }
+            StageLin L;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
+            double K0[4], K1[4], bk[4], kff[2], u[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { K0[i] = QW_SM(R_K + i, j); K1[i] = QW_SM(R_K + 4 + i, j); bk[i] = QW_SM(R_RB + i, j); }
+            kff[0] = QW_SM(R_KFF, j); kff[1] = QW_SM(R_KFF + 1, j);
+            const double xk[4] = {x[0], x[1], x[2], x[3]};
+            forward_stage(L, bk, K0, K1, kff, x, u);
+            QW_SM(R_GT + 0, j) = u[0]; QW_SM(R_GT + 1, j) = u[1];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) QW_SM(R_GT + 2 + i, j) = xk[i];
+        }
+    }
+    (void)QNp;
+}
+
+// Solve the QP of problem V with one warp.  sm: qp_warp_smem_doubles(N) doubles of shared memory owned by
+// this warp.  Outputs like qp_ipm: V.z (du,dx), V.lam, V.t, V.pi (pi[k] = pi_{k+1}), res, iters, status.
+template <class Ctx, int C>
+QS_HD void qp_ipm_warp(const Ctx& w, double* __restrict__ sm, const QpConst& Q, const QpView& V, bool valid_problem,
+                       int& iters_out, int& status_out, double res[4]) {
+    const int N = Q.N;
+    const int lane = w.lane();
+    const int Lw_ = qp_warp_lanes(N, C);
+    const bool act = valid_problem && lane < Lw_;
+    const int m_on = 6 * N - 2;
+    // ---------------- load the linearisation, initial point
+    if (act) {
+#pragma unroll 1
+        for (int j = 0; j < C; ++j) {
+            const int k = lane * C + j;
+            if (k > N) continue;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) QW_SM(R_Z + i, j) = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) QW_SM(R_PIK + i, j) = 0.0;
+            if (k == N) continue;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                QW_SM(R_A3 + i, j) = QS_AT(V.A, k, 8, i); QW_SM(R_A4 + i, j) = QS_AT(V.A, k, 8, 4 + i);
+                QW_SM(R_B1 + i, j) = QS_AT(V.B, k, 8, i); QW_SM(R_B2 + i, j) = QS_AT(V.B, k, 8, 4 + i);
+                QW_SM(R_BV + i, j) = QS_AT(V.b, k, 4, i);
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) QW_SM(R_G + i, j) = QS_AT(V.g, k, 6, i);
+            const double h[3] = {QS_AT(V.x, k, 4, 3), QS_AT(V.u, k, 2, 0), QS_AT(V.u, k, 2, 1)};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) QW_SM(R_HH + c, j) = h[c];
+            if (k == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) QW_SM(R_Z + 2 + i, j) = V.dx0[i * V.stride];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const bool on = !(k == 0 && c == 0);
+                const double v = QW_SM(R_Z + cidx(c), j);
+                double tl = fmax(v - (Q.lh[c] - h[c]), Q.thr), tu = fmax((Q.uh[c] - h[c]) - v, Q.thr);
+                double ll = Q.mu0 / tl, lu = Q.mu0 / tu;
+                if (!on) { tl = 1.0; tu = 1.0; ll = 0.0; lu = 0.0; }
+                QW_SM(R_T + c, j) = tl; QW_SM(R_T + 3 + c, j) = tu;
+                QW_SM(R_LAM + c, j) = ll; QW_SM(R_LAM + 3 + c, j) = lu;
+            }
+        }
+    }
+    double qN[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qN[i] = V.qN[i * V.stride];
+    w.sync();
+
+    int status = 1, it = 0, stall = 0;
+    double rmax_prev = 1e300;
+    double r_stat = 0.0, r_eq = 0.0, r_in = 0.0, r_cp = 0.0;
+    bool finished = !valid_problem;
+    for (;;) {
+        if (w.cta_all(finished)) break;                         // lockstep point of the CTA's warps
+        if (finished) continue;
+        // ================= (1) true residuals =================
+        double nx[4], npi[4];                                  // x and pi of the stage right of the chunk
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            nx[i] = w.shfl(act ? QW_SM(R_Z + 2 + i, 0) : 0.0, lane + 1);
+            npi[i] = w.shfl(act ? QW_SM(R_PIK + i, 0) : 0.0, lane + 1);
+        }
+        double l_stat = 0.0, l_eq = 0.0, l_in = 0.0, l_cp = 0.0, l_mu = 0.0;
+        bool l_nan = false;
+        if (act) {
+#pragma unroll 1
+            for (int j = C - 1; j >= 0; --j) {
+                const int k = lane * C + j;
+                if (k > N) continue;
+                double z6[6], pik[4];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) z6[i] = QW_SM(R_Z + i, j);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) pik[i] = QW_SM(R_PIK + i, j);
+                if (k == N) {
+                    double xN[4] = {z6[2], z6[3], z6[4], z6[5]}, rg[4];
+                    sym4_mul(Q.QN, xN, rg);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { rg[i] += qN[i] - pik[i]; QW_SM(R_RG + 2 + i, j) = rg[i]; l_stat = fmax(l_stat, fabs(rg[i])); l_nan = l_nan || !(rg[i] == rg[i]); }
+                } else {
+                    StageLin L;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
+                    const double* Hk = Q.H + (size_t)k * 21;
+                    double gh[6], rg[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        double a = QW_SM(R_G + i, j);
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) a = fma(Hk[LT(i, q)], z6[q], a);
+                        gh[i] = a;
+                    }
+                    lin_T_mul_add(L, npi, gh, rg);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) rg[2 + i] -= pik[i];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        if (k == 0 && c == 0) continue;
+                        const double h = QW_SM(R_HH + c, j), v = z6[cidx(c)];
+                        const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
+                        rg[cidx(c)] += lu - ll;
+                        const double rdl = v - (Q.lh[c] - h) - tl, rdu = (Q.uh[c] - h) - v - tu;
+                        l_in = fmax(l_in, fmax(fabs(rdl), fabs(rdu)));
+                        l_cp = fmax(l_cp, fmax(ll * tl, lu * tu));
+                        l_mu += ll * tl + lu * tu;
+                    }
+                    if (k == 0) { rg[2] = 0.0; rg[3] = 0.0; rg[4] = 0.0; rg[5] = 0.0; }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) { QW_SM(R_RG + i, j) = rg[i]; l_stat = fmax(l_stat, fabs(rg[i])); l_nan = l_nan || !(rg[i] == rg[i]); }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        double a = QW_SM(R_BV + i, j) + (i < 2 ? z6[2 + i] : 0.0) - nx[i];
+                        a = fma(L.a3[i], z6[4], a); a = fma(L.a4[i], z6[5], a);
+                        a = fma(L.b1[i], z6[0], a); a = fma(L.b2[i], z6[1], a);
+                        QW_SM(R_RB + i, j) = a; l_eq = fmax(l_eq, fabs(a)); l_nan = l_nan || !(a == a);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { nx[i] = z6[2 + i]; npi[i] = pik[i]; }
+            }
+        }
+        r_stat = w.wmax(l_stat); r_eq = w.wmax(l_eq); r_in = w.wmax(l_in); r_cp = w.wmax(l_cp);
+        const double mu_sum = w.wsum(l_mu);
+        const double mu = mu_sum / (double)m_on;
+        if (w.wany(l_nan ? 1 : 0) || !(mu == mu)) { status = 2; finished = true; continue; }
+        if (r_stat < Q.tol && r_eq < Q.tol && r_in < Q.tol && r_cp < Q.tol) { status = 0; finished = true; continue; }
+        {
+            const double rmax = fmax(fmax(r_stat, r_eq), fmax(r_in, r_cp));
+            if (rmax < 0.5 * rmax_prev) { rmax_prev = rmax; stall = 0; } else ++stall;
+            if (stall >= 5 && rmax < QS_QP_TOL_ACCEPT) { status = 0; finished = true; continue; }
+        }
+        if (it >= Q.max_iter) { status = 1; finished = true; continue; }
+        // ================= (2) barrier terms, affine rhs, stage elements, chunk aggregate =================
+        Elem E; elem_identity(E);
+        if (act) {
+#pragma unroll 1
+            for (int j = C - 1; j >= 0; --j) {
+                const int k = lane * C + j;
+                if (k > N) continue;
+                if (k == N) {                                   // terminal value function: J = Q_N, A = 0, C = 0
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) E.A[i] = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) { E.C[i] = 0.0; E.J[i] = Q.QN[i]; }
+                    continue;
+                }
+                const double* Hk = Q.H + (size_t)k * 21;
+                double D[3], gt[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) gt[i] = QW_SM(R_RG + i, j);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const double h = QW_SM(R_HH + c, j), v = QW_SM(R_Z + cidx(c), j);
+                    const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
+                    const double itl = 1.0 / tl, itu = 1.0 / tu;
+                    const bool on = !(k == 0 && c == 0);
+                    const double rdl = on ? v - (Q.lh[c] - h) - tl : 0.0, rdu = on ? (Q.uh[c] - h) - v - tu : 0.0;
+                    D[c] = ll * itl + lu * itu;
+                    gt[cidx(c)] += (ll + ll * rdl * itl) - (lu + lu * rdu * itu);
+                }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) QW_SM(R_GT + i, j) = gt[i];
+                // element of stage k: eliminate u.  Rt = H_uu + D_u, S = H_ux, Qt = H_xx + D_s
+                const double r00 = Hk[LT(0, 0)] + D[1], r10 = Hk[LT(1, 0)], r11 = Hk[LT(1, 1)] + D[2];
+                const double i00 = qs_rsqrt(r00), l10 = r10 * i00, i11 = qs_rsqrt(r11 - l10 * l10);
+                StageLin L;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
+                // Bh = B Lr^-T  (4x2):  columns of B R^-1 B' = Bh Bh'
+                double bh0[4], bh1[4], sh0[4], sh1[4];             // Sh = Lr^-1 S (2x4)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    bh0[i] = L.b1[i] * i00; bh1[i] = (L.b2[i] - l10 * bh0[i]) * i11;
+                    const double s0 = Hk[LT(2 + i, 0)], s1 = Hk[LT(2 + i, 1)];
+                    sh0[i] = s0 * i00; sh1[i] = (s1 - l10 * sh0[i]) * i11;
+                }
+                Elem e;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const double a = (q == 0) ? (i == 0 ? 1.0 : 0.0) : (q == 1) ? (i == 1 ? 1.0 : 0.0) : (q == 2 ? L.a3[i] : L.a4[i]);
+                        e.A[4 * i + q] = a - fma(bh0[i], sh0[q], bh1[i] * sh1[q]);
+                    }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int q = 0; q <= i; ++q) {
+                        e.C[LT(i, q)] = fma(bh0[i], bh0[q], bh1[i] * bh1[q]);
+                        e.J[LT(i, q)] = Hk[LT(2 + i, 2 + q)] - fma(sh0[i], sh0[q], sh1[i] * sh1[q]);
+                    }
+                e.J[LT(3, 3)] += D[0];
+                if (k == 0) {
+                    // x_0 is fixed (dx_0 = 0): only the reachable-set part matters; keep J finite and PSD
+                }
+                elem_combine(e, E.A, E.C, E.J);                  // E <- e (x) E
+                E = e;
+            }
+        }
+        // ================= (3) suffix scan of the chunk aggregates =================
+#pragma unroll 1
+        for (int dl = 1; dl < 32; dl <<= 1) {
+            double A2[16], C2[10], J2[10];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) A2[i] = w.shfl(E.A[i], lane + dl);
+#pragma unroll
+            for (int i = 0; i < 10; ++i) { C2[i] = w.shfl(E.C[i], lane + dl); J2[i] = w.shfl(E.J[i], lane + dl); }
+            if (act && lane + dl < Lw_) elem_combine(E, A2, C2, J2);
+        }
+        double P[10];                                          // P at the right boundary of the chunk
+#pragma unroll
+        for (int i = 0; i < 10; ++i) P[i] = w.shfl(E.J[i], lane + 1);
+        // ================= (4) local Riccati over the chunk: K_k, Cholesky, P_k, P_{k+1} r_b =================
+        bool ok = true;
+        if (act) {
+#pragma unroll 1
+            for (int j = C - 1; j >= 0; --j) {
+                const int k = lane * C + j;
+                if (k > N) continue;
+                if (k == N) {
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) { P[i] = Q.QN[i]; QW_SM(R_P + i, j) = P[i]; }
+                    continue;
+                }
+                StageLin L;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
+                double D[3], rb[4], Pb[4], K0[4], K1[4], Li[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) D[c] = QW_SM(R_LAM + c, j) / QW_SM(R_T + c, j) + QW_SM(R_LAM + 3 + c, j) / QW_SM(R_T + 3 + c, j);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rb[i] = QW_SM(R_RB + i, j);
+                sym4_mul(P, rb, Pb);
+                ok = riccati_factor_stage(L, Q.H + (size_t)k * 21, D, P, K0, K1, Li) && ok;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { QW_SM(R_K + i, j) = K0[i]; QW_SM(R_K + 4 + i, j) = K1[i]; QW_SM(R_PB + i, j) = Pb[i]; }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) QW_SM(R_LI + i, j) = Li[i];
+#pragma unroll
+                for (int i = 0; i < 10; ++i) QW_SM(R_P + i, j) = P[i];
+            }
+        }
+        if (w.wany(ok ? 0 : 1)) { status = 2; finished = true; continue; }
+        // ================= (5)-(7) predictor and corrector share ONE copy of the solve code =================
+        double smu = 0.0;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1 && act) {
+                // corrector rhs
+#pragma unroll 1
+                for (int j = 0; j < C; ++j) {
+                    const int k = lane * C + j;
+                    if (k >= N) continue;
+                    double gt[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) gt[i] = QW_SM(R_RG + i, j);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        if (k == 0 && c == 0) continue;
+                        const double h = QW_SM(R_HH + c, j), v = QW_SM(R_Z + cidx(c), j), dva = QW_SM(R_DZA + c, j);
+                        const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
+                        const double rdl = v - (Q.lh[c] - h) - tl, rdu = (Q.uh[c] - h) - v - tu;
+                        const double dtl = dva + rdl, dtu = -dva + rdu;
+                        const double cl = (-ll - ll * dtl / tl) * dtl, cu = (-lu - lu * dtu / tu) * dtu;
+                        gt[cidx(c)] += (ll * tl - smu + cl + ll * rdl) / tl - (lu * tu - smu + cu + lu * rdu) / tu;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) QW_SM(R_GT + i, j) = gt[i];
+                }
+            }
+            qp_warp_solve<Ctx, C>(w, sm, N, Lw_, Q.QN);
+            if (pass == 0) {
+                // step to the boundary of the affine step, mu_aff, centering parameter
+                double a_aff = 1.0, S1 = 0.0, S2 = 0.0;
+                if (act) {
+#pragma unroll 1
+                    for (int j = 0; j < C; ++j) {
+                        const int k = lane * C + j;
+                        if (k >= N) continue;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const double dva = QW_SM(R_GT + cidx(c), j);
+                            QW_SM(R_DZA + c, j) = dva;
+                            if (k == 0 && c == 0) continue;
+                            const double h = QW_SM(R_HH + c, j), v = QW_SM(R_Z + cidx(c), j);
+                            const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
+                            const double dtl = dva + (v - (Q.lh[c] - h) - tl), dtu = -dva + ((Q.uh[c] - h) - v - tu);
+                            const double dll = -ll - ll * dtl / tl, dlu = -lu - lu * dtu / tu;
+                            if (dtl < 0.0) a_aff = fmin(a_aff, -tl / dtl);
+                            if (dtu < 0.0) a_aff = fmin(a_aff, -tu / dtu);
+                            if (dll < 0.0) a_aff = fmin(a_aff, -ll / dll);
+                            if (dlu < 0.0) a_aff = fmin(a_aff, -lu / dlu);
+                            S1 += ll * dtl + tl * dll + lu * dtu + tu * dlu;
+                            S2 += dll * dtl + dlu * dtu;
+                        }
+                    }
+                }
+                a_aff = w.wmin(a_aff); S1 = w.wsum(S1); S2 = w.wsum(S2);
+                const double mu_aff = (mu_sum + a_aff * (S1 + a_aff * S2)) / (double)m_on;
+                double sigma = (mu > 0.0) ? mu_aff / mu : 0.0;
+                sigma = sigma * sigma * sigma;
+                smu = fmax(sigma * mu, 0.1 * Q.tol);
+            }
+        }
+        // ================= (8) step length and update =================
+        double a_max = 1.0;
+        if (act) {
+#pragma unroll 1
+            for (int j = 0; j < C; ++j) {
+                const int k = lane * C + j;
+                if (k >= N) continue;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (k == 0 && c == 0) continue;
+                    IneqStep s_ = ineq_step(QW_SM(R_Z + cidx(c), j), QW_SM(R_DZA + c, j), QW_SM(R_GT + cidx(c), j),
+                                            QW_SM(R_LAM + c, j), QW_SM(R_LAM + 3 + c, j), QW_SM(R_T + c, j), QW_SM(R_T + 3 + c, j),
+                                            Q.lh[c] - QW_SM(R_HH + c, j), Q.uh[c] - QW_SM(R_HH + c, j), smu);
+                    if (s_.dtl < 0.0) a_max = fmin(a_max, -QW_SM(R_T + c, j) / s_.dtl);
+                    if (s_.dtu < 0.0) a_max = fmin(a_max, -QW_SM(R_T + 3 + c, j) / s_.dtu);
+                    if (s_.dll < 0.0) a_max = fmin(a_max, -QW_SM(R_LAM + c, j) / s_.dll);
+                    if (s_.dlu < 0.0) a_max = fmin(a_max, -QW_SM(R_LAM + 3 + c, j) / s_.dlu);
+                }
+            }
+        }
+        a_max = w.wmin(a_max);
+        const double alpha = fmin(1.0, Q.tau * a_max);
+        if (!(alpha == alpha)) { status = 2; finished = true; continue; }
+        if (act) {
+#pragma unroll 1
+            for (int j = 0; j < C; ++j) {
+                const int k = lane * C + j;
+                if (k > N) continue;
+                double dz[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) dz[i] = QW_SM(R_GT + i, j);
+                if (k >= 1) {                                   // dpi_k = P_k dx_k + p_k
+                    double Pk[10], dxk[4] = {dz[2], dz[3], dz[4], dz[5]}, dp[4];
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) Pk[i] = QW_SM(R_P + i, j);
+                    sym4_mul(Pk, dxk, dp);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) QW_SM(R_PIK + i, j) = fma(alpha, dp[i] + QW_SM(R_PV + i, j), QW_SM(R_PIK + i, j));
+                }
+                if (k < N) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        if (k == 0 && c == 0) continue;
+                        IneqStep s_ = ineq_step(QW_SM(R_Z + cidx(c), j), QW_SM(R_DZA + c, j), dz[cidx(c)],
+                                                QW_SM(R_LAM + c, j), QW_SM(R_LAM + 3 + c, j), QW_SM(R_T + c, j), QW_SM(R_T + 3 + c, j),
+                                                Q.lh[c] - QW_SM(R_HH + c, j), Q.uh[c] - QW_SM(R_HH + c, j), smu);
+                        QW_SM(R_T + c, j) = fma(alpha, s_.dtl, QW_SM(R_T + c, j));
+                        QW_SM(R_T + 3 + c, j) = fma(alpha, s_.dtu, QW_SM(R_T + 3 + c, j));
+                        QW_SM(R_LAM + c, j) = fma(alpha, s_.dll, QW_SM(R_LAM + c, j));
+                        QW_SM(R_LAM + 3 + c, j) = fma(alpha, s_.dlu, QW_SM(R_LAM + 3 + c, j));
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) QW_SM(R_Z + i, j) = fma(alpha, dz[i], QW_SM(R_Z + i, j));
+            }
+        }
+        w.sync();
+        ++it;
+    }
+    // ---------------- write the point back to the slabs
+    if (act) {
+#pragma unroll 1
+        for (int j = 0; j < C; ++j) {
+            const int k = lane * C + j;
+            if (k > N) continue;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) QS_AT(V.z, k, 6, i) = QW_SM(R_Z + i, j);
+            if (k >= 1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) QS_AT(V.pi, k - 1, 4, i) = QW_SM(R_PIK + i, j);
+            }
+            if (k < N) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) { QS_AT(V.lam, k, 6, i) = QW_SM(R_LAM + i, j); QS_AT(V.t, k, 6, i) = QW_SM(R_T + i, j); }
+            }
+        }
+    }
+    iters_out = it; status_out = status;
+    res[0] = r_stat; res[1] = r_eq; res[2] = r_in; res[3] = r_cp;
+}
+
+}  // namespace qs

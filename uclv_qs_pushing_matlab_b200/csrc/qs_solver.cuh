@@ -7,6 +7,7 @@
 #pragma once
 #include "qs_device.cuh"
 #include "qs_qp.cuh"
+#include "qs_qp_warp.cuh"
 
 namespace qs {
 
@@ -217,6 +218,64 @@ QS_HD void qp_one(const SolverDev& S, const IpmOpts& o, int b, int apply) {
     S.sqp_iter[b] = 1;
     S.alpha[b] = 1.0;
     S.status[b] = nan ? 1 : (status == 2 ? 4 : 0);     // QP iteration limit is tolerated
+}
+
+// K4 (+ K5 in RTI mode), warp-per-problem version: all 32 lanes call this for problem b; sm = the warp's
+// shared-memory state (qp_warp_smem_doubles(N) doubles).
+template <class Ctx, int C>
+QS_HD void qp_one_warp(const Ctx& w, double* __restrict__ sm, const SolverDev& S, const IpmOpts& o, int b_in, int apply) {
+    const bool valid = b_in < S.B && !(S.done && S.done[b_in < S.B ? b_in : 0]);
+    const int b = valid ? b_in : 0;                             // idle warps of a CTA still take part in its barriers
+    QpConst Qc;
+    Qc.N = S.N; Qc.H = S.H; Qc.QN = S.QN;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { Qc.lh[i] = S.lh[i]; Qc.uh[i] = S.uh[i]; }
+    Qc.max_iter = o.max_iter; Qc.tol = o.tol; Qc.mu0 = o.mu0; Qc.thr = o.thr; Qc.tau = o.tau;
+    QpView V;
+    V.stride = (size_t)S.Bp;
+    V.A = S.A + b; V.B = S.Bm + b; V.b = S.b + b; V.g = S.g + b; V.qN = S.qN + b; V.dx0 = S.dx0 + b;
+    V.x = S.x + b; V.u = S.u + b;
+    V.z = S.z + b; V.zp = S.zp + b; V.zc = S.zc + b; V.t = S.t + b;
+    V.K = S.K + b; V.Li = S.Li + b; V.Pb = S.Pb + b; V.kff = S.kff + b;
+    V.rg = S.rg + b; V.rb = S.rb + b; V.rgs = S.rgs + b;
+    V.lam = (apply ? S.lam : S.lamq) + b;
+    V.pi = (apply ? S.pi : S.piq) + b;
+    int iters, status; double res[4];
+    qp_ipm_warp<Ctx, C>(w, sm, Qc, V, valid, iters, status, res);
+    if (!valid) return;
+    const int lane = w.lane();
+    if (lane == 0) {
+        S.qpstat[b] = status;
+        if (apply) S.qp_iter[b] = iters; else S.qp_iter[b] += iters;
+    }
+    if (!apply) return;
+    // ---- K5 (RTI): x += dx, u += du, cost, status — each lane updates its own stages
+    w.sync();
+    const int N = S.N;
+    double cost = 0.0;
+    int nan = 0;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        const int k = lane * C + j;
+        if (k > N) continue;
+        if (k < N) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { const double v = QS_EL(S.u, k * 2 + i, b) + QS_EL(S.z, k * 6 + i, b); QS_EL(S.u, k * 2 + i, b) = v; nan |= !(v == v); }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) QS_EL(S.x, k * 4 + i, b) += QS_EL(S.z, k * 6 + 2 + i, b);
+        cost += (k < N) ? stage_cost(S, k, b) : terminal_cost(S, b);
+    }
+    cost = w.wsum(cost);
+    nan = w.wany(nan);
+    if (lane == 0) {
+        S.cost[b] = cost;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) QS_EL(S.res, i, b) = res[i];
+        S.sqp_iter[b] = 1;
+        S.alpha[b] = 1.0;
+        S.status[b] = nan ? 1 : (status == 2 ? 4 : 0);
+    }
 }
 
 // NLP residuals (inf-norms) and the convergence test of one SQP iteration; returns 1 when problem b finishes

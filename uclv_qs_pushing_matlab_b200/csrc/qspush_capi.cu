@@ -250,6 +250,7 @@ void qspush_opts_default(qspush_opts* o) {
     o->alpha_min = 0.05; o->alpha_reduction = 0.7; o->eps_sufficient_descent = 1e-4;
     o->matlab_single_quirk = 1;
     o->problems_per_warp = 0;
+    o->qp_kernel = 1;
 }
 
 static size_t al(size_t doubles) { return (doubles + 31) / 32 * 32; }   // 256-byte granules
@@ -519,6 +520,31 @@ int qspush_prepare(qspush_solver* s) {
     return QSPUSH_OK;
 }
 
+// launch the QP kernel selected by opts.qp_kernel: 1 (default when the horizon fits) = warp per problem,
+// parallel-in-time; 0 = one problem per thread (any horizon)
+static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, int ppw, int apply) {
+    const int C = qp_warp_chunk(s->N);
+    const bool warp = (s->opts.qp_kernel != 0) && C <= 4 && qp_warp_smem_doubles(s->N) * 8 * QW_WARPS <= 220 * 1024;
+    if (!warp) {
+        k_qp<<<(unsigned)((s->B + ppw - 1) / ppw), 32, 0, s->stream>>>(D, io, ppw, apply);
+        return QSPUSH_OK;
+    }
+    const int pwd = (int)((qp_warp_smem_doubles(s->N) + 1) / 2 * 2);
+    const size_t smem = (size_t)pwd * QW_WARPS * sizeof(double);
+    const unsigned blocks = (unsigned)((s->B + QW_WARPS - 1) / QW_WARPS);
+#define QW_LAUNCH(CC)                                                                                              \
+    CK(cudaFuncSetAttribute(k_qp_warp<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+    k_qp_warp<CC><<<blocks, 32 * QW_WARPS, smem, s->stream>>>(D, io, apply, pwd)
+    switch (C) {
+        case 1: QW_LAUNCH(1); break;
+        case 2: QW_LAUNCH(2); break;
+        case 3: QW_LAUNCH(3); break;
+        default: QW_LAUNCH(4); break;
+    }
+#undef QW_LAUNCH
+    return QSPUSH_OK;
+}
+
 static int pick_ppw(const qspush_solver* s) {
     int p = s->opts.problems_per_warp;
     if (p == 32 || p == 16 || p == 8 || p == 4) return p;
@@ -538,13 +564,12 @@ int qspush_solve(qspush_solver* s) {
     const size_t smem = model_smem_bytes(s->nmodels);
     const size_t nlin = (size_t)(s->N + 1) * s->Bp;
     const unsigned lin_blocks = (unsigned)((nlin + 127) / 128);
-    const unsigned qp_blocks = (unsigned)((s->B + ppw - 1) / ppw);
     CK(cudaEventRecord(s->ev[0], s->stream));
     if (o.mode == QSPUSH_MODE_RTI) {
         SolverDev D = s->dev; D.done = nullptr;
         k_linearise<<<lin_blocks, 128, smem, s->stream>>>(D);
         CK(cudaEventRecord(s->ev[1], s->stream));
-        k_qp<<<qp_blocks, 32, 0, s->stream>>>(D, io, ppw, 1);
+        RET(launch_qp(s, D, io, ppw, 1));
         CK(cudaEventRecord(s->ev[2], s->stream));
         CK(cudaGetLastError());
         s->launches += 2;
@@ -565,7 +590,7 @@ int qspush_solve(qspush_solver* s) {
         CK(cudaMemcpyAsync(s->h_ndone, D.ndone, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
         if (*s->h_ndone >= s->B || it == o.max_sqp_iter) break;
-        k_qp<<<qp_blocks, 32, 0, s->stream>>>(D, io, ppw, 0);
+        RET(launch_qp(s, D, io, ppw, 0));
         k_linesearch<<<pb, 64, smem, s->stream>>>(D, so, it);
         s->launches += 2;
     }
