@@ -146,7 +146,7 @@ def run_ours(args):
     B, N = BATCH_PER_GPU, HORIZON
     gm = gpu_model(OBJECT)
     wl = make_rti_workload(B, N, dt=DT, seed=2 + rank)
-    solver = q.Solver([gm], N, DT, B, device=local_rank, qp_tol=QP_TOL, problems_per_warp=args.ppw)
+    solver = q.Solver([gm], N, DT, B, device=local_rank, qp_tol=QP_TOL, problems_per_warp=args.ppw, qp_kernel=args.qp_kernel)
     stream = torch.cuda.ExternalStream(solver.stream, device=dev)
 
     # device-resident inputs / outputs (value) and pinned host buffers (e2e)
@@ -244,7 +244,7 @@ def run_ours(args):
     achieved_gbs = B * ALG_BYTES_PER_ITER / (qp_avg_ms * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_qp_traffic.json"))).get("dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_qp_traffic.json")))["qp_kernel_%d" % args.qp_kernel]["dram_bytes_per_launch"]
     except Exception:
         pass
     # FP64 reference rate measured here with a cuBLAS DGEMM (MEASURED_PEAKS.json has no FP64 entry)
@@ -268,7 +268,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(h_u0.numel() * 8 + h_status.numel() * 4), "ms_per_step": 1e3 * t_e2e_max / args.steps},
         "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_qp (Riccati/Mehrotra IPM, one problem per thread)", "achieved": achieved_gbs, "peak": hbm_peak,
+        "roofline": {"bound": "hbm", "kernel": ("k_qp_warp<2> (Mehrotra IPM, warp per problem, parallel-in-time Riccati scan, smem-resident state)" if args.qp_kernel else "k_qp (Riccati/Mehrotra IPM, one problem per thread)"), "achieved": achieved_gbs, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src + " (of measured)",
                      "algorithmic_bytes_per_launch": B * ALG_BYTES_PER_ITER, "kernel_ms": qp_avg_ms,
                      "kernel_share_of_step": qp_avg_ms / (sum(step_ms) / len(step_ms)),
@@ -295,6 +295,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ppw", type=int, default=0, help="QP kernel packing (problems per warp), 0 = auto")
+    ap.add_argument("--qp-kernel", type=int, default=1, help="1 = warp per problem (parallel-in-time), 0 = one problem per thread")
     ap.add_argument("--cpu-passes", type=int, default=3, help="passes of the oracle over the batch for cpu_baseline")
     args = ap.parse_args()
     if args.impl == "reference":

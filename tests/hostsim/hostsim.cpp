@@ -130,21 +130,23 @@ struct WarpCtxHost {
     bool cta_all(bool pred) const { return pred; }      // one emulated warp per CTA
 };
 
-struct WarpJob { const SolverDev* S; const IpmOpts* io; int b; int apply; double* sm; int C; };
+struct WarpJob { const SolverDev* S; const IpmOpts* io; int b; int apply; double* sm; int C; int handed[32]; };
 static void warp_job_body(int lane, void* arg) {
     WarpJob* j = (WarpJob*)arg;
     WarpCtxHost w{lane};
+    // work queue of the emulated warp: exactly one problem (every lane sees the same sequence b, -1)
+    auto next = [j, lane]() -> int { return j->handed[lane]++ == 0 ? j->b : -1; };
     switch (j->C) {
-        case 1: qp_one_warp<WarpCtxHost, 1>(w, j->sm, *j->S, *j->io, j->b, j->apply); break;
-        case 2: qp_one_warp<WarpCtxHost, 2>(w, j->sm, *j->S, *j->io, j->b, j->apply); break;
-        case 3: qp_one_warp<WarpCtxHost, 3>(w, j->sm, *j->S, *j->io, j->b, j->apply); break;
-        default: qp_one_warp<WarpCtxHost, 4>(w, j->sm, *j->S, *j->io, j->b, j->apply); break;
+        case 1: qp_warp_persistent<WarpCtxHost, 1>(w, j->sm, *j->S, *j->io, j->apply, next); break;
+        case 2: qp_warp_persistent<WarpCtxHost, 2>(w, j->sm, *j->S, *j->io, j->apply, next); break;
+        case 3: qp_warp_persistent<WarpCtxHost, 3>(w, j->sm, *j->S, *j->io, j->apply, next); break;
+        default: qp_warp_persistent<WarpCtxHost, 4>(w, j->sm, *j->S, *j->io, j->apply, next); break;
     }
 }
 // mirrors k_qp_warp: one emulated warp per problem
 static void qp_warp_host(const SolverDev& S, const IpmOpts& io, int b, int apply) {
     std::vector<double> sm(qp_warp_smem_doubles(S.N), 0.0);
-    WarpJob j{&S, &io, b, apply, sm.data(), qp_warp_chunk(S.N)};
+    WarpJob j{&S, &io, b, apply, sm.data(), qp_warp_chunk(S.N), {0}};
     emu_run(warp_job_body, &j);
 }
 

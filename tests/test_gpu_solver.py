@@ -63,13 +63,14 @@ def test_set_get_roundtrip_and_errors():
     assert torch.equal(out, t)                                    # device-pointer path, no host copies
 
 
+@pytest.mark.parametrize("qp_kernel", [1, 0], ids=["warp_scan", "thread"])
 @pytest.mark.parametrize("name,N", [("santal", 40), ("montana", 10), ("balea", 100)])
-def test_prepare_qp_rti_vs_oracle(name, N):
+def test_prepare_qp_rti_vs_oracle(name, N, qp_kernel):
     gm, om = packaged_model_pair(name)
     B = 256
     wl = make_rti_workload(None, batch=B, N=N, seed=2)
     ocp, pr = _oracle_prepared(om, wl, N)
-    s = q.Solver([gm], N, 0.05, B)
+    s = q.Solver([gm], N, 0.05, B, qp_kernel=qp_kernel)
     _load(s, wl); s.prepare()
     assert np.array_equal(s.get("x0"), pr["x0"])
     assert rel_err(s.get("x"), pr["x"]) < REL and rel_err(s.get("u"), pr["u"]) < REL
@@ -170,7 +171,11 @@ def test_config3_full_size_properties():
     B, N = 4096, 40
     wl = make_rti_workload(None, batch=B, N=N, seed=2)
     s = q.Solver([gm], N, 0.05, B)
+    s2 = q.Solver([gm], N, 0.05, B, qp_kernel=0)                  # both QP kernels solve the same 4096 QPs
+    _load(s2, wl); s2.prepare(); s2.solve()
     _load(s, wl); s.prepare(); s.solve()
+    d12 = np.abs(s.get("u") - s2.get("u")).max(axis=(1, 2))
+    assert (d12 < 1e-6).mean() >= 0.95 and d12.max() < 2e-5 and (s2.get_int("status") == 0).all()
     st, it, res, u, x = s.get_int("status"), s.get_int("qp_iter"), s.get("res"), s.get("u"), s.get("x")
     assert (st == 0).all() and it.max() <= 30 and 8 < it.mean() < 16
     assert res.max() < 1e-11                                       # KKT certificate of all 4096 QPs

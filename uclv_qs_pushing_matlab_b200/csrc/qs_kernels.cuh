@@ -192,16 +192,25 @@ __global__ void __launch_bounds__(32) k_qp(SolverDev S, IpmOpts o, int ppw, int 
     qp_one(S, o, b, apply);
 }
 
-// K4 v2: one warp per problem, QW_WARPS warps (problems) per CTA kept in lockstep by one barrier per IPM
-// iteration; the IPM state of each problem lives in its warp's slice of the dynamic shared memory
+// K4 v2: warp per problem, persistent CTAs of QW_WARPS warps (one CTA per SM); finished warps pull the next
+// problem from a global work queue (S.ndone[1]); the IPM state of each problem lives in its warp's slice of
+// the dynamic shared memory.
 constexpr int QW_WARPS = 6;
 template <int C>
 __global__ void __launch_bounds__(32 * QW_WARPS, 1) k_qp_warp(SolverDev S, IpmOpts o, int apply, int per_warp_doubles) {
     extern __shared__ __align__(16) double qw_smem[];
     const int wid = threadIdx.x >> 5;
-    const int b = blockIdx.x * QW_WARPS + wid;
     WarpCtxDev w{(int)(threadIdx.x & 31)};
-    qp_one_warp<WarpCtxDev, C>(w, qw_smem + (size_t)wid * per_warp_doubles, S, o, b, apply);
+    auto next = [&]() -> int {
+        int b = -1;
+        for (;;) {
+            if (w.lane() == 0) b = atomicAdd(S.ndone + 1, 1);
+            b = w.bcast_int(b);
+            if (b >= S.B) return -1;
+            if (!(S.done && S.done[b])) return b;                // full SQP: skip problems that already converged
+        }
+    };
+    qp_warp_persistent<WarpCtxDev, C>(w, qw_smem + (size_t)wid * per_warp_doubles, S, o, apply, next);
 }
 
 __global__ void __launch_bounds__(64) k_nlp_res(SolverDev S, SqpOpts o, int it) {

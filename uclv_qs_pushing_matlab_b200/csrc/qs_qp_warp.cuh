@@ -51,6 +51,7 @@ struct WarpCtxDev {
     // CTA-wide vote: keeps the warps of a CTA (one problem each) in lockstep, one barrier per IPM iteration,
     // so that they share instruction fetches; returns true when every warp of the CTA has finished
     __device__ __forceinline__ bool cta_all(bool pred) const { return __syncthreads_and(pred ? 1 : 0) != 0; }
+    __device__ __forceinline__ int bcast_int(int v) const { return __shfl_sync(0xffffffffu, v, 0); }
 };
 #endif
 
@@ -64,7 +65,12 @@ enum : int {
 };
 QS_HD constexpr int qp_warp_chunk(int N) { return (N + 1 + 31) / 32; }
 QS_HD constexpr int qp_warp_lanes(int N, int C) { return (N + 1 + C - 1) / C; }
-QS_HD constexpr size_t qp_warp_smem_doubles(int N) { return (size_t)R_ROWS * qp_warp_chunk(N) * qp_warp_lanes(N, qp_warp_chunk(N)); }
+// exchange slots per lane behind the rows: one affine map (M 16, d 4); the scan element (A 16, C 10, J 10) is
+// exchanged through the rows R_K .. R_DZA, which are dead during the element scan (25*C >= 36 slots for C >= 2)
+QS_HD constexpr int qp_warp_xch_rows(int C) { return C >= 2 ? 20 : 36; }
+QS_HD constexpr size_t qp_warp_smem_doubles(int N) {
+    return ((size_t)R_ROWS * qp_warp_chunk(N) + qp_warp_xch_rows(qp_warp_chunk(N))) * qp_warp_lanes(N, qp_warp_chunk(N));
+}
 
 // ---- small dense helpers --------------------------------------------------------------------------
 // Cholesky of a packed symmetric positive SEMI-definite 4x4 (lower, LT indexing); non-positive pivots give
@@ -90,6 +96,18 @@ QS_HD void chol4_psd(const double A[10], double Lo[10], double id[4]) {
 }
 
 struct Elem { double A[16]; double C[10]; double J[10]; };   // A row-major, C and J packed lower
+
+// Exchange through shared memory instead of 64-bit shuffles (2 instructions per value instead of ~8):
+// every lane deposits n values in its column of the exchange area, the partner column is read after a
+// warp sync.  xch[c * L + lane].  Lanes outside [0, L) neither write nor read.
+template <class Ctx>
+QS_HD void xch_put(const Ctx& w, double* __restrict__ xch, int L, int lane, const double* v, int n0, int n) {
+    if (lane < L) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) xch[(size_t)(n0 + i) * L + lane] = v[i];
+    }
+    (void)w;
+}
 
 QS_HD void elem_identity(Elem& e) {
 #pragma unroll
@@ -295,19 +313,30 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
             for (int i = 0; i < 4; ++i) d[i] = dk[i];
         }
     }
-    // ---- (b) suffix scan over lanes; afterwards d = p at the first stage of the lane's chunk
+    // ---- (b) suffix scan over lanes (exchange through shared memory); afterwards d = p at the first stage of the chunk
+    double* xch = sm + (size_t)R_ROWS * C * Lw_;
 #pragma unroll 1
-    for (int dl = 1; dl < 32; dl <<= 1) {
-        double Mp[16], dp[4];
+    for (int dl = 1; dl < Lw_; dl <<= 1) {
+        w.sync();
+        xch_put(w, xch, Lw_, lane, M, 0, 16); xch_put(w, xch, Lw_, lane, d, 16, 4);
+        w.sync();
+        if (act && lane + dl < Lw_) {
+            double Mp[16], dp[4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) Mp[i] = w.shfl(M[i], lane + dl);
+            for (int i = 0; i < 16; ++i) Mp[i] = xch[(size_t)i * Lw_ + lane + dl];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) dp[i] = w.shfl(d[i], lane + dl);
-        if (act && lane + dl < Lw_) aff_compose(M, d, Mp, dp);
+            for (int i = 0; i < 4; ++i) dp[i] = xch[(size_t)(16 + i) * Lw_ + lane + dl];
+            aff_compose(M, d, Mp, dp);
+        }
     }
-    double pe[4];                                              // p at the right boundary of the chunk
+    w.sync();
+    xch_put(w, xch, Lw_, lane, d, 16, 4);
+    w.sync();
+    double pe[4] = {0, 0, 0, 0};                                // p at the right boundary of the chunk
+    if (act && lane + 1 < Lw_) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pe[i] = w.shfl(d[i], lane + 1);
+        for (int i = 0; i < 4; ++i) pe[i] = xch[(size_t)(16 + i) * Lw_ + lane + 1];
+    }
     // ---- (c) local back-substitution: k_ff and p_k
     if (act) {
 #pragma unroll 1
@@ -369,17 +398,27 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
         }
     }
 #pragma unroll 1
-    for (int dl = 1; dl < 32; dl <<= 1) {
-        double Mp[16], dp[4];
+    for (int dl = 1; dl < Lw_; dl <<= 1) {
+        w.sync();
+        xch_put(w, xch, Lw_, lane, M, 0, 16); xch_put(w, xch, Lw_, lane, d, 16, 4);
+        w.sync();
+        if (act && lane - dl >= 0) {
+            double Mp[16], dp[4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) Mp[i] = w.shfl(M[i], lane - dl);
+            for (int i = 0; i < 16; ++i) Mp[i] = xch[(size_t)i * Lw_ + lane - dl];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) dp[i] = w.shfl(d[i], lane - dl);
-        if (lane - dl >= 0) aff_compose(M, d, Mp, dp);
+            for (int i = 0; i < 4; ++i) dp[i] = xch[(size_t)(16 + i) * Lw_ + lane - dl];
+            aff_compose(M, d, Mp, dp);
+        }
     }
-    double x[4];                                               // dx at the first stage of the chunk (dx_0 = 0)
+    w.sync();
+    xch_put(w, xch, Lw_, lane, d, 16, 4);
+    w.sync();
+    double x[4] = {0, 0, 0, 0};                                // dx at the first stage of the chunk (dx_0 = 0)
+    if (act && lane >= 1) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { const double v = w.shfl(d[i], lane - 1); x[i] = (lane == 0) ? 0.0 : v; }
+        for (int i = 0; i < 4; ++i) x[i] = xch[(size_t)(16 + i) * Lw_ + lane - 1];
+    }
     if (act) {
 #pragma unroll 1
         for (int j = 0; j < C; ++j) {
@@ -408,16 +447,20 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
     (void)QNp;
 }
 
-// Solve the QP of problem V with one warp.  sm: qp_warp_smem_doubles(N) doubles of shared memory owned by
-// this warp.  Outputs like qp_ipm: V.z (du,dx), V.lam, V.t, V.pi (pi[k] = pi_{k+1}), res, iters, status.
+// Per-problem IPM state kept in registers across iterations (everything else lives in shared memory).
+struct QwState {
+    int it, stall, status;
+    double rmax_prev, r_stat, r_eq, r_in, r_cp;
+    double qN[4];
+};
+
+// ---- load the linearisation of problem V into the warp's shared memory, initial point
 template <class Ctx, int C>
-QS_HD void qp_ipm_warp(const Ctx& w, double* __restrict__ sm, const QpConst& Q, const QpView& V, bool valid_problem,
-                       int& iters_out, int& status_out, double res[4]) {
+QS_HD void qw_init(const Ctx& w, double* __restrict__ sm, const QpConst& Q, const QpView& V, QwState& st) {
     const int N = Q.N;
     const int lane = w.lane();
     const int Lw_ = qp_warp_lanes(N, C);
-    const bool act = valid_problem && lane < Lw_;
-    const int m_on = 6 * N - 2;
+    const bool act = lane < Lw_;
     // ---------------- load the linearisation, initial point
     if (act) {
 #pragma unroll 1
@@ -456,326 +499,359 @@ QS_HD void qp_ipm_warp(const Ctx& w, double* __restrict__ sm, const QpConst& Q, 
             }
         }
     }
-    double qN[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) qN[i] = V.qN[i * V.stride];
+    for (int i = 0; i < 4; ++i) st.qN[i] = V.qN[i * V.stride];
+    st.it = 0; st.stall = 0; st.status = 1; st.rmax_prev = 1e300;
+    st.r_stat = st.r_eq = st.r_in = st.r_cp = 0.0;
     w.sync();
 
-    int status = 1, it = 0, stall = 0;
-    double rmax_prev = 1e300;
-    double r_stat = 0.0, r_eq = 0.0, r_in = 0.0, r_cp = 0.0;
-    bool finished = !valid_problem;
-    for (;;) {
-        if (w.cta_all(finished)) break;                         // lockstep point of the CTA's warps
-        if (finished) continue;
-        // ================= (1) true residuals =================
-        double nx[4], npi[4];                                  // x and pi of the stage right of the chunk
+}
+
+// ---- one IPM iteration: true residuals + stopping tests, factorisation (parallel-in-time), predictor,
+// corrector, step.  Returns true when the problem is finished (st.status set), false to continue.
+template <class Ctx, int C>
+QS_HD bool qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, QwState& st) {
+    const int N = Q.N;
+    const int lane = w.lane();
+    const int Lw_ = qp_warp_lanes(N, C);
+    const bool act = lane < Lw_;
+    const int m_on = 6 * N - 2;
+    int& status = st.status; int& it = st.it; int& stall = st.stall;
+    double& rmax_prev = st.rmax_prev; double& r_stat = st.r_stat; double& r_eq = st.r_eq; double& r_in = st.r_in; double& r_cp = st.r_cp;
+    const double* qN = st.qN;
+    {
+    // ================= (1) true residuals =================
+    double nx[4] = {0, 0, 0, 0}, npi[4] = {0, 0, 0, 0};    // x and pi of the stage right of the chunk (neighbour lane, j = 0)
+    w.sync();
+    if (act && lane + 1 < Lw_) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            nx[i] = w.shfl(act ? QW_SM(R_Z + 2 + i, 0) : 0.0, lane + 1);
-            npi[i] = w.shfl(act ? QW_SM(R_PIK + i, 0) : 0.0, lane + 1);
+            nx[i] = sm[((size_t)(R_Z + 2 + i) * C + 0) * Lw_ + lane + 1];
+            npi[i] = sm[((size_t)(R_PIK + i) * C + 0) * Lw_ + lane + 1];
         }
-        double l_stat = 0.0, l_eq = 0.0, l_in = 0.0, l_cp = 0.0, l_mu = 0.0;
-        bool l_nan = false;
-        if (act) {
+    }
+    double l_stat = 0.0, l_eq = 0.0, l_in = 0.0, l_cp = 0.0, l_mu = 0.0;
+    bool l_nan = false;
+    if (act) {
 #pragma unroll 1
-            for (int j = C - 1; j >= 0; --j) {
-                const int k = lane * C + j;
-                if (k > N) continue;
-                double z6[6], pik[4];
+        for (int j = C - 1; j >= 0; --j) {
+            const int k = lane * C + j;
+            if (k > N) continue;
+            double z6[6], pik[4];
 #pragma unroll
-                for (int i = 0; i < 6; ++i) z6[i] = QW_SM(R_Z + i, j);
+            for (int i = 0; i < 6; ++i) z6[i] = QW_SM(R_Z + i, j);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) pik[i] = QW_SM(R_PIK + i, j);
-                if (k == N) {
-                    double xN[4] = {z6[2], z6[3], z6[4], z6[5]}, rg[4];
-                    sym4_mul(Q.QN, xN, rg);
+            for (int i = 0; i < 4; ++i) pik[i] = QW_SM(R_PIK + i, j);
+            if (k == N) {
+                double xN[4] = {z6[2], z6[3], z6[4], z6[5]}, rg[4];
+                sym4_mul(Q.QN, xN, rg);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { rg[i] += qN[i] - pik[i]; QW_SM(R_RG + 2 + i, j) = rg[i]; l_stat = fmax(l_stat, fabs(rg[i])); l_nan = l_nan || !(rg[i] == rg[i]); }
-                } else {
-                    StageLin L;
+                for (int i = 0; i < 4; ++i) { rg[i] += qN[i] - pik[i]; QW_SM(R_RG + 2 + i, j) = rg[i]; l_stat = fmax(l_stat, fabs(rg[i])); l_nan = l_nan || !(rg[i] == rg[i]); }
+            } else {
+                StageLin L;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
-                    const double* Hk = Q.H + (size_t)k * 21;
-                    double gh[6], rg[6];
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) {
-                        double a = QW_SM(R_G + i, j);
-#pragma unroll
-                        for (int q = 0; q < 6; ++q) a = fma(Hk[LT(i, q)], z6[q], a);
-                        gh[i] = a;
-                    }
-                    lin_T_mul_add(L, npi, gh, rg);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) rg[2 + i] -= pik[i];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        if (k == 0 && c == 0) continue;
-                        const double h = QW_SM(R_HH + c, j), v = z6[cidx(c)];
-                        const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
-                        rg[cidx(c)] += lu - ll;
-                        const double rdl = v - (Q.lh[c] - h) - tl, rdu = (Q.uh[c] - h) - v - tu;
-                        l_in = fmax(l_in, fmax(fabs(rdl), fabs(rdu)));
-                        l_cp = fmax(l_cp, fmax(ll * tl, lu * tu));
-                        l_mu += ll * tl + lu * tu;
-                    }
-                    if (k == 0) { rg[2] = 0.0; rg[3] = 0.0; rg[4] = 0.0; rg[5] = 0.0; }
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) { QW_SM(R_RG + i, j) = rg[i]; l_stat = fmax(l_stat, fabs(rg[i])); l_nan = l_nan || !(rg[i] == rg[i]); }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        double a = QW_SM(R_BV + i, j) + (i < 2 ? z6[2 + i] : 0.0) - nx[i];
-                        a = fma(L.a3[i], z6[4], a); a = fma(L.a4[i], z6[5], a);
-                        a = fma(L.b1[i], z6[0], a); a = fma(L.b2[i], z6[1], a);
-                        QW_SM(R_RB + i, j) = a; l_eq = fmax(l_eq, fabs(a)); l_nan = l_nan || !(a == a);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { nx[i] = z6[2 + i]; npi[i] = pik[i]; }
-            }
-        }
-        r_stat = w.wmax(l_stat); r_eq = w.wmax(l_eq); r_in = w.wmax(l_in); r_cp = w.wmax(l_cp);
-        const double mu_sum = w.wsum(l_mu);
-        const double mu = mu_sum / (double)m_on;
-        if (w.wany(l_nan ? 1 : 0) || !(mu == mu)) { status = 2; finished = true; continue; }
-        if (r_stat < Q.tol && r_eq < Q.tol && r_in < Q.tol && r_cp < Q.tol) { status = 0; finished = true; continue; }
-        {
-            const double rmax = fmax(fmax(r_stat, r_eq), fmax(r_in, r_cp));
-            if (rmax < 0.5 * rmax_prev) { rmax_prev = rmax; stall = 0; } else ++stall;
-            if (stall >= 5 && rmax < QS_QP_TOL_ACCEPT) { status = 0; finished = true; continue; }
-        }
-        if (it >= Q.max_iter) { status = 1; finished = true; continue; }
-        // ================= (2) barrier terms, affine rhs, stage elements, chunk aggregate =================
-        Elem E; elem_identity(E);
-        if (act) {
-#pragma unroll 1
-            for (int j = C - 1; j >= 0; --j) {
-                const int k = lane * C + j;
-                if (k > N) continue;
-                if (k == N) {                                   // terminal value function: J = Q_N, A = 0, C = 0
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) E.A[i] = 0.0;
-#pragma unroll
-                    for (int i = 0; i < 10; ++i) { E.C[i] = 0.0; E.J[i] = Q.QN[i]; }
-                    continue;
-                }
+                for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
                 const double* Hk = Q.H + (size_t)k * 21;
-                double D[3], gt[6];
+                double gh[6], rg[6];
 #pragma unroll
-                for (int i = 0; i < 6; ++i) gt[i] = QW_SM(R_RG + i, j);
+                for (int i = 0; i < 6; ++i) {
+                    double a = QW_SM(R_G + i, j);
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) a = fma(Hk[LT(i, q)], z6[q], a);
+                    gh[i] = a;
+                }
+                lin_T_mul_add(L, npi, gh, rg);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rg[2 + i] -= pik[i];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const double h = QW_SM(R_HH + c, j), v = QW_SM(R_Z + cidx(c), j);
+                    if (k == 0 && c == 0) continue;
+                    const double h = QW_SM(R_HH + c, j), v = z6[cidx(c)];
                     const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
-                    const double itl = 1.0 / tl, itu = 1.0 / tu;
-                    const bool on = !(k == 0 && c == 0);
-                    const double rdl = on ? v - (Q.lh[c] - h) - tl : 0.0, rdu = on ? (Q.uh[c] - h) - v - tu : 0.0;
-                    D[c] = ll * itl + lu * itu;
-                    gt[cidx(c)] += (ll + ll * rdl * itl) - (lu + lu * rdu * itu);
+                    rg[cidx(c)] += lu - ll;
+                    const double rdl = v - (Q.lh[c] - h) - tl, rdu = (Q.uh[c] - h) - v - tu;
+                    l_in = fmax(l_in, fmax(fabs(rdl), fabs(rdu)));
+                    l_cp = fmax(l_cp, fmax(ll * tl, lu * tu));
+                    l_mu += ll * tl + lu * tu;
                 }
+                if (k == 0) { rg[2] = 0.0; rg[3] = 0.0; rg[4] = 0.0; rg[5] = 0.0; }
 #pragma unroll
-                for (int i = 0; i < 6; ++i) QW_SM(R_GT + i, j) = gt[i];
-                // element of stage k: eliminate u.  Rt = H_uu + D_u, S = H_ux, Qt = H_xx + D_s
-                const double r00 = Hk[LT(0, 0)] + D[1], r10 = Hk[LT(1, 0)], r11 = Hk[LT(1, 1)] + D[2];
-                const double i00 = qs_rsqrt(r00), l10 = r10 * i00, i11 = qs_rsqrt(r11 - l10 * l10);
-                StageLin L;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
-                // Bh = B Lr^-T  (4x2):  columns of B R^-1 B' = Bh Bh'
-                double bh0[4], bh1[4], sh0[4], sh1[4];             // Sh = Lr^-1 S (2x4)
+                for (int i = 0; i < 6; ++i) { QW_SM(R_RG + i, j) = rg[i]; l_stat = fmax(l_stat, fabs(rg[i])); l_nan = l_nan || !(rg[i] == rg[i]); }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    bh0[i] = L.b1[i] * i00; bh1[i] = (L.b2[i] - l10 * bh0[i]) * i11;
-                    const double s0 = Hk[LT(2 + i, 0)], s1 = Hk[LT(2 + i, 1)];
-                    sh0[i] = s0 * i00; sh1[i] = (s1 - l10 * sh0[i]) * i11;
+                    double a = QW_SM(R_BV + i, j) + (i < 2 ? z6[2 + i] : 0.0) - nx[i];
+                    a = fma(L.a3[i], z6[4], a); a = fma(L.a4[i], z6[5], a);
+                    a = fma(L.b1[i], z6[0], a); a = fma(L.b2[i], z6[1], a);
+                    QW_SM(R_RB + i, j) = a; l_eq = fmax(l_eq, fabs(a)); l_nan = l_nan || !(a == a);
                 }
-                Elem e;
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const double a = (q == 0) ? (i == 0 ? 1.0 : 0.0) : (q == 1) ? (i == 1 ? 1.0 : 0.0) : (q == 2 ? L.a3[i] : L.a4[i]);
-                        e.A[4 * i + q] = a - fma(bh0[i], sh0[q], bh1[i] * sh1[q]);
-                    }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int q = 0; q <= i; ++q) {
-                        e.C[LT(i, q)] = fma(bh0[i], bh0[q], bh1[i] * bh1[q]);
-                        e.J[LT(i, q)] = Hk[LT(2 + i, 2 + q)] - fma(sh0[i], sh0[q], sh1[i] * sh1[q]);
-                    }
-                e.J[LT(3, 3)] += D[0];
-                if (k == 0) {
-                    // x_0 is fixed (dx_0 = 0): only the reachable-set part matters; keep J finite and PSD
-                }
-                elem_combine(e, E.A, E.C, E.J);                  // E <- e (x) E
-                E = e;
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { nx[i] = z6[2 + i]; npi[i] = pik[i]; }
         }
-        // ================= (3) suffix scan of the chunk aggregates =================
+    }
+    r_stat = w.wmax(l_stat); r_eq = w.wmax(l_eq); r_in = w.wmax(l_in); r_cp = w.wmax(l_cp);
+    const double mu_sum = w.wsum(l_mu);
+    const double mu = mu_sum / (double)m_on;
+    if (w.wany(l_nan ? 1 : 0) || !(mu == mu)) { status = 2; return true; }
+    if (r_stat < Q.tol && r_eq < Q.tol && r_in < Q.tol && r_cp < Q.tol) { status = 0; return true; }
+    {
+        const double rmax = fmax(fmax(r_stat, r_eq), fmax(r_in, r_cp));
+        if (rmax < 0.5 * rmax_prev) { rmax_prev = rmax; stall = 0; } else ++stall;
+        if (stall >= 5 && rmax < QS_QP_TOL_ACCEPT) { status = 0; return true; }
+    }
+    if (it >= Q.max_iter) { status = 1; return true; }
+    // ================= (2) barrier terms, affine rhs, stage elements, chunk aggregate =================
+    Elem E; elem_identity(E);
+    if (act) {
 #pragma unroll 1
-        for (int dl = 1; dl < 32; dl <<= 1) {
+        for (int j = C - 1; j >= 0; --j) {
+            const int k = lane * C + j;
+            if (k > N) continue;
+            if (k == N) {                                   // terminal value function: J = Q_N, A = 0, C = 0
+#pragma unroll
+                for (int i = 0; i < 16; ++i) E.A[i] = 0.0;
+#pragma unroll
+                for (int i = 0; i < 10; ++i) { E.C[i] = 0.0; E.J[i] = Q.QN[i]; }
+                continue;
+            }
+            const double* Hk = Q.H + (size_t)k * 21;
+            double D[3], gt[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) gt[i] = QW_SM(R_RG + i, j);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double h = QW_SM(R_HH + c, j), v = QW_SM(R_Z + cidx(c), j);
+                const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
+                const double itl = 1.0 / tl, itu = 1.0 / tu;
+                const bool on = !(k == 0 && c == 0);
+                const double rdl = on ? v - (Q.lh[c] - h) - tl : 0.0, rdu = on ? (Q.uh[c] - h) - v - tu : 0.0;
+                D[c] = ll * itl + lu * itu;
+                gt[cidx(c)] += (ll + ll * rdl * itl) - (lu + lu * rdu * itu);
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) QW_SM(R_GT + i, j) = gt[i];
+            // element of stage k: eliminate u.  Rt = H_uu + D_u, S = H_ux, Qt = H_xx + D_s
+            const double r00 = Hk[LT(0, 0)] + D[1], r10 = Hk[LT(1, 0)], r11 = Hk[LT(1, 1)] + D[2];
+            const double i00 = qs_rsqrt(r00), l10 = r10 * i00, i11 = qs_rsqrt(r11 - l10 * l10);
+            StageLin L;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
+            // Bh = B Lr^-T  (4x2):  columns of B R^-1 B' = Bh Bh'
+            double bh0[4], bh1[4], sh0[4], sh1[4];             // Sh = Lr^-1 S (2x4)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                bh0[i] = L.b1[i] * i00; bh1[i] = (L.b2[i] - l10 * bh0[i]) * i11;
+                const double s0 = Hk[LT(2 + i, 0)], s1 = Hk[LT(2 + i, 1)];
+                sh0[i] = s0 * i00; sh1[i] = (s1 - l10 * sh0[i]) * i11;
+            }
+            Elem e;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double a = (q == 0) ? (i == 0 ? 1.0 : 0.0) : (q == 1) ? (i == 1 ? 1.0 : 0.0) : (q == 2 ? L.a3[i] : L.a4[i]);
+                    e.A[4 * i + q] = a - fma(bh0[i], sh0[q], bh1[i] * sh1[q]);
+                }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int q = 0; q <= i; ++q) {
+                    e.C[LT(i, q)] = fma(bh0[i], bh0[q], bh1[i] * bh1[q]);
+                    e.J[LT(i, q)] = Hk[LT(2 + i, 2 + q)] - fma(sh0[i], sh0[q], sh1[i] * sh1[q]);
+                }
+            e.J[LT(3, 3)] += D[0];
+            if (k == 0) {
+                // x_0 is fixed (dx_0 = 0): only the reachable-set part matters; keep J finite and PSD
+            }
+            elem_combine(e, E.A, E.C, E.J);                  // E <- e (x) E
+            E = e;
+        }
+    }
+    // ================= (3) suffix scan of the chunk aggregates =================
+    double* xch = (C >= 2) ? sm + (size_t)R_K * C * Lw_ : sm + (size_t)R_ROWS * C * Lw_;
+#pragma unroll 1
+    for (int dl = 1; dl < Lw_; dl <<= 1) {
+        w.sync();
+        xch_put(w, xch, Lw_, lane, E.A, 0, 16); xch_put(w, xch, Lw_, lane, E.C, 16, 10); xch_put(w, xch, Lw_, lane, E.J, 26, 10);
+        w.sync();
+        if (act && lane + dl < Lw_) {
             double A2[16], C2[10], J2[10];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) A2[i] = w.shfl(E.A[i], lane + dl);
+            for (int i = 0; i < 16; ++i) A2[i] = xch[(size_t)i * Lw_ + lane + dl];
 #pragma unroll
-            for (int i = 0; i < 10; ++i) { C2[i] = w.shfl(E.C[i], lane + dl); J2[i] = w.shfl(E.J[i], lane + dl); }
-            if (act && lane + dl < Lw_) elem_combine(E, A2, C2, J2);
+            for (int i = 0; i < 10; ++i) { C2[i] = xch[(size_t)(16 + i) * Lw_ + lane + dl]; J2[i] = xch[(size_t)(26 + i) * Lw_ + lane + dl]; }
+            elem_combine(E, A2, C2, J2);
         }
-        double P[10];                                          // P at the right boundary of the chunk
+    }
+    w.sync();
+    xch_put(w, xch, Lw_, lane, E.J, 26, 10);
+    w.sync();
+    double P[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};          // P at the right boundary of the chunk
+    if (act && lane + 1 < Lw_) {
 #pragma unroll
-        for (int i = 0; i < 10; ++i) P[i] = w.shfl(E.J[i], lane + 1);
-        // ================= (4) local Riccati over the chunk: K_k, Cholesky, P_k, P_{k+1} r_b =================
-        bool ok = true;
-        if (act) {
+        for (int i = 0; i < 10; ++i) P[i] = xch[(size_t)(26 + i) * Lw_ + lane + 1];
+    }
+    // ================= (4) local Riccati over the chunk: K_k, Cholesky, P_k, P_{k+1} r_b =================
+    bool ok = true;
+    if (act) {
 #pragma unroll 1
-            for (int j = C - 1; j >= 0; --j) {
-                const int k = lane * C + j;
-                if (k > N) continue;
-                if (k == N) {
+        for (int j = C - 1; j >= 0; --j) {
+            const int k = lane * C + j;
+            if (k > N) continue;
+            if (k == N) {
 #pragma unroll
-                    for (int i = 0; i < 10; ++i) { P[i] = Q.QN[i]; QW_SM(R_P + i, j) = P[i]; }
-                    continue;
-                }
-                StageLin L;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
-                double D[3], rb[4], Pb[4], K0[4], K1[4], Li[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) D[c] = QW_SM(R_LAM + c, j) / QW_SM(R_T + c, j) + QW_SM(R_LAM + 3 + c, j) / QW_SM(R_T + 3 + c, j);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) rb[i] = QW_SM(R_RB + i, j);
-                sym4_mul(P, rb, Pb);
-                ok = riccati_factor_stage(L, Q.H + (size_t)k * 21, D, P, K0, K1, Li) && ok;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { QW_SM(R_K + i, j) = K0[i]; QW_SM(R_K + 4 + i, j) = K1[i]; QW_SM(R_PB + i, j) = Pb[i]; }
-#pragma unroll
-                for (int i = 0; i < 3; ++i) QW_SM(R_LI + i, j) = Li[i];
-#pragma unroll
-                for (int i = 0; i < 10; ++i) QW_SM(R_P + i, j) = P[i];
+                for (int i = 0; i < 10; ++i) { P[i] = Q.QN[i]; QW_SM(R_P + i, j) = P[i]; }
+                continue;
             }
+            StageLin L;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
+            double D[3], rb[4], Pb[4], K0[4], K1[4], Li[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) D[c] = QW_SM(R_LAM + c, j) / QW_SM(R_T + c, j) + QW_SM(R_LAM + 3 + c, j) / QW_SM(R_T + 3 + c, j);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rb[i] = QW_SM(R_RB + i, j);
+            sym4_mul(P, rb, Pb);
+            ok = riccati_factor_stage(L, Q.H + (size_t)k * 21, D, P, K0, K1, Li) && ok;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { QW_SM(R_K + i, j) = K0[i]; QW_SM(R_K + 4 + i, j) = K1[i]; QW_SM(R_PB + i, j) = Pb[i]; }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) QW_SM(R_LI + i, j) = Li[i];
+#pragma unroll
+            for (int i = 0; i < 10; ++i) QW_SM(R_P + i, j) = P[i];
         }
-        if (w.wany(ok ? 0 : 1)) { status = 2; finished = true; continue; }
-        // ================= (5)-(7) predictor and corrector share ONE copy of the solve code =================
-        double smu = 0.0;
+    }
+    if (w.wany(ok ? 0 : 1)) { status = 2; return true; }
+    // ================= (5)-(7) predictor and corrector share ONE copy of the solve code =================
+    double smu = 0.0;
 #pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            if (pass == 1 && act) {
-                // corrector rhs
-#pragma unroll 1
-                for (int j = 0; j < C; ++j) {
-                    const int k = lane * C + j;
-                    if (k >= N) continue;
-                    double gt[6];
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) gt[i] = QW_SM(R_RG + i, j);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        if (k == 0 && c == 0) continue;
-                        const double h = QW_SM(R_HH + c, j), v = QW_SM(R_Z + cidx(c), j), dva = QW_SM(R_DZA + c, j);
-                        const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
-                        const double rdl = v - (Q.lh[c] - h) - tl, rdu = (Q.uh[c] - h) - v - tu;
-                        const double dtl = dva + rdl, dtu = -dva + rdu;
-                        const double cl = (-ll - ll * dtl / tl) * dtl, cu = (-lu - lu * dtu / tu) * dtu;
-                        gt[cidx(c)] += (ll * tl - smu + cl + ll * rdl) / tl - (lu * tu - smu + cu + lu * rdu) / tu;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) QW_SM(R_GT + i, j) = gt[i];
-                }
-            }
-            qp_warp_solve<Ctx, C>(w, sm, N, Lw_, Q.QN);
-            if (pass == 0) {
-                // step to the boundary of the affine step, mu_aff, centering parameter
-                double a_aff = 1.0, S1 = 0.0, S2 = 0.0;
-                if (act) {
-#pragma unroll 1
-                    for (int j = 0; j < C; ++j) {
-                        const int k = lane * C + j;
-                        if (k >= N) continue;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const double dva = QW_SM(R_GT + cidx(c), j);
-                            QW_SM(R_DZA + c, j) = dva;
-                            if (k == 0 && c == 0) continue;
-                            const double h = QW_SM(R_HH + c, j), v = QW_SM(R_Z + cidx(c), j);
-                            const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
-                            const double dtl = dva + (v - (Q.lh[c] - h) - tl), dtu = -dva + ((Q.uh[c] - h) - v - tu);
-                            const double dll = -ll - ll * dtl / tl, dlu = -lu - lu * dtu / tu;
-                            if (dtl < 0.0) a_aff = fmin(a_aff, -tl / dtl);
-                            if (dtu < 0.0) a_aff = fmin(a_aff, -tu / dtu);
-                            if (dll < 0.0) a_aff = fmin(a_aff, -ll / dll);
-                            if (dlu < 0.0) a_aff = fmin(a_aff, -lu / dlu);
-                            S1 += ll * dtl + tl * dll + lu * dtu + tu * dlu;
-                            S2 += dll * dtl + dlu * dtu;
-                        }
-                    }
-                }
-                a_aff = w.wmin(a_aff); S1 = w.wsum(S1); S2 = w.wsum(S2);
-                const double mu_aff = (mu_sum + a_aff * (S1 + a_aff * S2)) / (double)m_on;
-                double sigma = (mu > 0.0) ? mu_aff / mu : 0.0;
-                sigma = sigma * sigma * sigma;
-                smu = fmax(sigma * mu, 0.1 * Q.tol);
-            }
-        }
-        // ================= (8) step length and update =================
-        double a_max = 1.0;
-        if (act) {
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1 && act) {
+            // corrector rhs
 #pragma unroll 1
             for (int j = 0; j < C; ++j) {
                 const int k = lane * C + j;
                 if (k >= N) continue;
+                double gt[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) gt[i] = QW_SM(R_RG + i, j);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     if (k == 0 && c == 0) continue;
-                    IneqStep s_ = ineq_step(QW_SM(R_Z + cidx(c), j), QW_SM(R_DZA + c, j), QW_SM(R_GT + cidx(c), j),
-                                            QW_SM(R_LAM + c, j), QW_SM(R_LAM + 3 + c, j), QW_SM(R_T + c, j), QW_SM(R_T + 3 + c, j),
-                                            Q.lh[c] - QW_SM(R_HH + c, j), Q.uh[c] - QW_SM(R_HH + c, j), smu);
-                    if (s_.dtl < 0.0) a_max = fmin(a_max, -QW_SM(R_T + c, j) / s_.dtl);
-                    if (s_.dtu < 0.0) a_max = fmin(a_max, -QW_SM(R_T + 3 + c, j) / s_.dtu);
-                    if (s_.dll < 0.0) a_max = fmin(a_max, -QW_SM(R_LAM + c, j) / s_.dll);
-                    if (s_.dlu < 0.0) a_max = fmin(a_max, -QW_SM(R_LAM + 3 + c, j) / s_.dlu);
+                    const double h = QW_SM(R_HH + c, j), v = QW_SM(R_Z + cidx(c), j), dva = QW_SM(R_DZA + c, j);
+                    const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
+                    const double rdl = v - (Q.lh[c] - h) - tl, rdu = (Q.uh[c] - h) - v - tu;
+                    const double dtl = dva + rdl, dtu = -dva + rdu;
+                    const double cl = (-ll - ll * dtl / tl) * dtl, cu = (-lu - lu * dtu / tu) * dtu;
+                    gt[cidx(c)] += (ll * tl - smu + cl + ll * rdl) / tl - (lu * tu - smu + cu + lu * rdu) / tu;
                 }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) QW_SM(R_GT + i, j) = gt[i];
             }
         }
-        a_max = w.wmin(a_max);
-        const double alpha = fmin(1.0, Q.tau * a_max);
-        if (!(alpha == alpha)) { status = 2; finished = true; continue; }
-        if (act) {
+        qp_warp_solve<Ctx, C>(w, sm, N, Lw_, Q.QN);
+        if (pass == 0) {
+            // step to the boundary of the affine step, mu_aff, centering parameter
+            double a_aff = 1.0, S1 = 0.0, S2 = 0.0;
+            if (act) {
 #pragma unroll 1
-            for (int j = 0; j < C; ++j) {
-                const int k = lane * C + j;
-                if (k > N) continue;
-                double dz[6];
-#pragma unroll
-                for (int i = 0; i < 6; ++i) dz[i] = QW_SM(R_GT + i, j);
-                if (k >= 1) {                                   // dpi_k = P_k dx_k + p_k
-                    double Pk[10], dxk[4] = {dz[2], dz[3], dz[4], dz[5]}, dp[4];
-#pragma unroll
-                    for (int i = 0; i < 10; ++i) Pk[i] = QW_SM(R_P + i, j);
-                    sym4_mul(Pk, dxk, dp);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) QW_SM(R_PIK + i, j) = fma(alpha, dp[i] + QW_SM(R_PV + i, j), QW_SM(R_PIK + i, j));
-                }
-                if (k < N) {
+                for (int j = 0; j < C; ++j) {
+                    const int k = lane * C + j;
+                    if (k >= N) continue;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
+                        const double dva = QW_SM(R_GT + cidx(c), j);
+                        QW_SM(R_DZA + c, j) = dva;
                         if (k == 0 && c == 0) continue;
-                        IneqStep s_ = ineq_step(QW_SM(R_Z + cidx(c), j), QW_SM(R_DZA + c, j), dz[cidx(c)],
-                                                QW_SM(R_LAM + c, j), QW_SM(R_LAM + 3 + c, j), QW_SM(R_T + c, j), QW_SM(R_T + 3 + c, j),
-                                                Q.lh[c] - QW_SM(R_HH + c, j), Q.uh[c] - QW_SM(R_HH + c, j), smu);
-                        QW_SM(R_T + c, j) = fma(alpha, s_.dtl, QW_SM(R_T + c, j));
-                        QW_SM(R_T + 3 + c, j) = fma(alpha, s_.dtu, QW_SM(R_T + 3 + c, j));
-                        QW_SM(R_LAM + c, j) = fma(alpha, s_.dll, QW_SM(R_LAM + c, j));
-                        QW_SM(R_LAM + 3 + c, j) = fma(alpha, s_.dlu, QW_SM(R_LAM + 3 + c, j));
+                        const double h = QW_SM(R_HH + c, j), v = QW_SM(R_Z + cidx(c), j);
+                        const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
+                        const double dtl = dva + (v - (Q.lh[c] - h) - tl), dtu = -dva + ((Q.uh[c] - h) - v - tu);
+                        const double dll = -ll - ll * dtl / tl, dlu = -lu - lu * dtu / tu;
+                        if (dtl < 0.0) a_aff = fmin(a_aff, -tl / dtl);
+                        if (dtu < 0.0) a_aff = fmin(a_aff, -tu / dtu);
+                        if (dll < 0.0) a_aff = fmin(a_aff, -ll / dll);
+                        if (dlu < 0.0) a_aff = fmin(a_aff, -lu / dlu);
+                        S1 += ll * dtl + tl * dll + lu * dtu + tu * dlu;
+                        S2 += dll * dtl + dlu * dtu;
                     }
                 }
+            }
+            a_aff = w.wmin(a_aff); S1 = w.wsum(S1); S2 = w.wsum(S2);
+            const double mu_aff = (mu_sum + a_aff * (S1 + a_aff * S2)) / (double)m_on;
+            double sigma = (mu > 0.0) ? mu_aff / mu : 0.0;
+            sigma = sigma * sigma * sigma;
+            smu = fmax(sigma * mu, 0.1 * Q.tol);
+        }
+    }
+    // ================= (8) step length and update =================
+    double a_max = 1.0;
+    if (act) {
+#pragma unroll 1
+        for (int j = 0; j < C; ++j) {
+            const int k = lane * C + j;
+            if (k >= N) continue;
 #pragma unroll
-                for (int i = 0; i < 6; ++i) QW_SM(R_Z + i, j) = fma(alpha, dz[i], QW_SM(R_Z + i, j));
+            for (int c = 0; c < 3; ++c) {
+                if (k == 0 && c == 0) continue;
+                IneqStep s_ = ineq_step(QW_SM(R_Z + cidx(c), j), QW_SM(R_DZA + c, j), QW_SM(R_GT + cidx(c), j),
+                                        QW_SM(R_LAM + c, j), QW_SM(R_LAM + 3 + c, j), QW_SM(R_T + c, j), QW_SM(R_T + 3 + c, j),
+                                        Q.lh[c] - QW_SM(R_HH + c, j), Q.uh[c] - QW_SM(R_HH + c, j), smu);
+                if (s_.dtl < 0.0) a_max = fmin(a_max, -QW_SM(R_T + c, j) / s_.dtl);
+                if (s_.dtu < 0.0) a_max = fmin(a_max, -QW_SM(R_T + 3 + c, j) / s_.dtu);
+                if (s_.dll < 0.0) a_max = fmin(a_max, -QW_SM(R_LAM + c, j) / s_.dll);
+                if (s_.dlu < 0.0) a_max = fmin(a_max, -QW_SM(R_LAM + 3 + c, j) / s_.dlu);
             }
         }
-        w.sync();
-        ++it;
     }
+    a_max = w.wmin(a_max);
+    const double alpha = fmin(1.0, Q.tau * a_max);
+    if (!(alpha == alpha)) { status = 2; return true; }
+    if (act) {
+#pragma unroll 1
+        for (int j = 0; j < C; ++j) {
+            const int k = lane * C + j;
+            if (k > N) continue;
+            double dz[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) dz[i] = QW_SM(R_GT + i, j);
+            if (k >= 1) {                                   // dpi_k = P_k dx_k + p_k
+                double Pk[10], dxk[4] = {dz[2], dz[3], dz[4], dz[5]}, dp[4];
+#pragma unroll
+                for (int i = 0; i < 10; ++i) Pk[i] = QW_SM(R_P + i, j);
+                sym4_mul(Pk, dxk, dp);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) QW_SM(R_PIK + i, j) = fma(alpha, dp[i] + QW_SM(R_PV + i, j), QW_SM(R_PIK + i, j));
+            }
+            if (k < N) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (k == 0 && c == 0) continue;
+                    IneqStep s_ = ineq_step(QW_SM(R_Z + cidx(c), j), QW_SM(R_DZA + c, j), dz[cidx(c)],
+                                            QW_SM(R_LAM + c, j), QW_SM(R_LAM + 3 + c, j), QW_SM(R_T + c, j), QW_SM(R_T + 3 + c, j),
+                                            Q.lh[c] - QW_SM(R_HH + c, j), Q.uh[c] - QW_SM(R_HH + c, j), smu);
+                    QW_SM(R_T + c, j) = fma(alpha, s_.dtl, QW_SM(R_T + c, j));
+                    QW_SM(R_T + 3 + c, j) = fma(alpha, s_.dtu, QW_SM(R_T + 3 + c, j));
+                    QW_SM(R_LAM + c, j) = fma(alpha, s_.dll, QW_SM(R_LAM + c, j));
+                    QW_SM(R_LAM + 3 + c, j) = fma(alpha, s_.dlu, QW_SM(R_LAM + 3 + c, j));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) QW_SM(R_Z + i, j) = fma(alpha, dz[i], QW_SM(R_Z + i, j));
+        }
+    }
+    w.sync();
+    ++it;
+    return false;
+    }
+}
+
+// ---- write the point back to the slabs: V.z (du, dx), V.pi (pi[k] = pi_{k+1}), V.lam, V.t
+template <class Ctx, int C>
+QS_HD void qw_writeback(const Ctx& w, double* __restrict__ sm, const QpConst& Q, const QpView& V) {
+    const int N = Q.N;
+    const int lane = w.lane();
+    const int Lw_ = qp_warp_lanes(N, C);
+    const bool act = lane < Lw_;
     // ---------------- write the point back to the slabs
     if (act) {
 #pragma unroll 1
@@ -794,8 +870,6 @@ QS_HD void qp_ipm_warp(const Ctx& w, double* __restrict__ sm, const QpConst& Q, 
             }
         }
     }
-    iters_out = it; status_out = status;
-    res[0] = r_stat; res[1] = r_eq; res[2] = r_in; res[3] = r_cp;
 }
 
 }  // namespace qs

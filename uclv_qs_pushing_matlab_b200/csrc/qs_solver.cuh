@@ -33,7 +33,7 @@ struct SolverDev {
     const double *QN;       // [10]
     double lh[3], uh[3];
     // bookkeeping
-    int *status, *sqp_iter, *qp_iter, *cold, *done, *qpstat, *ndone;
+    int *status, *sqp_iter, *qp_iter, *cold, *done, *qpstat, *ndone;   // ndone[0]: SQP finished count, ndone[1]: QP work-queue head
     double *cost, *res, *alpha;
     // SQP merit weights
     double *wpi, *wlam, *wx0;
@@ -220,61 +220,74 @@ QS_HD void qp_one(const SolverDev& S, const IpmOpts& o, int b, int apply) {
     S.status[b] = nan ? 1 : (status == 2 ? 4 : 0);     // QP iteration limit is tolerated
 }
 
-// K4 (+ K5 in RTI mode), warp-per-problem version: all 32 lanes call this for problem b; sm = the warp's
-// shared-memory state (qp_warp_smem_doubles(N) doubles).
-template <class Ctx, int C>
-QS_HD void qp_one_warp(const Ctx& w, double* __restrict__ sm, const SolverDev& S, const IpmOpts& o, int b_in, int apply) {
-    const bool valid = b_in < S.B && !(S.done && S.done[b_in < S.B ? b_in : 0]);
-    const int b = valid ? b_in : 0;                             // idle warps of a CTA still take part in its barriers
+// K4 (+ K5 in RTI mode), warp-per-problem version, persistent: every warp of a CTA owns one problem at a
+// time and pulls the next one from a work queue when it finishes (`next` returns a warp-uniform problem
+// index or -1), while one CTA-wide vote per IPM iteration keeps the warps in lockstep (shared instruction
+// fetches).  sm = the warp's shared-memory state (qp_warp_smem_doubles(N) doubles).
+template <class Ctx, int C, class NextFn>
+QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm, const SolverDev& S, const IpmOpts& o, int apply, NextFn next) {
     QpConst Qc;
     Qc.N = S.N; Qc.H = S.H; Qc.QN = S.QN;
 #pragma unroll
     for (int i = 0; i < 3; ++i) { Qc.lh[i] = S.lh[i]; Qc.uh[i] = S.uh[i]; }
     Qc.max_iter = o.max_iter; Qc.tol = o.tol; Qc.mu0 = o.mu0; Qc.thr = o.thr; Qc.tau = o.tau;
-    QpView V;
-    V.stride = (size_t)S.Bp;
-    V.A = S.A + b; V.B = S.Bm + b; V.b = S.b + b; V.g = S.g + b; V.qN = S.qN + b; V.dx0 = S.dx0 + b;
-    V.x = S.x + b; V.u = S.u + b;
-    V.z = S.z + b; V.zp = S.zp + b; V.zc = S.zc + b; V.t = S.t + b;
-    V.K = S.K + b; V.Li = S.Li + b; V.Pb = S.Pb + b; V.kff = S.kff + b;
-    V.rg = S.rg + b; V.rb = S.rb + b; V.rgs = S.rgs + b;
-    V.lam = (apply ? S.lam : S.lamq) + b;
-    V.pi = (apply ? S.pi : S.piq) + b;
-    int iters, status; double res[4];
-    qp_ipm_warp<Ctx, C>(w, sm, Qc, V, valid, iters, status, res);
-    if (!valid) return;
     const int lane = w.lane();
-    if (lane == 0) {
-        S.qpstat[b] = status;
-        if (apply) S.qp_iter[b] = iters; else S.qp_iter[b] += iters;
-    }
-    if (!apply) return;
-    // ---- K5 (RTI): x += dx, u += du, cost, status — each lane updates its own stages
-    w.sync();
     const int N = S.N;
-    double cost = 0.0;
-    int nan = 0;
-#pragma unroll
-    for (int j = 0; j < C; ++j) {
-        const int k = lane * C + j;
-        if (k > N) continue;
-        if (k < N) {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) { const double v = QS_EL(S.u, k * 2 + i, b) + QS_EL(S.z, k * 6 + i, b); QS_EL(S.u, k * 2 + i, b) = v; nan |= !(v == v); }
+    QpView V;
+    QwState st;
+    int b = next();
+    bool fresh = true;
+    for (;;) {
+        if (w.cta_all(b < 0)) break;                            // lockstep point; leaves when the queue is drained
+        if (b < 0) continue;
+        if (fresh) {
+            V.stride = (size_t)S.Bp;
+            V.A = S.A + b; V.B = S.Bm + b; V.b = S.b + b; V.g = S.g + b; V.qN = S.qN + b; V.dx0 = S.dx0 + b;
+            V.x = S.x + b; V.u = S.u + b;
+            V.z = S.z + b; V.zp = S.zp + b; V.zc = S.zc + b; V.t = S.t + b;
+            V.K = S.K + b; V.Li = S.Li + b; V.Pb = S.Pb + b; V.kff = S.kff + b;
+            V.rg = S.rg + b; V.rb = S.rb + b; V.rgs = S.rgs + b;
+            V.lam = (apply ? S.lam : S.lamq) + b;
+            V.pi = (apply ? S.pi : S.piq) + b;
+            qw_init<Ctx, C>(w, sm, Qc, V, st);
+            fresh = false;
         }
+        if (!qw_iterate<Ctx, C>(w, sm, Qc, st)) continue;
+        // ---- problem b is finished: write back, K5 epilogue, fetch the next problem
+        qw_writeback<Ctx, C>(w, sm, Qc, V);
+        if (lane == 0) {
+            S.qpstat[b] = st.status;
+            if (apply) S.qp_iter[b] = st.it; else S.qp_iter[b] += st.it;
+        }
+        if (apply) {
+            // K5 (RTI): x += dx, u += du, cost, status — each lane updates its own stages
+            w.sync();
+            double cost = 0.0;
+            int nan = 0;
+#pragma unroll 1
+            for (int j = 0; j < C; ++j) {
+                const int k = lane * C + j;
+                if (k > N) continue;
+                if (k < N) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) QS_EL(S.x, k * 4 + i, b) += QS_EL(S.z, k * 6 + 2 + i, b);
-        cost += (k < N) ? stage_cost(S, k, b) : terminal_cost(S, b);
-    }
-    cost = w.wsum(cost);
-    nan = w.wany(nan);
-    if (lane == 0) {
-        S.cost[b] = cost;
+                    for (int i = 0; i < 2; ++i) { const double v = QS_EL(S.u, k * 2 + i, b) + QS_EL(S.z, k * 6 + i, b); QS_EL(S.u, k * 2 + i, b) = v; nan |= !(v == v); }
+                }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) QS_EL(S.res, i, b) = res[i];
-        S.sqp_iter[b] = 1;
-        S.alpha[b] = 1.0;
-        S.status[b] = nan ? 1 : (status == 2 ? 4 : 0);
+                for (int i = 0; i < 4; ++i) QS_EL(S.x, k * 4 + i, b) += QS_EL(S.z, k * 6 + 2 + i, b);
+                cost += (k < N) ? stage_cost(S, k, b) : terminal_cost(S, b);
+            }
+            cost = w.wsum(cost);
+            nan = w.wany(nan);
+            if (lane == 0) {
+                S.cost[b] = cost;
+                QS_EL(S.res, 0, b) = st.r_stat; QS_EL(S.res, 1, b) = st.r_eq; QS_EL(S.res, 2, b) = st.r_in; QS_EL(S.res, 3, b) = st.r_cp;
+                S.sqp_iter[b] = 1;
+                S.alpha[b] = 1.0;
+                S.status[b] = nan ? 1 : (st.status == 2 ? 4 : 0);
+            }
+        }
+        b = next();
+        fresh = true;
     }
 }
 

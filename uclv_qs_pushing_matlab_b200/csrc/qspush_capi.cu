@@ -2,6 +2,7 @@
 // every compute entry point requires a CUDA device and fails with QSPUSH_ERR_NO_DEVICE otherwise.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -531,7 +532,10 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
     }
     const int pwd = (int)((qp_warp_smem_doubles(s->N) + 1) / 2 * 2);
     const size_t smem = (size_t)pwd * QW_WARPS * sizeof(double);
-    const unsigned blocks = (unsigned)((s->B + QW_WARPS - 1) / QW_WARPS);
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device);
+    const unsigned blocks = (unsigned)std::min((s->B + QW_WARPS - 1) / QW_WARPS, nsm);   // persistent: one CTA per SM
+    CK(cudaMemsetAsync(D.ndone + 1, 0, sizeof(int), s->stream));                       // work-queue head
 #define QW_LAUNCH(CC)                                                                                              \
     CK(cudaFuncSetAttribute(k_qp_warp<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
     k_qp_warp<CC><<<blocks, 32 * QW_WARPS, smem, s->stream>>>(D, io, apply, pwd)
