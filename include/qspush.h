@@ -57,7 +57,7 @@ typedef struct {
     double alpha_min, alpha_reduction, eps_sufficient_descent;   /* 0.05, 0.7, 1e-4           */
     int    matlab_single_quirk;     /* reproduce MATLAB `single` rounding of mod(s,b) in prepare */
     int    problems_per_warp;       /* thread-per-problem QP kernel packing: 32, 16, 8, 4 (0 = auto) */
-    int    qp_kernel;               /* 1 = warp per problem, parallel-in-time Riccati (N <= 127); 0 = one problem per thread */
+    int    qp_kernel;               /* 2 = auto by batch size (default); 1 = warp per problem, parallel-in-time Riccati (N <= 127); 0 = one problem per thread */
 } qspush_opts;
 
 /* controller-side constants of NMPC_controller (NMPC_controller.m:23-26, 98-100) */

@@ -224,3 +224,65 @@ def test_nmpc_controller_closed_loop_config1():
     assert abs(p.SP.getMaxCurvature() - om.get_curvatures(np.arange(0, om.b + 1e-12, 0.001)).max()) < 1e-6
     assert rel_err(p.SP.evalSpline(p.SP.FC, [-0.01, 0.3]), om.eval_spline([-0.01, 0.3], wrap=1)["C"]) < REL
     assert rel_err(p.evalModelVariableShape(np.array([0, 0, 0.1, -0.01]), np.array([0.01, 0.002])), om.dynamics([[0, 0, 0.1, -0.01]], [[0.01, 0.002]])[0]) < REL
+
+
+def test_long_horizon_falls_back_to_thread_kernel_and_auto_selection():
+    """N = 130 does not fit the warp kernel (C <= 4): the C-ABI silently uses the thread-per-problem kernel.
+    qp_kernel = 2 (auto, default) must agree with both explicit choices."""
+    gm, om = packaged_model_pair("santal")
+    B, N = 32, 130
+    wl = make_rti_workload(None, batch=B, N=N, seed=6)
+    ocp, pr = _oracle_prepared(om, wl, N)
+    ro = ocp.solve("rti", pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"], nthreads=8)
+    s = q.Solver([gm], N, 0.05, B, qp_kernel=1)
+    _load(s, wl); s.prepare(); s.solve()
+    e = np.abs(s.get("u") - ro["u"]).max(axis=(1, 2))
+    assert (s.get_int("status") == 0).all() and (e < 1e-6).mean() >= 0.8 and e.max() < 1e-4
+    B, N = 64, 40
+    wl = make_rti_workload(None, batch=B, N=N, seed=6)
+    us = []
+    for kern in (2, 1, 0):
+        s = q.Solver([gm], N, 0.05, B, qp_kernel=kern)
+        _load(s, wl); s.prepare(); s.solve(); us.append(s.get("u"))
+    assert np.array_equal(us[0], us[1]) and np.abs(us[0] - us[2]).max() < 1e-5
+
+
+def test_closed_loop_disturbance_noise_and_delay():
+    """helper.closed_loop_matlab extras (helper.m:221-242, NMPC_controller.m:106-120): lateral disturbance with
+    re-projection of s onto the outline, state noise, controller delay compensation."""
+    sel = q.object_selection("santal")
+    p = q.PusherSliderModel("real_plant", sel, 0, sel.cad_model_path, 3, sel.pcl_path, "santal")
+    p.symbolic_model_variable_shape()
+    Hp, dt, steps = 10, 0.05, 30
+    t = np.arange(201) * dt
+    traj = np.zeros((6, 201)); traj[0] = np.minimum(0.01 * t, 0.10)
+    c = q.NMPC_controller("NMPC", p, dt, Hp, nlp_solver="sqp_rti")
+    c.create_ocp_solver()
+    c.set_delay_comp(0.0)
+    c.initial_condition_update(np.zeros(4))
+    c.set_reference_trajectory(traj)
+    out = q.helper.closed_loop_matlab(p, c, np.zeros(4), (steps - 1) * dt, sim_noise=True, disturbance_=True, amplitude_dist=-0.005, t_dist=10,
+                                      rng=np.random.default_rng(1))
+    x_s, y_s, S_p_x, S_p_y, found = out[0], out[2], out[4], out[5], out[10]
+    assert found.all() and np.isfinite(x_s).all()
+    assert abs(y_s[9] - y_s[8]) > 0.003                               # the shove is applied to x(:, t_dist) (1-based, helper.m:224)
+    assert np.abs(S_p_x).max() < 0.05 and np.abs(S_p_y).max() < 0.06   # contact point stays on the outline
+    # re-projection: the new s is the outline point closest to the displaced contact point
+    s_new = q.helper._reproject_s(p, np.array([-0.031, 0.01]), 0.0)
+    C = p.SP.evalSpline(p.SP.FC, [s_new])[0]
+    grid = p.SP.evalSpline(p.SP.FC, np.linspace(0, p.SP.b, 4001)[:-1])
+    assert np.linalg.norm(C - [-0.031, 0.01]) <= np.linalg.norm(grid - np.array([-0.031, 0.01]), axis=1).min() + 1e-9
+    # delay compensation: the controller predicts the state through its own input buffer
+    c2 = q.NMPC_controller("NMPC", p, dt, Hp, nlp_solver="sqp_rti")
+    c2.create_ocp_solver()
+    c2.set_delay_comp(0.1)
+    c2.initial_condition_update(np.zeros(4))
+    c2.set_reference_trajectory(traj)
+    assert c2.delay_buff_comp == 2 and c2.y_ref.shape == (6, 203)
+    c2.u_buff_contr = np.array([[0.01, 0.02], [0.0, 0.001]])
+    xk = c2.delay_buffer_sim(p, np.array([0.0, 0.0, 0.0, -0.01]))
+    om = oracle_model("santal")
+    x1 = np.array([0.0, 0.0, 0.0, -0.01]); x1 = x1 + dt * om.dynamics([x1], [[0.02, 0.001]])[0]; x2 = x1 + dt * om.dynamics([x1], [[0.01, 0.0]])[0]
+    assert np.abs(xk - x2).max() < 1e-14
+    out2 = q.helper.closed_loop_matlab(p, c2, np.zeros(4), 10 * dt)
+    assert out2[10].all()

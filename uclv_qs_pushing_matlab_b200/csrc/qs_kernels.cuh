@@ -195,7 +195,10 @@ __global__ void __launch_bounds__(32) k_qp(SolverDev S, IpmOpts o, int ppw, int 
 // K4 v2: warp per problem, persistent CTAs of QW_WARPS warps (one CTA per SM); finished warps pull the next
 // problem from a global work queue (S.ndone[1]); the IPM state of each problem lives in its warp's slice of
 // the dynamic shared memory.
-constexpr int QW_WARPS = 6;
+#ifndef QW_WARPS_DEF
+#define QW_WARPS_DEF 6
+#endif
+constexpr int QW_WARPS = QW_WARPS_DEF;
 template <int C>
 __global__ void __launch_bounds__(32 * QW_WARPS, 1) k_qp_warp(SolverDev S, IpmOpts o, int apply, int per_warp_doubles) {
     extern __shared__ __align__(16) double qw_smem[];

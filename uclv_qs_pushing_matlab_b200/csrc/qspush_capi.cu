@@ -251,7 +251,7 @@ void qspush_opts_default(qspush_opts* o) {
     o->alpha_min = 0.05; o->alpha_reduction = 0.7; o->eps_sufficient_descent = 1e-4;
     o->matlab_single_quirk = 1;
     o->problems_per_warp = 0;
-    o->qp_kernel = 1;
+    o->qp_kernel = 2;
 }
 
 static size_t al(size_t doubles) { return (doubles + 31) / 32 * 32; }   // 256-byte granules
@@ -525,7 +525,11 @@ int qspush_prepare(qspush_solver* s) {
 // parallel-in-time; 0 = one problem per thread (any horizon)
 static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, int ppw, int apply) {
     const int C = qp_warp_chunk(s->N);
-    const bool warp = (s->opts.qp_kernel != 0) && C <= 4 && qp_warp_smem_doubles(s->N) * 8 * QW_WARPS <= 220 * 1024;
+    // auto (2): the warp-per-problem kernel wins while the batch cannot fill the GPU with one problem per thread
+    // (measured crossover on B200 at N = 40: ~12k problems; 1.0M it/s flat vs 0.37M -> 2.0M it/s), DESIGN.md 4.1
+    const bool want_warp = s->opts.qp_kernel == 1 || (s->opts.qp_kernel == 2 && s->B < 12288);
+    const bool warp = want_warp && C <= 4 && qp_warp_smem_doubles(s->N) * 8 * QW_WARPS <= 220 * 1024;
+    if (!warp && s->opts.qp_kernel == 2 && s->opts.problems_per_warp == 0) ppw = (s->B >= 12288) ? 32 : ppw;
     if (!warp) {
         k_qp<<<(unsigned)((s->B + ppw - 1) / ppw), 32, 0, s->stream>>>(D, io, ppw, apply);
         return QSPUSH_OK;
