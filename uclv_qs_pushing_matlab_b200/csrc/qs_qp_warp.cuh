@@ -248,11 +248,12 @@ struct IneqStep { double dtl, dtu, dll, dlu; };
 QS_HD IneqStep ineq_step(double v, double dva, double dv, double ll, double lu, double tl, double tu, double dl, double du, double smu) {
     const double rdl = v - dl - tl, rdu = du - v - tu;
     const double dtal = dva + rdl, dtau = -dva + rdu;
-    const double cl = (-ll - ll * dtal / tl) * dtal, cu = (-lu - lu * dtau / tu) * dtau;
+    const double itl = 1.0 / tl, itu = 1.0 / tu;               // one reciprocal per slack instead of two divisions
+    const double cl = (-ll - ll * dtal * itl) * dtal, cu = (-lu - lu * dtau * itu) * dtau;
     IneqStep s;
     s.dtl = dv + rdl; s.dtu = -dv + rdu;
-    s.dll = -(ll * tl - smu + cl + ll * s.dtl) / tl;
-    s.dlu = -(lu * tu - smu + cu + lu * s.dtu) / tu;
+    s.dll = -(ll * tl - smu + cl + ll * s.dtl) * itl;
+    s.dlu = -(lu * tu - smu + cu + lu * s.dtu) * itu;
     return s;
 }
 
@@ -266,6 +267,7 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
     const bool act = lane < Lw_;
     // ---- (a) local: d_k, kff0_k and the chunk's composed backward map  p_start = M p_end + d
     double M[16], d[4];
+    bool acc_identity = true;
 #pragma unroll
     for (int i = 0; i < 16; ++i) M[i] = (i % 5 == 0) ? 1.0 : 0.0;
 #pragma unroll
@@ -280,6 +282,7 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
                 for (int i = 0; i < 16; ++i) M[i] = 0.0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { d[i] = QW_SM(R_RG + 2 + i, j); QW_SM(R_PV + i, j) = d[i]; }
+                acc_identity = false;
                 continue;
             }
             StageLin L;
@@ -306,7 +309,8 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
 #pragma unroll
                 for (int q = 0; q < 4; ++q) At[4 * i + q] = Ab[4 * q + i];
             // acc <- f_k o acc
-            aff_compose(At, dk, M, d);
+            if (!acc_identity) aff_compose(At, dk, M, d);
+            acc_identity = false;
 #pragma unroll
             for (int i = 0; i < 16; ++i) M[i] = At[i];
 #pragma unroll
@@ -371,6 +375,7 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
         }
     }
     // ---- (d) forward: chunk's composed map dx_end = M dx_start + d, prefix scan, local rollout
+    acc_identity = true;
 #pragma unroll
     for (int i = 0; i < 16; ++i) M[i] = (i % 5 == 0) ? 1.0 : 0.0;
 #pragma unroll
@@ -390,7 +395,8 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
 #pragma unroll
             for (int i = 0; i < 4; ++i) bb[i] = QW_SM(R_RB + i, j) - fma(L.b1[i], f0, L.b2[i] * f1);
             closed_loop(L, K0, K1, Ab);
-            aff_compose(Ab, bb, M, d);
+            if (!acc_identity) aff_compose(Ab, bb, M, d);
+            acc_identity = false;
 #pragma unroll
             for (int i = 0; i < 16; ++i) M[i] = Ab[i];
 #pragma unroll
@@ -508,9 +514,9 @@ QS_HD void qw_init(const Ctx& w, double* __restrict__ sm, const QpConst& Q, cons
 }
 
 // ---- one IPM iteration: true residuals + stopping tests, factorisation (parallel-in-time), predictor,
-// corrector, step.  Returns true when the problem is finished (st.status set), false to continue.
+// corrector, step.  Returns 0 to continue, 1 when the problem is finished (st.status set).
 template <class Ctx, int C>
-QS_HD bool qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, QwState& st) {
+QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, QwState& st) {
     const int N = Q.N;
     const int lane = w.lane();
     const int Lw_ = qp_warp_lanes(N, C);
@@ -592,14 +598,14 @@ QS_HD bool qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Q
     r_stat = w.wmax(l_stat); r_eq = w.wmax(l_eq); r_in = w.wmax(l_in); r_cp = w.wmax(l_cp);
     const double mu_sum = w.wsum(l_mu);
     const double mu = mu_sum / (double)m_on;
-    if (w.wany(l_nan ? 1 : 0) || !(mu == mu)) { status = 2; return true; }
-    if (r_stat < Q.tol && r_eq < Q.tol && r_in < Q.tol && r_cp < Q.tol) { status = 0; return true; }
+    if (w.wany(l_nan ? 1 : 0) || !(mu == mu)) { status = 2; return 1; }
+    if (r_stat < Q.tol && r_eq < Q.tol && r_in < Q.tol && r_cp < Q.tol) { status = 0; return 1; }
     {
         const double rmax = fmax(fmax(r_stat, r_eq), fmax(r_in, r_cp));
         if (rmax < 0.5 * rmax_prev) { rmax_prev = rmax; stall = 0; } else ++stall;
-        if (stall >= 5 && rmax < QS_QP_TOL_ACCEPT) { status = 0; return true; }
+        if (stall >= 5 && rmax < QS_QP_TOL_ACCEPT) { status = 0; return 1; }
     }
-    if (it >= Q.max_iter) { status = 1; return true; }
+    if (it >= Q.max_iter) { status = 1; return 1; }
     // ================= (2) barrier terms, affine rhs, stage elements, chunk aggregate =================
     Elem E; elem_identity(E);
     if (act) {
@@ -721,7 +727,7 @@ QS_HD bool qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Q
             for (int i = 0; i < 10; ++i) QW_SM(R_P + i, j) = P[i];
         }
     }
-    if (w.wany(ok ? 0 : 1)) { status = 2; return true; }
+    if (w.wany(ok ? 0 : 1)) { status = 2; return 1; }
     // ================= (5)-(7) predictor and corrector share ONE copy of the solve code =================
     double smu = 0.0;
 #pragma unroll 1
@@ -805,7 +811,7 @@ QS_HD bool qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Q
     }
     a_max = w.wmin(a_max);
     const double alpha = fmin(1.0, Q.tau * a_max);
-    if (!(alpha == alpha)) { status = 2; return true; }
+    if (!(alpha == alpha)) { status = 2; return 1; }
     if (act) {
 #pragma unroll 1
         for (int j = 0; j < C; ++j) {
