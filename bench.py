@@ -255,6 +255,23 @@ def run_ours(args):
     e0.record(); c = a @ b; e1.record(); torch.cuda.synchronize(dev)
     fp64_peak_tf = 2 * 4096 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
     fp64_ach_tf = B * alg_flops_per_iter(k_ipm) / (qp_avg_ms * 1e-3 + sum(lin_ms) / len(lin_ms) * 1e-3) / 1e12
+    # per-solve latency of a single NMPC instance (the MEX drop-in case): host buffers through the C-ABI, wall clock
+    lat_b1 = {}
+    for tag, n1, mode in (("rti_N40", HORIZON, 0), ("rti_N10", 10, 0), ("sqp_N10", 10, 1)):
+        w1 = make_rti_workload(1, n1, dt=DT, seed=7)
+        s1 = q.Solver([gm], n1, DT, 1, device=local_rank, qp_tol=QP_TOL, mode=mode)
+        u1 = np.zeros((1, 2)); c1 = np.zeros(1, dtype=np.int32)
+        ts = []
+        for i in range(args.latency_solves + 10):
+            t0 = time.perf_counter()
+            s1.set("x0", w1["x0"]); s1.set("yref", w1["yref"]); s1.set("yref_e", w1["yref_e"]); s1.set("u", w1["u_init"]); s1.set_int("cold", c1)
+            s1.prepare(); s1.solve(); s1.get("u", stage=0, out=u1)
+            if i >= 10:
+                ts.append(1e3 * (time.perf_counter() - t0))
+        ts.sort()
+        lat_b1[tag] = {"p50_ms": ts[len(ts) // 2], "p99_ms": ts[min(len(ts) - 1, int(0.99 * len(ts)))], "solves": len(ts),
+                       "sqp_iter": int(s1.get_int("sqp_iter")[0])}
+        del s1
     cores = os.cpu_count() or 1
     cpu_t = cpu_oracle_rate(args.cpu_passes, cores)
     cpu_rate = BATCH_PER_GPU * len(cpu_t) / sum(cpu_t)
@@ -281,6 +298,7 @@ def run_ours(args):
         "phase_ms": {"prepare": sum(prep_ms) / len(prep_ms), "linearise": sum(lin_ms) / len(lin_ms), "qp": qp_avg_ms},
         "latency_ms": {"p50": srt[len(srt) // 2], "p99": srt[min(len(srt) - 1, int(0.99 * len(srt)))], "max": srt[-1],
                        "what": "per-step device time of one batched solve (all instances of the batch finish together)"},
+        "latency_b1": lat_b1,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -296,6 +314,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ppw", type=int, default=0, help="QP kernel packing (problems per warp), 0 = auto")
     ap.add_argument("--qp-kernel", type=int, default=1, help="1 = warp per problem (parallel-in-time; what auto picks at 4096/GPU), 0 = one problem per thread")
+    ap.add_argument("--latency-solves", type=int, default=200, help="solves per B=1 latency measurement")
     ap.add_argument("--cpu-passes", type=int, default=3, help="passes of the oracle over the batch for cpu_baseline")
     args = ap.parse_args()
     if args.impl == "reference":
