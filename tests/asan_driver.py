@@ -1,0 +1,25 @@
+"""Driver executed under AddressSanitizer by tests/test_hostsim_asan.py: every kernel body (both QP kernels, all
+chunk sizes of the warp kernel, full SQP, multi-object batches, ragged sizes) on small problems."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+
+import tests.hostsim.hostsim as hs  # noqa: E402
+
+hs._LIB = sys.argv[1]
+hs.subprocess.check_call = lambda *a, **k: 0          # use the ASan build as is
+from tests.workloads import OBJECT_ORDER, hostsim_model, make_rti_workload  # noqa: E402
+
+mhs = [hostsim_model(n) for n in OBJECT_ORDER]
+for N, B, kern, mode in ((40, 7, 1, "rti"), (10, 5, 1, "rti"), (100, 3, 1, "rti"), (40, 33, 0, "rti"), (10, 4, 1, "sqp"),
+                         (64, 3, 1, "rti"), (31, 3, 1, "rti"), (95, 2, 1, "rti"), (1, 2, 1, "rti"), (130, 2, 1, "rti")):
+    wl = make_rti_workload(None, batch=B, N=N, seed=1, n_objects=4)
+    r = hs.solve(mhs, N, 0.05, wl["x0"], wl["yref"], wl["yref_e"], np.zeros((B, N + 1, 4)), wl["u_init"], objid=wl["object_id"],
+                 mode=mode, prepare=True, shift=True, qp_kernel=kern, max_sqp_iter=3)
+    assert np.isfinite(r["u"]).all()
+x = np.random.default_rng(0).uniform(-0.7, 0.7, (500, 4)); u = np.random.default_rng(1).uniform(-0.05, 0.05, (500, 2))
+mhs[3].eval_spline(x[:, 3], wrap=2); mhs[3].dynamics(x, u); mhs[3].erk4_sens(x, u, 0.05); mhs[3].v_bound(x[:, 3])
+print("ASAN-DRIVER-OK")
