@@ -286,3 +286,15 @@ def test_closed_loop_disturbance_noise_and_delay():
     assert np.abs(xk - x2).max() < 1e-14
     out2 = q.helper.closed_loop_matlab(p, c2, np.zeros(4), 10 * dt)
     assert out2[10].all()
+
+
+def test_open_loop_driver():
+    sel = q.object_selection("balea")
+    p = q.PusherSliderModel("real_plant", sel, 0, sel.cad_model_path, 3, sel.pcl_path, "balea")
+    out = q.helper.open_loop_matlab(p, np.array([0.0, 0.0, 0.0, -0.01]), 0.01, 0.0, 1.0, 0.05)     # helper.m:132-193
+    x_s, y_s, th_s, t = out[0], out[1], out[2], out[7]
+    om = oracle_model("balea")
+    x = np.array([0.0, 0.0, 0.0, -0.01])
+    for k in range(len(t) - 1):
+        x = x + 0.05 * om.dynamics([x], [[0.01, 0.0]])[0]
+    assert len(t) == 21 and abs(x_s[-1] - x[0]) < 1e-12 and abs(y_s[-1] - x[1]) < 1e-12 and abs(th_s[-1] - x[2]) < 1e-12

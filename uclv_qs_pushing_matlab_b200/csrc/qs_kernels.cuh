@@ -123,7 +123,8 @@ __global__ void k_eval_dynamics(const double* __restrict__ gmodel, int cnt, cons
     }
 }
 
-__global__ void __launch_bounds__(128)
+// 3 CTAs of 128 threads per SM (168 registers): measured +24 % over the unconstrained 182-register build
+__global__ void __launch_bounds__(128, 3)
 k_eval_erk4(const double* __restrict__ gmodel, int cnt, const double* __restrict__ x, const double* __restrict__ u, double dt,
             double* Phi, double* A, double* Bo) {
     const double* M = stage_models(gmodel, 1);
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(128) k_prepare(SolverDev S, CtrlDev cp) {
 }
 
 // one thread per (problem, stage); consecutive threads walk problems -> coalesced slab accesses
-__global__ void __launch_bounds__(128) k_linearise(SolverDev S) {
+__global__ void __launch_bounds__(128, 3) k_linearise(SolverDev S) {
     const double* Mall = stage_models(S.models, S.nmodels);
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int k = (int)(tid / S.Bp), b = (int)(tid % S.Bp);
