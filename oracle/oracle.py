@@ -169,7 +169,7 @@ class Model:
 
 DEFAULT_OPTS = dict(
     max_sqp_iter=30, tol_stat=1e-6, tol_eq=1e-6, tol_ineq=1e-6, tol_comp=1e-6,
-    qp_max_iter=50, qp_tol=1e-12, qp_mu0=1.0, qp_thr=1e-3, qp_tau=0.995,
+    qp_max_iter=50, qp_tol=1e-12, qp_mu0=0.1, qp_thr=1e-3, qp_tau=0.9995,
     alpha_min=0.05, alpha_reduction=0.7, eps_sufficient_descent=1e-4, globalization=1, local_spline=1,
 )
 _OPT_ORDER = list(DEFAULT_OPTS.keys())

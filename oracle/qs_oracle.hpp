@@ -109,9 +109,9 @@ struct OcpOpts {
     double tol_stat = 1e-6, tol_eq = 1e-6, tol_ineq = 1e-6, tol_comp = 1e-6;  // :276
     int    qp_max_iter = 50;           // acados default qp_solver_iter_max
     double qp_tol = 1e-12;              // QP residual tolerance (all four)
-    double qp_mu0 = 1.0;               // initial barrier parameter
+    double qp_mu0 = 0.1;               // initial barrier parameter
     double qp_thr = 1e-3;              // lower clamp on initial slacks
-    double qp_tau = 0.995;             // fraction to the boundary
+    double qp_tau = 0.9995;            // fraction to the boundary
     double alpha_min = 0.05, alpha_reduction = 0.7, eps_sufficient_descent = 1e-4;  // acados defaults
     int    globalization = 1;          // 1 = merit backtracking (NMPC_controller.m:272), 0 = full step
 };
