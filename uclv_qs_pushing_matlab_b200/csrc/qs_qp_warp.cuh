@@ -55,6 +55,18 @@ struct WarpCtxDev {
 };
 #endif
 
+// optional per-phase cycle counters (build with -DQW_PROFILE; development aid, tools/gpu_phase_profile.py)
+#if defined(QW_PROFILE) && defined(__CUDACC__)
+__device__ unsigned long long qw_prof[16];
+#endif
+#if defined(QW_PROFILE) && defined(__CUDA_ARCH__)
+#define QW_T0() long long qw_t__ = clock64()
+#define QW_TICK(slot) do { const long long n__ = clock64(); if (w.lane() == 0) atomicAdd(&qw_prof[slot], (unsigned long long)(n__ - qw_t__)); qw_t__ = n__; } while (0)
+#else
+#define QW_T0() do { } while (0)
+#define QW_TICK(slot) do { } while (0)
+#endif
+
 // rows of the per-problem shared-memory state; element (row, j) of lane l sits at sm[((row)*C + j)*L + l]
 enum : int {
     R_A3 = 0, R_A4 = 4, R_B1 = 8, R_B2 = 12, R_BV = 16, R_G = 20, R_HH = 26,      // linearisation (29)
@@ -241,6 +253,15 @@ QS_HD void closed_loop(const StageLin& L, const double K0[4], const double K1[4]
             const double a = (j == 0) ? (i == 0 ? 1.0 : 0.0) : (j == 1) ? (i == 1 ? 1.0 : 0.0) : (j == 2 ? L.a3[i] : L.a4[i]);
             Ab[4 * i + j] = a - fma(L.b1[i], K0[j], L.b2[i] * K1[j]);
         }
+}
+
+// Ratio test without divisions: keep the pair (num, den) with the smallest num/den among the candidates
+// v / (-dv) with dv < 0 (cross-multiplication; one division per lane at the end instead of one per candidate).
+QS_HD void ratio_min(double v, double dv, double& num, double& den) {
+    const double dn = -dv;
+    const bool better = (dn > 0.0) && (v * den < num * dn);
+    num = better ? v : num;
+    den = better ? dn : den;
 }
 
 // Newton step of one two-sided bound pair (lower: t = v - dl, upper: t = du - v), Mehrotra corrector included.
@@ -526,6 +547,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
     double& rmax_prev = st.rmax_prev; double& r_stat = st.r_stat; double& r_eq = st.r_eq; double& r_in = st.r_in; double& r_cp = st.r_cp;
     const double* qN = st.qN;
     {
+    QW_T0();
     // ================= (1) true residuals =================
     double nx[4] = {0, 0, 0, 0}, npi[4] = {0, 0, 0, 0};    // x and pi of the stage right of the chunk (neighbour lane, j = 0)
     w.sync();
@@ -606,6 +628,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
         if (stall >= 5 && rmax < QS_QP_TOL_ACCEPT) { status = 0; return 1; }
     }
     if (it >= Q.max_iter) { status = 1; return 1; }
+    QW_TICK(1);
     // ================= (2) barrier terms, affine rhs, stage elements, chunk aggregate =================
     Elem E; elem_identity(E);
     if (act) {
@@ -673,6 +696,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             E = e;
         }
     }
+    QW_TICK(2);
     // ================= (3) suffix scan of the chunk aggregates =================
     double* xch = (C >= 2) ? sm + (size_t)R_K * C * Lw_ : sm + (size_t)R_ROWS * C * Lw_;
 #pragma unroll 1
@@ -697,6 +721,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
 #pragma unroll
         for (int i = 0; i < 10; ++i) P[i] = xch[(size_t)(26 + i) * Lw_ + lane + 1];
     }
+    QW_TICK(3);
     // ================= (4) local Riccati over the chunk: K_k, Cholesky, P_k, P_{k+1} r_b =================
     bool ok = true;
     if (act) {
@@ -728,6 +753,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
         }
     }
     if (w.wany(ok ? 0 : 1)) { status = 2; return 1; }
+    QW_TICK(4);
     // ================= (5)-(7) predictor and corrector share ONE copy of the solve code =================
     double smu = 0.0;
 #pragma unroll 1
@@ -748,17 +774,20 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                     const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
                     const double rdl = v - (Q.lh[c] - h) - tl, rdu = (Q.uh[c] - h) - v - tu;
                     const double dtl = dva + rdl, dtu = -dva + rdu;
-                    const double cl = (-ll - ll * dtl / tl) * dtl, cu = (-lu - lu * dtu / tu) * dtu;
-                    gt[cidx(c)] += (ll * tl - smu + cl + ll * rdl) / tl - (lu * tu - smu + cu + lu * rdu) / tu;
+                    const double itl = 1.0 / tl, itu = 1.0 / tu;
+                    const double cl = (-ll - ll * dtl * itl) * dtl, cu = (-lu - lu * dtu * itu) * dtu;
+                    gt[cidx(c)] += (ll * tl - smu + cl + ll * rdl) * itl - (lu * tu - smu + cu + lu * rdu) * itu;
                 }
 #pragma unroll
                 for (int i = 0; i < 6; ++i) QW_SM(R_GT + i, j) = gt[i];
             }
         }
+        QW_TICK(5);
         qp_warp_solve<Ctx, C>(w, sm, N, Lw_, Q.QN);
+        QW_TICK(6);
         if (pass == 0) {
             // step to the boundary of the affine step, mu_aff, centering parameter
-            double a_aff = 1.0, S1 = 0.0, S2 = 0.0;
+            double a_aff = 1.0, a_num = 1.0, a_den = 1.0, S1 = 0.0, S2 = 0.0;
             if (act) {
 #pragma unroll 1
                 for (int j = 0; j < C; ++j) {
@@ -772,25 +801,24 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                         const double h = QW_SM(R_HH + c, j), v = QW_SM(R_Z + cidx(c), j);
                         const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
                         const double dtl = dva + (v - (Q.lh[c] - h) - tl), dtu = -dva + ((Q.uh[c] - h) - v - tu);
-                        const double dll = -ll - ll * dtl / tl, dlu = -lu - lu * dtu / tu;
-                        if (dtl < 0.0) a_aff = fmin(a_aff, -tl / dtl);
-                        if (dtu < 0.0) a_aff = fmin(a_aff, -tu / dtu);
-                        if (dll < 0.0) a_aff = fmin(a_aff, -ll / dll);
-                        if (dlu < 0.0) a_aff = fmin(a_aff, -lu / dlu);
+                        const double dll = -ll - ll * dtl * (1.0 / tl), dlu = -lu - lu * dtu * (1.0 / tu);
+                        ratio_min(tl, dtl, a_num, a_den); ratio_min(tu, dtu, a_num, a_den);
+                        ratio_min(ll, dll, a_num, a_den); ratio_min(lu, dlu, a_num, a_den);
                         S1 += ll * dtl + tl * dll + lu * dtu + tu * dlu;
                         S2 += dll * dtl + dlu * dtu;
                     }
                 }
             }
-            a_aff = w.wmin(a_aff); S1 = w.wsum(S1); S2 = w.wsum(S2);
+            a_aff = w.wmin(fmin(a_aff, a_num / a_den)); S1 = w.wsum(S1); S2 = w.wsum(S2);
             const double mu_aff = (mu_sum + a_aff * (S1 + a_aff * S2)) / (double)m_on;
             double sigma = (mu > 0.0) ? mu_aff / mu : 0.0;
             sigma = sigma * sigma * sigma;
             smu = fmax(sigma * mu, 0.1 * Q.tol);
         }
     }
+    QW_TICK(7);
     // ================= (8) step length and update =================
-    double a_max = 1.0;
+    double a_max = 1.0, m_num = 1.0, m_den = 1.0;
     if (act) {
 #pragma unroll 1
         for (int j = 0; j < C; ++j) {
@@ -802,14 +830,12 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                 IneqStep s_ = ineq_step(QW_SM(R_Z + cidx(c), j), QW_SM(R_DZA + c, j), QW_SM(R_GT + cidx(c), j),
                                         QW_SM(R_LAM + c, j), QW_SM(R_LAM + 3 + c, j), QW_SM(R_T + c, j), QW_SM(R_T + 3 + c, j),
                                         Q.lh[c] - QW_SM(R_HH + c, j), Q.uh[c] - QW_SM(R_HH + c, j), smu);
-                if (s_.dtl < 0.0) a_max = fmin(a_max, -QW_SM(R_T + c, j) / s_.dtl);
-                if (s_.dtu < 0.0) a_max = fmin(a_max, -QW_SM(R_T + 3 + c, j) / s_.dtu);
-                if (s_.dll < 0.0) a_max = fmin(a_max, -QW_SM(R_LAM + c, j) / s_.dll);
-                if (s_.dlu < 0.0) a_max = fmin(a_max, -QW_SM(R_LAM + 3 + c, j) / s_.dlu);
+                ratio_min(QW_SM(R_T + c, j), s_.dtl, m_num, m_den); ratio_min(QW_SM(R_T + 3 + c, j), s_.dtu, m_num, m_den);
+                ratio_min(QW_SM(R_LAM + c, j), s_.dll, m_num, m_den); ratio_min(QW_SM(R_LAM + 3 + c, j), s_.dlu, m_num, m_den);
             }
         }
     }
-    a_max = w.wmin(a_max);
+    a_max = w.wmin(fmin(a_max, m_num / m_den));
     const double alpha = fmin(1.0, Q.tau * a_max);
     if (!(alpha == alpha)) { status = 2; return 1; }
     if (act) {
@@ -846,8 +872,9 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
         }
     }
     w.sync();
+    QW_TICK(8);
     ++it;
-    return false;
+    return 0;
     }
 }
 

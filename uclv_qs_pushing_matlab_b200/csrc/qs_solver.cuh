@@ -240,7 +240,9 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm, const Solve
     for (;;) {
         // lockstep point once per IPM iteration (measured: voting every 2nd / 4th iteration is 9 % / 16 % slower,
         // the warps drift and stop sharing instruction fetches); leaves when the queue is drained
+        QW_T0();
         if (w.cta_all(b < 0)) break;
+        QW_TICK(0);
         if (b < 0) continue;
         if (fresh) {
             V.stride = (size_t)S.Bp;
@@ -253,6 +255,7 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm, const Solve
             V.pi = (apply ? S.pi : S.piq) + b;
             qw_init<Ctx, C>(w, sm, Qc, V, st);
             fresh = false;
+            QW_TICK(9);
         }
         const int fin = qw_iterate<Ctx, C>(w, sm, Qc, st);
         if (fin == 0) continue;
@@ -291,6 +294,7 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm, const Solve
         }
         b = next();
         fresh = true;
+        QW_TICK(10);
     }
 }
 

@@ -667,4 +667,15 @@ int qspush_get_stat(qspush_solver* s, qspush_stat which, double* out) {
 }
 long long qspush_launch_count(const qspush_solver* s) { return s ? s->launches : 0; }
 
+#if defined(QW_PROFILE)
+// development aid (not part of include/qspush.h): read and reset the per-phase cycle counters of k_qp_warp
+int qspush_dev_phase_cycles(unsigned long long* out16) {
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(out16, qw_prof, sizeof(unsigned long long) * 16));
+    unsigned long long z[16] = {0};
+    CK(cudaMemcpyToSymbol(qw_prof, z, sizeof z));
+    return QSPUSH_OK;
+}
+#endif
+
 }  // extern "C"
