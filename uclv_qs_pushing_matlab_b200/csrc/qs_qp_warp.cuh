@@ -67,7 +67,9 @@ __device__ unsigned long long qw_prof[16];
 #define QW_TICK(slot) do { } while (0)
 #endif
 
-// rows of the per-problem shared-memory state; element (row, j) of lane l sits at sm[((row)*C + j)*L + l]
+// rows of the per-problem shared-memory state.  Layout: one RECORD of R_ROWS doubles per (local stage j, lane l) at
+// sm[(j*L + l)*R_ROWS + row]: a row access is a compile-time immediate offset from the record pointer (no integer
+// address arithmetic), and the odd record stride (101) makes the 64-bit accesses of a half-warp conflict-free.
 enum : int {
     R_A3 = 0, R_A4 = 4, R_B1 = 8, R_B2 = 12, R_BV = 16, R_G = 20, R_HH = 26,      // linearisation (29)
     R_Z = 29, R_PIK = 35, R_LAM = 39, R_T = 45,                                    // point (22): z, pi_k, lam, t
@@ -77,11 +79,13 @@ enum : int {
 };
 QS_HD constexpr int qp_warp_chunk(int N) { return (N + 1 + 31) / 32; }
 QS_HD constexpr int qp_warp_lanes(int N, int C) { return (N + 1 + C - 1) / C; }
-// exchange slots per lane behind the rows: one affine map (M 16, d 4); the scan element (A 16, C 10, J 10) is
-// exchanged through the rows R_K .. R_DZA, which are dead during the element scan (25*C >= 36 slots for C >= 2)
-QS_HD constexpr int qp_warp_xch_rows(int C) { return C >= 2 ? 20 : 36; }
+// Exchange areas of the warp scans.  Affine maps (M 16, d 4): a dedicated area behind the records, odd stride 21 per
+// lane.  Scan elements (A 16, C 10, J 10): for C >= 2 they travel through rows R_K.. of the j = 0 (A) and j = 1
+// (C, J) records, which are dead during the element scan; for C == 1 through a dedicated area of stride 37.
+constexpr int QW_XA = 21, QW_XE = 37;
 QS_HD constexpr size_t qp_warp_smem_doubles(int N) {
-    return ((size_t)R_ROWS * qp_warp_chunk(N) + qp_warp_xch_rows(qp_warp_chunk(N))) * qp_warp_lanes(N, qp_warp_chunk(N));
+    const int C = qp_warp_chunk(N), L = qp_warp_lanes(N, C);
+    return (size_t)R_ROWS * C * L + (size_t)QW_XA * L + (C >= 2 ? 0 : (size_t)QW_XE * L);
 }
 
 // ---- small dense helpers --------------------------------------------------------------------------
@@ -111,12 +115,12 @@ struct Elem { double A[16]; double C[10]; double J[10]; };   // A row-major, C a
 
 // Exchange through shared memory instead of 64-bit shuffles (2 instructions per value instead of ~8):
 // every lane deposits n values in its column of the exchange area, the partner column is read after a
-// warp sync.  xch[c * L + lane].  Lanes outside [0, L) neither write nor read.
+// warp sync.  Lanes outside [0, L) neither write nor read.
 template <class Ctx>
-QS_HD void xch_put(const Ctx& w, double* __restrict__ xch, int L, int lane, const double* v, int n0, int n) {
-    if (lane < L) {
+QS_HD void xch_put(const Ctx& w, double* __restrict__ slot, bool on, const double* v, int n) {
+    if (on) {
 #pragma unroll
-        for (int i = 0; i < n; ++i) xch[(size_t)(n0 + i) * L + lane] = v[i];
+        for (int i = 0; i < n; ++i) slot[i] = v[i];
     }
     (void)w;
 }
@@ -278,7 +282,7 @@ QS_HD IneqStep ineq_step(double v, double dva, double dv, double ll, double lu, 
     return s;
 }
 
-#define QW_SM(row, j) sm[((size_t)(row) * C + (j)) * Lw_ + lane]
+#define QW_SM(row, j) sm[((size_t)(j) * Lw_ + lane) * R_ROWS + (row)]
 
 // One Newton solve with the current factorisation: rhs gt (R_GT rows) and r_b (R_RB) ->
 // step dz (R_GT rows, aliased), costate offsets p_k (R_PV), feed-forward k_ff (R_KFF).
@@ -339,28 +343,29 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
         }
     }
     // ---- (b) suffix scan over lanes (exchange through shared memory); afterwards d = p at the first stage of the chunk
-    double* xch = sm + (size_t)R_ROWS * C * Lw_;
+    double* xa = sm + (size_t)R_ROWS * C * Lw_ + (size_t)lane * QW_XA;      // this lane's affine exchange slot
 #pragma unroll 1
     for (int dl = 1; dl < Lw_; dl <<= 1) {
         w.sync();
-        xch_put(w, xch, Lw_, lane, M, 0, 16); xch_put(w, xch, Lw_, lane, d, 16, 4);
+        xch_put(w, xa, act, M, 16); xch_put(w, xa + 16, act, d, 4);
         w.sync();
         if (act && lane + dl < Lw_) {
             double Mp[16], dp[4];
+            const double* xp = xa + (size_t)dl * QW_XA;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) Mp[i] = xch[(size_t)i * Lw_ + lane + dl];
+            for (int i = 0; i < 16; ++i) Mp[i] = xp[i];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) dp[i] = xch[(size_t)(16 + i) * Lw_ + lane + dl];
+            for (int i = 0; i < 4; ++i) dp[i] = xp[16 + i];
             aff_compose(M, d, Mp, dp);
         }
     }
     w.sync();
-    xch_put(w, xch, Lw_, lane, d, 16, 4);
+    xch_put(w, xa + 16, act, d, 4);
     w.sync();
     double pe[4] = {0, 0, 0, 0};                                // p at the right boundary of the chunk
     if (act && lane + 1 < Lw_) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) pe[i] = xch[(size_t)(16 + i) * Lw_ + lane + 1];
+        for (int i = 0; i < 4; ++i) pe[i] = xa[QW_XA + 16 + i];
     }
     // ---- (c) local back-substitution: k_ff and p_k
     if (act) {
@@ -427,24 +432,25 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
 #pragma unroll 1
     for (int dl = 1; dl < Lw_; dl <<= 1) {
         w.sync();
-        xch_put(w, xch, Lw_, lane, M, 0, 16); xch_put(w, xch, Lw_, lane, d, 16, 4);
+        xch_put(w, xa, act, M, 16); xch_put(w, xa + 16, act, d, 4);
         w.sync();
         if (act && lane - dl >= 0) {
             double Mp[16], dp[4];
+            const double* xp = xa - (size_t)dl * QW_XA;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) Mp[i] = xch[(size_t)i * Lw_ + lane - dl];
+            for (int i = 0; i < 16; ++i) Mp[i] = xp[i];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) dp[i] = xch[(size_t)(16 + i) * Lw_ + lane - dl];
+            for (int i = 0; i < 4; ++i) dp[i] = xp[16 + i];
             aff_compose(M, d, Mp, dp);
         }
     }
     w.sync();
-    xch_put(w, xch, Lw_, lane, d, 16, 4);
+    xch_put(w, xa + 16, act, d, 4);
     w.sync();
     double x[4] = {0, 0, 0, 0};                                // dx at the first stage of the chunk (dx_0 = 0)
     if (act && lane >= 1) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) x[i] = xch[(size_t)(16 + i) * Lw_ + lane - 1];
+        for (int i = 0; i < 4; ++i) x[i] = xa[16 + i - QW_XA];
     }
     if (act) {
 #pragma unroll 1
@@ -554,8 +560,8 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
     if (act && lane + 1 < Lw_) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            nx[i] = sm[((size_t)(R_Z + 2 + i) * C + 0) * Lw_ + lane + 1];
-            npi[i] = sm[((size_t)(R_PIK + i) * C + 0) * Lw_ + lane + 1];
+            nx[i] = sm[((size_t)lane + 1) * R_ROWS + R_Z + 2 + i];      // record (j = 0, lane + 1)
+            npi[i] = sm[((size_t)lane + 1) * R_ROWS + R_PIK + i];
         }
     }
     double l_stat = 0.0, l_eq = 0.0, l_in = 0.0, l_cp = 0.0, l_mu = 0.0;
@@ -631,6 +637,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
     QW_TICK(1);
     // ================= (2) barrier terms, affine rhs, stage elements, chunk aggregate =================
     Elem E; elem_identity(E);
+    bool E_is_identity = true;                              // combining with the identity is a copy: skip the arithmetic
     if (act) {
 #pragma unroll 1
         for (int j = C - 1; j >= 0; --j) {
@@ -641,6 +648,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                 for (int i = 0; i < 16; ++i) E.A[i] = 0.0;
 #pragma unroll
                 for (int i = 0; i < 10; ++i) { E.C[i] = 0.0; E.J[i] = Q.QN[i]; }
+                E_is_identity = false;
                 continue;
             }
             const double* Hk = Q.H + (size_t)k * 21;
@@ -692,34 +700,40 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             if (k == 0) {
                 // x_0 is fixed (dx_0 = 0): only the reachable-set part matters; keep J finite and PSD
             }
-            elem_combine(e, E.A, E.C, E.J);                  // E <- e (x) E
+            if (!E_is_identity) elem_combine(e, E.A, E.C, E.J);   // E <- e (x) E
             E = e;
+            E_is_identity = false;
         }
     }
     QW_TICK(2);
     // ================= (3) suffix scan of the chunk aggregates =================
-    double* xch = (C >= 2) ? sm + (size_t)R_K * C * Lw_ : sm + (size_t)R_ROWS * C * Lw_;
+    // exchange slots of this lane: A (16) and C, J (10 + 10)
+    double* xeA = (C >= 2) ? &QW_SM(R_K, 0) : sm + (size_t)R_ROWS * C * Lw_ + (size_t)QW_XA * Lw_ + (size_t)lane * QW_XE;
+    double* xeCJ = (C >= 2) ? &QW_SM(R_K, (C >= 2 ? 1 : 0)) : xeA + 16;
+    const size_t xstride = (C >= 2) ? (size_t)R_ROWS : (size_t)QW_XE;     // distance between neighbouring lanes' slots
 #pragma unroll 1
     for (int dl = 1; dl < Lw_; dl <<= 1) {
         w.sync();
-        xch_put(w, xch, Lw_, lane, E.A, 0, 16); xch_put(w, xch, Lw_, lane, E.C, 16, 10); xch_put(w, xch, Lw_, lane, E.J, 26, 10);
+        xch_put(w, xeA, act, E.A, 16); xch_put(w, xeCJ, act, E.C, 10); xch_put(w, xeCJ + 10, act, E.J, 10);
         w.sync();
         if (act && lane + dl < Lw_) {
             double A2[16], C2[10], J2[10];
+            const double* pA = xeA + (size_t)dl * xstride;
+            const double* pCJ = xeCJ + (size_t)dl * xstride;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) A2[i] = xch[(size_t)i * Lw_ + lane + dl];
+            for (int i = 0; i < 16; ++i) A2[i] = pA[i];
 #pragma unroll
-            for (int i = 0; i < 10; ++i) { C2[i] = xch[(size_t)(16 + i) * Lw_ + lane + dl]; J2[i] = xch[(size_t)(26 + i) * Lw_ + lane + dl]; }
+            for (int i = 0; i < 10; ++i) { C2[i] = pCJ[i]; J2[i] = pCJ[10 + i]; }
             elem_combine(E, A2, C2, J2);
         }
     }
     w.sync();
-    xch_put(w, xch, Lw_, lane, E.J, 26, 10);
+    xch_put(w, xeCJ + 10, act, E.J, 10);
     w.sync();
     double P[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};          // P at the right boundary of the chunk
     if (act && lane + 1 < Lw_) {
 #pragma unroll
-        for (int i = 0; i < 10; ++i) P[i] = xch[(size_t)(26 + i) * Lw_ + lane + 1];
+        for (int i = 0; i < 10; ++i) P[i] = xeCJ[xstride + 10 + i];
     }
     QW_TICK(3);
     // ================= (4) local Riccati over the chunk: K_k, Cholesky, P_k, P_{k+1} r_b =================
