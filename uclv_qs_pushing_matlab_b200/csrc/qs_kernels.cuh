@@ -193,18 +193,26 @@ __global__ void __launch_bounds__(32) k_qp(SolverDev S, IpmOpts o, int ppw, int 
     qp_one(S, o, b, apply);
 }
 
-// K4 v2: warp per problem, persistent CTAs of QW_WARPS warps (one CTA per SM); finished warps pull the next
-// problem from a global work queue (S.ndone[1]); the IPM state of each problem lives in its warp's slice of
-// the dynamic shared memory.
-#ifndef QW_WARPS_DEF
-#define QW_WARPS_DEF 6
-#endif
-constexpr int QW_WARPS = QW_WARPS_DEF;
+// K4 v2: warp per problem, persistent CTAs of up to QW_MAX_WARPS warps (one CTA per SM); finished warps pull the
+// next problem from a global work queue (S.ndone[1]).  The IPM state of each problem lives in its warp's slice of
+// the dynamic shared memory; the read-only linearisation lives in tensor memory: the CTA allocates all 512 TMEM
+// columns, warp w owns TMEM lanes 32*(w%4).. (the quarter the hardware lets it address) and columns 256*(w/4)..
+constexpr int QW_MAX_WARPS = 8;
 template <int C>
-__global__ void __launch_bounds__(32 * QW_WARPS, 1) k_qp_warp(SolverDev S, IpmOpts o, int apply, int per_warp_doubles) {
+__global__ void __launch_bounds__(32 * QW_MAX_WARPS, 1) k_qp_warp(SolverDev S, IpmOpts o, int apply, int per_warp_doubles) {
     extern __shared__ __align__(16) double qw_smem[];
+    __shared__ unsigned tmem_base;
     const int wid = threadIdx.x >> 5;
-    WarpCtxDev w{(int)(threadIdx.x & 31)};
+    if (wid == 0) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&tmem_base);
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(dst) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tbase = tmem_base;
+    WarpCtxDev w{(int)(threadIdx.x & 31), tbase + (((unsigned)(wid & 3) * 32u) << 16) + (unsigned)(wid >> 2) * 256u};
     auto next = [&]() -> int {
         int b = -1;
         for (;;) {
@@ -215,6 +223,10 @@ __global__ void __launch_bounds__(32 * QW_WARPS, 1) k_qp_warp(SolverDev S, IpmOp
         }
     };
     qp_warp_persistent<WarpCtxDev, C>(w, qw_smem + (size_t)wid * per_warp_doubles, S, o, apply, next);
+    // every warp left the loop through the same CTA-wide vote: no TMEM access is in flight any more
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tbase) : "memory");
 }
 
 __global__ void __launch_bounds__(64) k_nlp_res(SolverDev S, SqpOpts o, int it) {

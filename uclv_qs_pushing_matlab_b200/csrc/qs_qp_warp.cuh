@@ -27,8 +27,61 @@
 namespace qs {
 
 #if defined(__CUDACC__)
+// tcgen05.ld / tcgen05.st of n doubles (2n 32-bit columns) of this thread's TMEM lane.  The instructions are
+// warp-collective (.sync.aligned): callers keep them outside lane-divergent code, the __syncwarp() in front
+// re-converges lanes that left the previous loop iteration through different paths.
+#define QW_TM_REGS8 "t0,t1,t2,t3,t4,t5,t6,t7"
+#define QW_TM_REGS16 QW_TM_REGS8 ",t8,t9,t10,t11,t12,t13,t14,t15"
+#define QW_TM_REGS32 QW_TM_REGS16 ",t16,t17,t18,t19,t20,t21,t22,t23,t24,t25,t26,t27,t28,t29,t30,t31"
 struct WarpCtxDev {
     int lane_;
+    unsigned tm_;        // TMEM address of this warp's private block: (32 * (warp % 4)) << 16 | first column
+    template <int n> __device__ __forceinline__ void tm_ld(int off, double* v) const {
+        static_assert(n == 4 || n == 8 || n == 16, "tm_ld: 4, 8 or 16 doubles");
+        const unsigned a = tm_ + 2u * (unsigned)off;
+        __syncwarp();
+        if constexpr (n == 4) {
+            asm volatile("{\n\t.reg .b32 t<8>;\n\t"
+                         "tcgen05.ld.sync.aligned.32x32b.x8.b32 {" QW_TM_REGS8 "}, [%4];\n\t"
+                         "tcgen05.wait::ld.sync.aligned;\n\t"
+                         "mov.b64 %0, {t0,t1};\n\tmov.b64 %1, {t2,t3};\n\tmov.b64 %2, {t4,t5};\n\tmov.b64 %3, {t6,t7};\n\t}"
+                         : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "r"(a) : "memory");
+        } else if constexpr (n == 8) {
+            asm volatile("{\n\t.reg .b32 t<16>;\n\t"
+                         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {" QW_TM_REGS16 "}, [%8];\n\t"
+                         "tcgen05.wait::ld.sync.aligned;\n\t"
+                         "mov.b64 %0, {t0,t1};\n\tmov.b64 %1, {t2,t3};\n\tmov.b64 %2, {t4,t5};\n\tmov.b64 %3, {t6,t7};\n\t"
+                         "mov.b64 %4, {t8,t9};\n\tmov.b64 %5, {t10,t11};\n\tmov.b64 %6, {t12,t13};\n\tmov.b64 %7, {t14,t15};\n\t}"
+                         : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]), "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7])
+                         : "r"(a) : "memory");
+        } else {
+            asm volatile("{\n\t.reg .b32 t<32>;\n\t"
+                         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {" QW_TM_REGS32 "}, [%16];\n\t"
+                         "tcgen05.wait::ld.sync.aligned;\n\t"
+                         "mov.b64 %0, {t0,t1};\n\tmov.b64 %1, {t2,t3};\n\tmov.b64 %2, {t4,t5};\n\tmov.b64 %3, {t6,t7};\n\t"
+                         "mov.b64 %4, {t8,t9};\n\tmov.b64 %5, {t10,t11};\n\tmov.b64 %6, {t12,t13};\n\tmov.b64 %7, {t14,t15};\n\t"
+                         "mov.b64 %8, {t16,t17};\n\tmov.b64 %9, {t18,t19};\n\tmov.b64 %10, {t20,t21};\n\tmov.b64 %11, {t22,t23};\n\t"
+                         "mov.b64 %12, {t24,t25};\n\tmov.b64 %13, {t26,t27};\n\tmov.b64 %14, {t28,t29};\n\tmov.b64 %15, {t30,t31};\n\t}"
+                         : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]), "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7]),
+                           "=d"(v[8]), "=d"(v[9]), "=d"(v[10]), "=d"(v[11]), "=d"(v[12]), "=d"(v[13]), "=d"(v[14]), "=d"(v[15])
+                         : "r"(a) : "memory");
+        }
+    }
+    // 16 doubles -> 32 columns
+    __device__ __forceinline__ void tm_st16(int off, const double* v) const {
+        const unsigned a = tm_ + 2u * (unsigned)off;
+        __syncwarp();
+        asm volatile("{\n\t.reg .b32 t<32>;\n\t"
+                     "mov.b64 {t0,t1}, %1;\n\tmov.b64 {t2,t3}, %2;\n\tmov.b64 {t4,t5}, %3;\n\tmov.b64 {t6,t7}, %4;\n\t"
+                     "mov.b64 {t8,t9}, %5;\n\tmov.b64 {t10,t11}, %6;\n\tmov.b64 {t12,t13}, %7;\n\tmov.b64 {t14,t15}, %8;\n\t"
+                     "mov.b64 {t16,t17}, %9;\n\tmov.b64 {t18,t19}, %10;\n\tmov.b64 {t20,t21}, %11;\n\tmov.b64 {t22,t23}, %12;\n\t"
+                     "mov.b64 {t24,t25}, %13;\n\tmov.b64 {t26,t27}, %14;\n\tmov.b64 {t28,t29}, %15;\n\tmov.b64 {t30,t31}, %16;\n\t"
+                     "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {" QW_TM_REGS32 "};\n\t"
+                     "tcgen05.wait::st.sync.aligned;\n\t}"
+                     :: "r"(a), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]), "d"(v[4]), "d"(v[5]), "d"(v[6]), "d"(v[7]),
+                        "d"(v[8]), "d"(v[9]), "d"(v[10]), "d"(v[11]), "d"(v[12]), "d"(v[13]), "d"(v[14]), "d"(v[15])
+                     : "memory");
+    }
     __device__ __forceinline__ int lane() const { return lane_; }
     __device__ __forceinline__ double shfl(double v, int src) const { return __shfl_sync(0xffffffffu, v, src & 31); }
     __device__ __forceinline__ double wmax(double v) const {
@@ -67,16 +120,23 @@ __device__ unsigned long long qw_prof[16];
 #define QW_TICK(slot) do { } while (0)
 #endif
 
-// rows of the per-problem shared-memory state.  Layout: one RECORD of R_ROWS doubles per (local stage j, lane l) at
-// sm[(j*L + l)*R_ROWS + row]: a row access is a compile-time immediate offset from the record pointer (no integer
-// address arithmetic), and the odd record stride (101) makes the 64-bit accesses of a half-warp conflict-free.
+// Per-problem state.  Two on-chip homes:
+//   * shared memory: one RECORD of R_ROWS doubles per (local stage j, lane l) at sm[(j*L + l)*R_ROWS + row]: a row
+//     access is a compile-time immediate offset from the record pointer (no integer address arithmetic), and the odd
+//     record stride makes the 64-bit accesses of a half-warp conflict-free;
+//   * tensor memory (TMEM): the read-only linearisation of the stage (A, B, b, h, g: 29 doubles, padded to
+//     QW_TM_STAGE = 32) sits in the lane's own TMEM lane, 64 columns per local stage, written once per problem and
+//     read back with tcgen05.ld.  TMEM is otherwise idle in this kernel; moving these rows out of the records brings
+//     the record from 101 to 73 doubles, i.e. 8 instead of 6 resident problems per SM at N = 40 (shared memory is
+//     what bounds the number of resident warps).
 enum : int {
-    R_A3 = 0, R_A4 = 4, R_B1 = 8, R_B2 = 12, R_BV = 16, R_G = 20, R_HH = 26,      // linearisation (29)
-    R_Z = 29, R_PIK = 35, R_LAM = 39, R_T = 45,                                    // point (22): z, pi_k, lam, t
-    R_RG = 51, R_RB = 57, R_K = 61, R_LI = 69, R_P = 72, R_PB = 82, R_DZA = 86,    // residuals, factor, P_k, P_{k+1} r_b, affine step
-    R_GT = 89, R_PV = 95, R_KFF = 99,                                              // rhs / step (aliased), p_k, k_ff
-    R_ROWS = 101
+    R_Z = 0, R_PIK = 6, R_LAM = 10, R_T = 16,                                      // point (22): z, pi_k, lam, t
+    R_RG = 22, R_RB = 28, R_K = 32, R_LI = 40, R_P = 43, R_PB = 53, R_DZA = 57,    // residuals, factor, P_k, P_{k+1} r_b, affine step
+    R_GT = 60, R_PV = 66, R_KFF = 70,                                              // rhs / step (aliased), p_k, k_ff
+    R_ROWS = 73
 };
+// offsets (doubles) inside the TMEM block of one local stage
+enum : int { QW_TM_AB = 0, QW_TM_BV = 16, QW_TM_HH = 20, QW_TM_G = 24, QW_TM_STAGE = 32 };
 QS_HD constexpr int qp_warp_chunk(int N) { return (N + 1 + 31) / 32; }
 QS_HD constexpr int qp_warp_lanes(int N, int C) { return (N + 1 + C - 1) / C; }
 // Exchange areas of the warp scans.  Affine maps (M 16, d 4): a dedicated area behind the records, odd stride 21 per
@@ -284,6 +344,22 @@ QS_HD IneqStep ineq_step(double v, double dva, double dv, double ll, double lu, 
 
 #define QW_SM(row, j) sm[((size_t)(j) * Lw_ + lane) * R_ROWS + (row)]
 
+// A_k (columns 3, 4) and B_k of local stage j from the lane's TMEM block (warp-collective: every lane calls it)
+template <class Ctx>
+QS_HD void qw_ld_lin(const Ctx& w, int j, StageLin& L) {
+    double v[16];
+    w.template tm_ld<16>(j * QW_TM_STAGE + QW_TM_AB, v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { L.a3[i] = v[i]; L.a4[i] = v[4 + i]; L.b1[i] = v[8 + i]; L.b2[i] = v[12 + i]; }
+}
+// h_k = (s, u_n, u_t) at the linearisation point
+template <class Ctx>
+QS_HD void qw_ld_h(const Ctx& w, int j, double* h) {
+    double v[4];
+    w.template tm_ld<4>(j * QW_TM_STAGE + QW_TM_HH, v);
+    h[0] = v[0]; h[1] = v[1]; h[2] = v[2];
+}
+
 // One Newton solve with the current factorisation: rhs gt (R_GT rows) and r_b (R_RB) ->
 // step dz (R_GT rows, aliased), costate offsets p_k (R_PV), feed-forward k_ff (R_KFF).
 template <class Ctx, int C>
@@ -297,11 +373,13 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
     for (int i = 0; i < 16; ++i) M[i] = (i % 5 == 0) ? 1.0 : 0.0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) d[i] = 0.0;
-    if (act) {
+    {
 #pragma unroll 1
         for (int j = C - 1; j >= 0; --j) {
             const int k = lane * C + j;
-            if (k > N) continue;
+            StageLin L;
+            qw_ld_lin(w, j, L);
+            if (!act || k > N) continue;
             if (k == N) {                                       // terminal: p_N = rg_N (constant map)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) M[i] = 0.0;
@@ -310,9 +388,6 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
                 acc_identity = false;
                 continue;
             }
-            StageLin L;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
             double gt[6], Pb[4], K0[4], K1[4], Li[3], m[6];
 #pragma unroll
             for (int i = 0; i < 6; ++i) gt[i] = QW_SM(R_GT + i, j);
@@ -368,19 +443,18 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
         for (int i = 0; i < 4; ++i) pe[i] = xa[QW_XA + 16 + i];
     }
     // ---- (c) local back-substitution: k_ff and p_k
-    if (act) {
+    {
 #pragma unroll 1
         for (int j = C - 1; j >= 0; --j) {
             const int k = lane * C + j;
-            if (k > N) continue;
+            StageLin L;
+            qw_ld_lin(w, j, L);
+            if (!act || k > N) continue;
             if (k == N) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) pe[i] = QW_SM(R_PV + i, j);
                 continue;
             }
-            StageLin L;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
             double K0[4], K1[4], Li[3];
 #pragma unroll
             for (int i = 0; i < 4; ++i) { K0[i] = QW_SM(R_K + i, j); K1[i] = QW_SM(R_K + 4 + i, j); }
@@ -406,14 +480,13 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
     for (int i = 0; i < 16; ++i) M[i] = (i % 5 == 0) ? 1.0 : 0.0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) d[i] = 0.0;
-    if (act) {
+    {
 #pragma unroll 1
         for (int j = 0; j < C; ++j) {
             const int k = lane * C + j;
-            if (k >= N) continue;
             StageLin L;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
+            qw_ld_lin(w, j, L);
+            if (!act || k >= N) continue;
             double K0[4], K1[4], Ab[16], bb[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) { K0[i] = QW_SM(R_K + i, j); K1[i] = QW_SM(R_K + 4 + i, j); }
@@ -452,20 +525,19 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
 #pragma unroll
         for (int i = 0; i < 4; ++i) x[i] = xa[16 + i - QW_XA];
     }
-    if (act) {
+    {
 #pragma unroll 1
         for (int j = 0; j < C; ++j) {
             const int k = lane * C + j;
-            if (k > N) continue;
+            StageLin L;
+            qw_ld_lin(w, j, L);
+            if (!act || k > N) continue;
             if (k == N) {
                 QW_SM(R_GT + 0, j) = 0.0; QW_SM(R_GT + 1, j) = 0.0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) QW_SM(R_GT + 2 + i, j) = x[i];
                 continue;
             }
-            StageLin L;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
             double K0[4], K1[4], bk[4], kff[2], u[2];
 #pragma unroll
             for (int i = 0; i < 4; ++i) { K0[i] = QW_SM(R_K + i, j); K1[i] = QW_SM(R_K + 4 + i, j); bk[i] = QW_SM(R_RB + i, j); }
@@ -494,39 +566,46 @@ QS_HD void qw_init(const Ctx& w, double* __restrict__ sm, const QpConst& Q, cons
     const int lane = w.lane();
     const int Lw_ = qp_warp_lanes(N, C);
     const bool act = lane < Lw_;
-    // ---------------- load the linearisation, initial point
-    if (act) {
+    // ---------------- load the linearisation (into the lane's TMEM block), initial point
 #pragma unroll 1
-        for (int j = 0; j < C; ++j) {
-            const int k = lane * C + j;
-            if (k > N) continue;
+    for (int j = 0; j < C; ++j) {
+        const int k = lane * C + j;
+        const bool on = act && k < N;
+        double v[QW_TM_STAGE];
+#pragma unroll
+        for (int i = 0; i < QW_TM_STAGE; ++i) v[i] = 0.0;
+        if (act && k <= N) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) QW_SM(R_Z + i, j) = 0.0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) QW_SM(R_PIK + i, j) = 0.0;
-            if (k == N) continue;
+        }
+        if (on) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                QW_SM(R_A3 + i, j) = QS_AT(V.A, k, 8, i); QW_SM(R_A4 + i, j) = QS_AT(V.A, k, 8, 4 + i);
-                QW_SM(R_B1 + i, j) = QS_AT(V.B, k, 8, i); QW_SM(R_B2 + i, j) = QS_AT(V.B, k, 8, 4 + i);
-                QW_SM(R_BV + i, j) = QS_AT(V.b, k, 4, i);
+                v[QW_TM_AB + i] = QS_AT(V.A, k, 8, i); v[QW_TM_AB + 4 + i] = QS_AT(V.A, k, 8, 4 + i);
+                v[QW_TM_AB + 8 + i] = QS_AT(V.B, k, 8, i); v[QW_TM_AB + 12 + i] = QS_AT(V.B, k, 8, 4 + i);
+                v[QW_TM_BV + i] = QS_AT(V.b, k, 4, i);
             }
 #pragma unroll
-            for (int i = 0; i < 6; ++i) QW_SM(R_G + i, j) = QS_AT(V.g, k, 6, i);
-            const double h[3] = {QS_AT(V.x, k, 4, 3), QS_AT(V.u, k, 2, 0), QS_AT(V.u, k, 2, 1)};
-#pragma unroll
-            for (int c = 0; c < 3; ++c) QW_SM(R_HH + c, j) = h[c];
+            for (int i = 0; i < 6; ++i) v[QW_TM_G + i] = QS_AT(V.g, k, 6, i);
+            v[QW_TM_HH + 0] = QS_AT(V.x, k, 4, 3); v[QW_TM_HH + 1] = QS_AT(V.u, k, 2, 0); v[QW_TM_HH + 2] = QS_AT(V.u, k, 2, 1);
+        }
+        w.tm_st16(j * QW_TM_STAGE, v);                      // warp-collective: every lane stores (zeros when idle)
+        w.tm_st16(j * QW_TM_STAGE + 16, v + 16);
+        if (on) {
+            const double* h = v + QW_TM_HH;
             if (k == 0) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) QW_SM(R_Z + 2 + i, j) = V.dx0[i * V.stride];
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const bool on = !(k == 0 && c == 0);
-                const double v = QW_SM(R_Z + cidx(c), j);
-                double tl = fmax(v - (Q.lh[c] - h[c]), Q.thr), tu = fmax((Q.uh[c] - h[c]) - v, Q.thr);
+                const bool bon = !(k == 0 && c == 0);
+                const double z = QW_SM(R_Z + cidx(c), j);
+                double tl = fmax(z - (Q.lh[c] - h[c]), Q.thr), tu = fmax((Q.uh[c] - h[c]) - z, Q.thr);
                 double ll = Q.mu0 / tl, lu = Q.mu0 / tu;
-                if (!on) { tl = 1.0; tu = 1.0; ll = 0.0; lu = 0.0; }
+                if (!bon) { tl = 1.0; tu = 1.0; ll = 0.0; lu = 0.0; }
                 QW_SM(R_T + c, j) = tl; QW_SM(R_T + 3 + c, j) = tu;
                 QW_SM(R_LAM + c, j) = ll; QW_SM(R_LAM + 3 + c, j) = lu;
             }
@@ -566,11 +645,17 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
     }
     double l_stat = 0.0, l_eq = 0.0, l_in = 0.0, l_cp = 0.0, l_mu = 0.0;
     bool l_nan = false;
-    if (act) {
+    {
 #pragma unroll 1
         for (int j = C - 1; j >= 0; --j) {
             const int k = lane * C + j;
-            if (k > N) continue;
+            StageLin L;
+            double gk[8], hk[4], bv[4];
+            qw_ld_lin(w, j, L);
+            w.template tm_ld<8>(j * QW_TM_STAGE + QW_TM_G, gk);
+            w.template tm_ld<4>(j * QW_TM_STAGE + QW_TM_HH, hk);
+            w.template tm_ld<4>(j * QW_TM_STAGE + QW_TM_BV, bv);
+            if (!act || k > N) continue;
             double z6[6], pik[4];
 #pragma unroll
             for (int i = 0; i < 6; ++i) z6[i] = QW_SM(R_Z + i, j);
@@ -582,14 +667,11 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { rg[i] += qN[i] - pik[i]; QW_SM(R_RG + 2 + i, j) = rg[i]; l_stat = fmax(l_stat, fabs(rg[i])); l_nan = l_nan || !(rg[i] == rg[i]); }
             } else {
-                StageLin L;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
                 const double* Hk = Q.H + (size_t)k * 21;
                 double gh[6], rg[6];
 #pragma unroll
                 for (int i = 0; i < 6; ++i) {
-                    double a = QW_SM(R_G + i, j);
+                    double a = gk[i];
 #pragma unroll
                     for (int q = 0; q < 6; ++q) a = fma(Hk[LT(i, q)], z6[q], a);
                     gh[i] = a;
@@ -600,7 +682,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     if (k == 0 && c == 0) continue;
-                    const double h = QW_SM(R_HH + c, j), v = z6[cidx(c)];
+                    const double h = hk[c], v = z6[cidx(c)];
                     const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
                     rg[cidx(c)] += lu - ll;
                     const double rdl = v - (Q.lh[c] - h) - tl, rdu = (Q.uh[c] - h) - v - tu;
@@ -613,7 +695,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                 for (int i = 0; i < 6; ++i) { QW_SM(R_RG + i, j) = rg[i]; l_stat = fmax(l_stat, fabs(rg[i])); l_nan = l_nan || !(rg[i] == rg[i]); }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    double a = QW_SM(R_BV + i, j) + (i < 2 ? z6[2 + i] : 0.0) - nx[i];
+                    double a = bv[i] + (i < 2 ? z6[2 + i] : 0.0) - nx[i];
                     a = fma(L.a3[i], z6[4], a); a = fma(L.a4[i], z6[5], a);
                     a = fma(L.b1[i], z6[0], a); a = fma(L.b2[i], z6[1], a);
                     QW_SM(R_RB + i, j) = a; l_eq = fmax(l_eq, fabs(a)); l_nan = l_nan || !(a == a);
@@ -638,11 +720,15 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
     // ================= (2) barrier terms, affine rhs, stage elements, chunk aggregate =================
     Elem E; elem_identity(E);
     bool E_is_identity = true;                              // combining with the identity is a copy: skip the arithmetic
-    if (act) {
+    {
 #pragma unroll 1
         for (int j = C - 1; j >= 0; --j) {
             const int k = lane * C + j;
-            if (k > N) continue;
+            StageLin L;
+            double hk[3];
+            qw_ld_lin(w, j, L);
+            qw_ld_h(w, j, hk);
+            if (!act || k > N) continue;
             if (k == N) {                                   // terminal value function: J = Q_N, A = 0, C = 0
 #pragma unroll
                 for (int i = 0; i < 16; ++i) E.A[i] = 0.0;
@@ -657,7 +743,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             for (int i = 0; i < 6; ++i) gt[i] = QW_SM(R_RG + i, j);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const double h = QW_SM(R_HH + c, j), v = QW_SM(R_Z + cidx(c), j);
+                const double h = hk[c], v = QW_SM(R_Z + cidx(c), j);
                 const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
                 const double itl = 1.0 / tl, itu = 1.0 / tu;
                 const bool on = !(k == 0 && c == 0);
@@ -670,9 +756,6 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             // element of stage k: eliminate u.  Rt = H_uu + D_u, S = H_ux, Qt = H_xx + D_s
             const double r00 = Hk[LT(0, 0)] + D[1], r10 = Hk[LT(1, 0)], r11 = Hk[LT(1, 1)] + D[2];
             const double i00 = qs_rsqrt(r00), l10 = r10 * i00, i11 = qs_rsqrt(r11 - l10 * l10);
-            StageLin L;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
             // Bh = B Lr^-T  (4x2):  columns of B R^-1 B' = Bh Bh'
             double bh0[4], bh1[4], sh0[4], sh1[4];             // Sh = Lr^-1 S (2x4)
 #pragma unroll
@@ -738,19 +821,18 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
     QW_TICK(3);
     // ================= (4) local Riccati over the chunk: K_k, Cholesky, P_k, P_{k+1} r_b =================
     bool ok = true;
-    if (act) {
+    {
 #pragma unroll 1
         for (int j = C - 1; j >= 0; --j) {
             const int k = lane * C + j;
-            if (k > N) continue;
+            StageLin L;
+            qw_ld_lin(w, j, L);
+            if (!act || k > N) continue;
             if (k == N) {
 #pragma unroll
                 for (int i = 0; i < 10; ++i) { P[i] = Q.QN[i]; QW_SM(R_P + i, j) = P[i]; }
                 continue;
             }
-            StageLin L;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { L.a3[i] = QW_SM(R_A3 + i, j); L.a4[i] = QW_SM(R_A4 + i, j); L.b1[i] = QW_SM(R_B1 + i, j); L.b2[i] = QW_SM(R_B2 + i, j); }
             double D[3], rb[4], Pb[4], K0[4], K1[4], Li[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) D[c] = QW_SM(R_LAM + c, j) / QW_SM(R_T + c, j) + QW_SM(R_LAM + 3 + c, j) / QW_SM(R_T + 3 + c, j);
@@ -772,19 +854,21 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
     double smu = 0.0;
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-        if (pass == 1 && act) {
+        if (pass == 1) {
             // corrector rhs
 #pragma unroll 1
             for (int j = 0; j < C; ++j) {
                 const int k = lane * C + j;
-                if (k >= N) continue;
+                double hk[3];
+                qw_ld_h(w, j, hk);
+                if (!act || k >= N) continue;
                 double gt[6];
 #pragma unroll
                 for (int i = 0; i < 6; ++i) gt[i] = QW_SM(R_RG + i, j);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     if (k == 0 && c == 0) continue;
-                    const double h = QW_SM(R_HH + c, j), v = QW_SM(R_Z + cidx(c), j), dva = QW_SM(R_DZA + c, j);
+                    const double h = hk[c], v = QW_SM(R_Z + cidx(c), j), dva = QW_SM(R_DZA + c, j);
                     const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
                     const double rdl = v - (Q.lh[c] - h) - tl, rdu = (Q.uh[c] - h) - v - tu;
                     const double dtl = dva + rdl, dtu = -dva + rdu;
@@ -802,17 +886,19 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
         if (pass == 0) {
             // step to the boundary of the affine step, mu_aff, centering parameter
             double a_aff = 1.0, a_num = 1.0, a_den = 1.0, S1 = 0.0, S2 = 0.0;
-            if (act) {
+            {
 #pragma unroll 1
                 for (int j = 0; j < C; ++j) {
                     const int k = lane * C + j;
-                    if (k >= N) continue;
+                    double hk[3];
+                    qw_ld_h(w, j, hk);
+                    if (!act || k >= N) continue;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         const double dva = QW_SM(R_GT + cidx(c), j);
                         QW_SM(R_DZA + c, j) = dva;
                         if (k == 0 && c == 0) continue;
-                        const double h = QW_SM(R_HH + c, j), v = QW_SM(R_Z + cidx(c), j);
+                        const double h = hk[c], v = QW_SM(R_Z + cidx(c), j);
                         const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
                         const double dtl = dva + (v - (Q.lh[c] - h) - tl), dtu = -dva + ((Q.uh[c] - h) - v - tu);
                         const double dll = -ll - ll * dtl * (1.0 / tl), dlu = -lu - lu * dtu * (1.0 / tu);
@@ -833,17 +919,19 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
     QW_TICK(7);
     // ================= (8) step length and update =================
     double a_max = 1.0, m_num = 1.0, m_den = 1.0;
-    if (act) {
+    {
 #pragma unroll 1
         for (int j = 0; j < C; ++j) {
             const int k = lane * C + j;
-            if (k >= N) continue;
+            double hk[3];
+            qw_ld_h(w, j, hk);
+            if (!act || k >= N) continue;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 if (k == 0 && c == 0) continue;
                 IneqStep s_ = ineq_step(QW_SM(R_Z + cidx(c), j), QW_SM(R_DZA + c, j), QW_SM(R_GT + cidx(c), j),
                                         QW_SM(R_LAM + c, j), QW_SM(R_LAM + 3 + c, j), QW_SM(R_T + c, j), QW_SM(R_T + 3 + c, j),
-                                        Q.lh[c] - QW_SM(R_HH + c, j), Q.uh[c] - QW_SM(R_HH + c, j), smu);
+                                        Q.lh[c] - hk[c], Q.uh[c] - hk[c], smu);
                 ratio_min(QW_SM(R_T + c, j), s_.dtl, m_num, m_den); ratio_min(QW_SM(R_T + 3 + c, j), s_.dtu, m_num, m_den);
                 ratio_min(QW_SM(R_LAM + c, j), s_.dll, m_num, m_den); ratio_min(QW_SM(R_LAM + 3 + c, j), s_.dlu, m_num, m_den);
             }
@@ -852,11 +940,13 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
     a_max = w.wmin(fmin(a_max, m_num / m_den));
     const double alpha = fmin(1.0, Q.tau * a_max);
     if (!(alpha == alpha)) { status = 2; return 1; }
-    if (act) {
+    {
 #pragma unroll 1
         for (int j = 0; j < C; ++j) {
             const int k = lane * C + j;
-            if (k > N) continue;
+            double hk[3];
+            qw_ld_h(w, j, hk);
+            if (!act || k > N) continue;
             double dz[6];
 #pragma unroll
             for (int i = 0; i < 6; ++i) dz[i] = QW_SM(R_GT + i, j);
@@ -874,7 +964,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                     if (k == 0 && c == 0) continue;
                     IneqStep s_ = ineq_step(QW_SM(R_Z + cidx(c), j), QW_SM(R_DZA + c, j), dz[cidx(c)],
                                             QW_SM(R_LAM + c, j), QW_SM(R_LAM + 3 + c, j), QW_SM(R_T + c, j), QW_SM(R_T + 3 + c, j),
-                                            Q.lh[c] - QW_SM(R_HH + c, j), Q.uh[c] - QW_SM(R_HH + c, j), smu);
+                                            Q.lh[c] - hk[c], Q.uh[c] - hk[c], smu);
                     QW_SM(R_T + c, j) = fma(alpha, s_.dtl, QW_SM(R_T + c, j));
                     QW_SM(R_T + 3 + c, j) = fma(alpha, s_.dtu, QW_SM(R_T + 3 + c, j));
                     QW_SM(R_LAM + c, j) = fma(alpha, s_.dll, QW_SM(R_LAM + c, j));

@@ -528,21 +528,28 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
     // auto (2): the warp-per-problem kernel wins while the batch cannot fill the GPU with one problem per thread
     // (measured crossover on B200 at N = 40: ~12k problems; 1.0M it/s flat vs 0.37M -> 2.0M it/s), DESIGN.md 4.1
     const bool want_warp = s->opts.qp_kernel == 1 || (s->opts.qp_kernel == 2 && s->B < 12288);
-    const bool warp = want_warp && C <= 4 && qp_warp_smem_doubles(s->N) * 8 * QW_WARPS <= 220 * 1024;
+    // resident problems (= warps) per CTA: bounded by shared memory (one CTA per SM), by the register file
+    // (8 warps of 255 registers) and by TMEM (8 blocks of 32 lanes x 256 columns)
+    const int pwd = (int)((qp_warp_smem_doubles(s->N) + 1) / 2 * 2);
+    const size_t smem_cap = 227 * 1024 - 1024;                                       // static __shared__ + reserve
+    const int W = (int)std::min<size_t>(QW_MAX_WARPS, smem_cap / ((size_t)pwd * sizeof(double)));
+    const bool warp = want_warp && C <= 4 && W >= 2;
     if (!warp && s->opts.qp_kernel == 2 && s->opts.problems_per_warp == 0) ppw = (s->B >= 12288) ? 32 : ppw;
     if (!warp) {
         k_qp<<<(unsigned)((s->B + ppw - 1) / ppw), 32, 0, s->stream>>>(D, io, ppw, apply);
         return QSPUSH_OK;
     }
-    const int pwd = (int)((qp_warp_smem_doubles(s->N) + 1) / 2 * 2);
-    const size_t smem = (size_t)pwd * QW_WARPS * sizeof(double);
+    // at least half of the SM's shared memory, so that two CTAs (both wanting all TMEM columns) never share an SM
+    const size_t smem = std::max((size_t)pwd * W * sizeof(double), (size_t)116 * 1024);   // (sized for W warps, Wl <= W used)
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device);
-    const unsigned blocks = (unsigned)std::min((s->B + QW_WARPS - 1) / QW_WARPS, nsm);   // persistent: one CTA per SM
+    // small batches: spread the problems over the SMs first (a warp alone on an SM runs its problem fastest)
+    const int Wl = std::max(1, std::min(W, (s->B + nsm - 1) / nsm));
+    const unsigned blocks = (unsigned)std::min((s->B + Wl - 1) / Wl, nsm);             // persistent: one CTA per SM
     CK(cudaMemsetAsync(D.ndone + 1, 0, sizeof(int), s->stream));                       // work-queue head
 #define QW_LAUNCH(CC)                                                                                              \
     CK(cudaFuncSetAttribute(k_qp_warp<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
-    k_qp_warp<CC><<<blocks, 32 * QW_WARPS, smem, s->stream>>>(D, io, apply, pwd)
+    k_qp_warp<CC><<<blocks, 32 * Wl, smem, s->stream>>>(D, io, apply, pwd)
     switch (C) {
         case 1: QW_LAUNCH(1); break;
         case 2: QW_LAUNCH(2); break;
