@@ -55,7 +55,7 @@ struct WarpEmu {
     static constexpr int W = 32;
     static constexpr size_t STACK = 512 * 1024;
     double xbuf[2][W];
-    double tm[W][128];                            // emulated TMEM: 256 32-bit columns per lane, private to the lane
+    double tm[W][256];                            // emulated TMEM: 512 32-bit columns per lane, private to the lane
     int count[W];
     void* sp[W];
     void* main_sp = nullptr;
@@ -82,7 +82,7 @@ static void emu_run(void (*body)(int, void*), void* arg) {
     e.stacks.assign(WarpEmu::W * WarpEmu::STACK, 0);
     for (int l = 0; l < WarpEmu::W; ++l) {
         e.done[l] = false; e.count[l] = 0;
-        for (int i = 0; i < 128; ++i) e.tm[l][i] = std::nan("");      // uninitialised TMEM must never reach the arithmetic
+        for (int i = 0; i < 256; ++i) e.tm[l][i] = std::nan("");      // uninitialised TMEM must never reach the arithmetic
         char* top = e.stacks.data() + (size_t)(l + 1) * WarpEmu::STACK;
         top = (char*)((uintptr_t)top & ~(uintptr_t)15);
         void** p = (void**)top;
@@ -133,6 +133,7 @@ struct WarpCtxHost {
     // tensor-memory block of the lane (tcgen05.ld / tcgen05.st on the device; warp-collective there, so the emulator
     // makes them collectives too: a lane that skips one deadlocks the emulated warp instead of passing silently)
     template <int n> void tm_ld(int off, double* v) const { sync(); for (int i = 0; i < n; ++i) v[i] = g_emu->tm[lane_][off + i]; }
+    template <int n> void tm_st(int off, const double* v) const { sync(); for (int i = 0; i < n; ++i) g_emu->tm[lane_][off + i] = v[i]; }
     void tm_st16(int off, const double* v) const { sync(); for (int i = 0; i < 16; ++i) g_emu->tm[lane_][off + i] = v[i]; }
 };
 

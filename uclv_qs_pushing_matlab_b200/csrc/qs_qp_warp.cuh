@@ -67,6 +67,25 @@ struct WarpCtxDev {
                          : "r"(a) : "memory");
         }
     }
+    template <int n> __device__ __forceinline__ void tm_st(int off, const double* v) const {
+        static_assert(n == 4 || n == 8, "tm_st: 4 or 8 doubles (16: tm_st16)");
+        const unsigned a = tm_ + 2u * (unsigned)off;
+        __syncwarp();
+        if constexpr (n == 4) {
+            asm volatile("{\n\t.reg .b32 t<8>;\n\t"
+                         "mov.b64 {t0,t1}, %1;\n\tmov.b64 {t2,t3}, %2;\n\tmov.b64 {t4,t5}, %3;\n\tmov.b64 {t6,t7}, %4;\n\t"
+                         "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {" QW_TM_REGS8 "};\n\t"
+                         "tcgen05.wait::st.sync.aligned;\n\t}"
+                         :: "r"(a), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+        } else {
+            asm volatile("{\n\t.reg .b32 t<16>;\n\t"
+                         "mov.b64 {t0,t1}, %1;\n\tmov.b64 {t2,t3}, %2;\n\tmov.b64 {t4,t5}, %3;\n\tmov.b64 {t6,t7}, %4;\n\t"
+                         "mov.b64 {t8,t9}, %5;\n\tmov.b64 {t10,t11}, %6;\n\tmov.b64 {t12,t13}, %7;\n\tmov.b64 {t14,t15}, %8;\n\t"
+                         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {" QW_TM_REGS16 "};\n\t"
+                         "tcgen05.wait::st.sync.aligned;\n\t}"
+                         :: "r"(a), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]), "d"(v[4]), "d"(v[5]), "d"(v[6]), "d"(v[7]) : "memory");
+        }
+    }
     // 16 doubles -> 32 columns
     __device__ __forceinline__ void tm_st16(int off, const double* v) const {
         const unsigned a = tm_ + 2u * (unsigned)off;
@@ -136,7 +155,10 @@ enum : int {
     R_ROWS = 73
 };
 // offsets (doubles) inside the TMEM block of one local stage
-enum : int { QW_TM_AB = 0, QW_TM_BV = 16, QW_TM_HH = 20, QW_TM_G = 24, QW_TM_STAGE = 32 };
+// (linearisation 0..31, written once per problem; 32..47 rewritten every IPM iteration in phase (2): the slack
+// reciprocals 1/t_l, 1/t_u and the barrier diagonal D = lam_l/t_l + lam_u/t_u, reused by phases (4)-(8) — 30 FP64
+// divisions per stage and iteration become 6)
+enum : int { QW_TM_AB = 0, QW_TM_BV = 16, QW_TM_HH = 20, QW_TM_G = 24, QW_TM_IT = 32, QW_TM_D = 40, QW_TM_STAGE = 48 };
 QS_HD constexpr int qp_warp_chunk(int N) { return (N + 1 + 31) / 32; }
 QS_HD constexpr int qp_warp_lanes(int N, int C) { return (N + 1 + C - 1) / C; }
 // Exchange areas of the warp scans.  Affine maps (M 16, d 4): a dedicated area behind the records, odd stride 21 per
@@ -330,10 +352,9 @@ QS_HD void ratio_min(double v, double dv, double& num, double& den) {
 
 // Newton step of one two-sided bound pair (lower: t = v - dl, upper: t = du - v), Mehrotra corrector included.
 struct IneqStep { double dtl, dtu, dll, dlu; };
-QS_HD IneqStep ineq_step(double v, double dva, double dv, double ll, double lu, double tl, double tu, double dl, double du, double smu) {
+QS_HD IneqStep ineq_step(double v, double dva, double dv, double ll, double lu, double tl, double tu, double itl, double itu, double dl, double du, double smu) {
     const double rdl = v - dl - tl, rdu = du - v - tu;
     const double dtal = dva + rdl, dtau = -dva + rdu;
-    const double itl = 1.0 / tl, itu = 1.0 / tu;               // one reciprocal per slack instead of two divisions
     const double cl = (-ll - ll * dtal * itl) * dtal, cu = (-lu - lu * dtau * itu) * dtau;
     IneqStep s;
     s.dtl = dv + rdl; s.dtu = -dv + rdu;
@@ -352,6 +373,9 @@ QS_HD void qw_ld_lin(const Ctx& w, int j, StageLin& L) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { L.a3[i] = v[i]; L.a4[i] = v[4 + i]; L.b1[i] = v[8 + i]; L.b2[i] = v[12 + i]; }
 }
+// 1/t_l (0..2) and 1/t_u (4..6) of local stage j, as left by phase (2) of the current iteration
+template <class Ctx>
+QS_HD void qw_ld_it(const Ctx& w, int j, double* it8) { w.template tm_ld<8>(j * QW_TM_STAGE + QW_TM_IT, it8); }
 // h_k = (s, u_n, u_t) at the linearisation point
 template <class Ctx>
 QS_HD void qw_ld_h(const Ctx& w, int j, double* h) {
@@ -728,6 +752,32 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             double hk[3];
             qw_ld_lin(w, j, L);
             qw_ld_h(w, j, hk);
+            // barrier terms first: slack reciprocals and D go to the TMEM block (warp-collective store), affine rhs to R_GT
+            double it8[8], D[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) it8[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) D[i] = 0.0;
+            if (act && k < N) {
+                double gt[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) gt[i] = QW_SM(R_RG + i, j);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const double h = hk[c], v = QW_SM(R_Z + cidx(c), j);
+                    const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
+                    const double itl = 1.0 / tl, itu = 1.0 / tu;
+                    const bool on = !(k == 0 && c == 0);
+                    const double rdl = on ? v - (Q.lh[c] - h) - tl : 0.0, rdu = on ? (Q.uh[c] - h) - v - tu : 0.0;
+                    it8[c] = itl; it8[4 + c] = itu;
+                    D[c] = ll * itl + lu * itu;
+                    gt[cidx(c)] += (ll + ll * rdl * itl) - (lu + lu * rdu * itu);
+                }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) QW_SM(R_GT + i, j) = gt[i];
+            }
+            w.template tm_st<8>(j * QW_TM_STAGE + QW_TM_IT, it8);
+            w.template tm_st<4>(j * QW_TM_STAGE + QW_TM_D, D);
             if (!act || k > N) continue;
             if (k == N) {                                   // terminal value function: J = Q_N, A = 0, C = 0
 #pragma unroll
@@ -738,21 +788,6 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                 continue;
             }
             const double* Hk = Q.H + (size_t)k * 21;
-            double D[3], gt[6];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) gt[i] = QW_SM(R_RG + i, j);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const double h = hk[c], v = QW_SM(R_Z + cidx(c), j);
-                const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
-                const double itl = 1.0 / tl, itu = 1.0 / tu;
-                const bool on = !(k == 0 && c == 0);
-                const double rdl = on ? v - (Q.lh[c] - h) - tl : 0.0, rdu = on ? (Q.uh[c] - h) - v - tu : 0.0;
-                D[c] = ll * itl + lu * itu;
-                gt[cidx(c)] += (ll + ll * rdl * itl) - (lu + lu * rdu * itu);
-            }
-#pragma unroll
-            for (int i = 0; i < 6; ++i) QW_SM(R_GT + i, j) = gt[i];
             // element of stage k: eliminate u.  Rt = H_uu + D_u, S = H_ux, Qt = H_xx + D_s
             const double r00 = Hk[LT(0, 0)] + D[1], r10 = Hk[LT(1, 0)], r11 = Hk[LT(1, 1)] + D[2];
             const double i00 = qs_rsqrt(r00), l10 = r10 * i00, i11 = qs_rsqrt(r11 - l10 * l10);
@@ -826,16 +861,16 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
         for (int j = C - 1; j >= 0; --j) {
             const int k = lane * C + j;
             StageLin L;
+            double D[4];
             qw_ld_lin(w, j, L);
+            w.template tm_ld<4>(j * QW_TM_STAGE + QW_TM_D, D);
             if (!act || k > N) continue;
             if (k == N) {
 #pragma unroll
                 for (int i = 0; i < 10; ++i) { P[i] = Q.QN[i]; QW_SM(R_P + i, j) = P[i]; }
                 continue;
             }
-            double D[3], rb[4], Pb[4], K0[4], K1[4], Li[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) D[c] = QW_SM(R_LAM + c, j) / QW_SM(R_T + c, j) + QW_SM(R_LAM + 3 + c, j) / QW_SM(R_T + 3 + c, j);
+            double rb[4], Pb[4], K0[4], K1[4], Li[3];
 #pragma unroll
             for (int i = 0; i < 4; ++i) rb[i] = QW_SM(R_RB + i, j);
             sym4_mul(P, rb, Pb);
@@ -859,8 +894,9 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
 #pragma unroll 1
             for (int j = 0; j < C; ++j) {
                 const int k = lane * C + j;
-                double hk[3];
+                double hk[3], it8[8];
                 qw_ld_h(w, j, hk);
+                qw_ld_it(w, j, it8);
                 if (!act || k >= N) continue;
                 double gt[6];
 #pragma unroll
@@ -872,7 +908,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                     const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
                     const double rdl = v - (Q.lh[c] - h) - tl, rdu = (Q.uh[c] - h) - v - tu;
                     const double dtl = dva + rdl, dtu = -dva + rdu;
-                    const double itl = 1.0 / tl, itu = 1.0 / tu;
+                    const double itl = it8[c], itu = it8[4 + c];
                     const double cl = (-ll - ll * dtl * itl) * dtl, cu = (-lu - lu * dtu * itu) * dtu;
                     gt[cidx(c)] += (ll * tl - smu + cl + ll * rdl) * itl - (lu * tu - smu + cu + lu * rdu) * itu;
                 }
@@ -890,8 +926,9 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
 #pragma unroll 1
                 for (int j = 0; j < C; ++j) {
                     const int k = lane * C + j;
-                    double hk[3];
+                    double hk[3], it8[8];
                     qw_ld_h(w, j, hk);
+                    qw_ld_it(w, j, it8);
                     if (!act || k >= N) continue;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
@@ -901,7 +938,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                         const double h = hk[c], v = QW_SM(R_Z + cidx(c), j);
                         const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
                         const double dtl = dva + (v - (Q.lh[c] - h) - tl), dtu = -dva + ((Q.uh[c] - h) - v - tu);
-                        const double dll = -ll - ll * dtl * (1.0 / tl), dlu = -lu - lu * dtu * (1.0 / tu);
+                        const double dll = -ll - ll * dtl * it8[c], dlu = -lu - lu * dtu * it8[4 + c];
                         ratio_min(tl, dtl, a_num, a_den); ratio_min(tu, dtu, a_num, a_den);
                         ratio_min(ll, dll, a_num, a_den); ratio_min(lu, dlu, a_num, a_den);
                         S1 += ll * dtl + tl * dll + lu * dtu + tu * dlu;
@@ -923,15 +960,16 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
 #pragma unroll 1
         for (int j = 0; j < C; ++j) {
             const int k = lane * C + j;
-            double hk[3];
+            double hk[3], it8[8];
             qw_ld_h(w, j, hk);
+            qw_ld_it(w, j, it8);
             if (!act || k >= N) continue;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 if (k == 0 && c == 0) continue;
                 IneqStep s_ = ineq_step(QW_SM(R_Z + cidx(c), j), QW_SM(R_DZA + c, j), QW_SM(R_GT + cidx(c), j),
                                         QW_SM(R_LAM + c, j), QW_SM(R_LAM + 3 + c, j), QW_SM(R_T + c, j), QW_SM(R_T + 3 + c, j),
-                                        Q.lh[c] - hk[c], Q.uh[c] - hk[c], smu);
+                                        it8[c], it8[4 + c], Q.lh[c] - hk[c], Q.uh[c] - hk[c], smu);
                 ratio_min(QW_SM(R_T + c, j), s_.dtl, m_num, m_den); ratio_min(QW_SM(R_T + 3 + c, j), s_.dtu, m_num, m_den);
                 ratio_min(QW_SM(R_LAM + c, j), s_.dll, m_num, m_den); ratio_min(QW_SM(R_LAM + 3 + c, j), s_.dlu, m_num, m_den);
             }
@@ -944,8 +982,9 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
 #pragma unroll 1
         for (int j = 0; j < C; ++j) {
             const int k = lane * C + j;
-            double hk[3];
+            double hk[3], it8[8];
             qw_ld_h(w, j, hk);
+            qw_ld_it(w, j, it8);
             if (!act || k > N) continue;
             double dz[6];
 #pragma unroll
@@ -964,7 +1003,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                     if (k == 0 && c == 0) continue;
                     IneqStep s_ = ineq_step(QW_SM(R_Z + cidx(c), j), QW_SM(R_DZA + c, j), dz[cidx(c)],
                                             QW_SM(R_LAM + c, j), QW_SM(R_LAM + 3 + c, j), QW_SM(R_T + c, j), QW_SM(R_T + 3 + c, j),
-                                            Q.lh[c] - hk[c], Q.uh[c] - hk[c], smu);
+                                            it8[c], it8[4 + c], Q.lh[c] - hk[c], Q.uh[c] - hk[c], smu);
                     QW_SM(R_T + c, j) = fma(alpha, s_.dtl, QW_SM(R_T + c, j));
                     QW_SM(R_T + 3 + c, j) = fma(alpha, s_.dtu, QW_SM(R_T + 3 + c, j));
                     QW_SM(R_LAM + c, j) = fma(alpha, s_.dll, QW_SM(R_LAM + c, j));

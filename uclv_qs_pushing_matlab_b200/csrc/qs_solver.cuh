@@ -235,8 +235,26 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm, const Solve
     const int N = S.N;
     QpView V;
     QwState st;
+    // bind problem b to this warp: slab views + linearisation and initial point into shared memory / TMEM.  Done
+    // right after the previous problem finishes, i.e. BEFORE the next lockstep vote: the other warps of the CTA are
+    // still inside their IPM iteration then, so nobody waits for the loads of a newly fetched problem.
+    auto bind = [&](int b_) {
+        V.stride = (size_t)S.Bp;
+        V.A = S.A + b_; V.B = S.Bm + b_; V.b = S.b + b_; V.g = S.g + b_; V.qN = S.qN + b_; V.dx0 = S.dx0 + b_;
+        V.x = S.x + b_; V.u = S.u + b_;
+        V.z = S.z + b_; V.zp = S.zp + b_; V.zc = S.zc + b_; V.t = S.t + b_;
+        V.K = S.K + b_; V.Li = S.Li + b_; V.Pb = S.Pb + b_; V.kff = S.kff + b_;
+        V.rg = S.rg + b_; V.rb = S.rb + b_; V.rgs = S.rgs + b_;
+        V.lam = (apply ? S.lam : S.lamq) + b_;
+        V.pi = (apply ? S.pi : S.piq) + b_;
+        qw_init<Ctx, C>(w, sm, Qc, V, st);
+    };
     int b = next();
-    bool fresh = true;
+    {
+        QW_T0();
+        if (b >= 0) bind(b);
+        QW_TICK(9);
+    }
     for (;;) {
         // lockstep point once per IPM iteration (measured: voting every 2nd / 4th iteration is 9 % / 16 % slower,
         // the warps drift and stop sharing instruction fetches); leaves when the queue is drained
@@ -244,19 +262,6 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm, const Solve
         if (w.cta_all(b < 0)) break;
         QW_TICK(0);
         if (b < 0) continue;
-        if (fresh) {
-            V.stride = (size_t)S.Bp;
-            V.A = S.A + b; V.B = S.Bm + b; V.b = S.b + b; V.g = S.g + b; V.qN = S.qN + b; V.dx0 = S.dx0 + b;
-            V.x = S.x + b; V.u = S.u + b;
-            V.z = S.z + b; V.zp = S.zp + b; V.zc = S.zc + b; V.t = S.t + b;
-            V.K = S.K + b; V.Li = S.Li + b; V.Pb = S.Pb + b; V.kff = S.kff + b;
-            V.rg = S.rg + b; V.rb = S.rb + b; V.rgs = S.rgs + b;
-            V.lam = (apply ? S.lam : S.lamq) + b;
-            V.pi = (apply ? S.pi : S.piq) + b;
-            qw_init<Ctx, C>(w, sm, Qc, V, st);
-            fresh = false;
-            QW_TICK(9);
-        }
         const int fin = qw_iterate<Ctx, C>(w, sm, Qc, st);
         if (fin == 0) continue;
         // ---- problem b is finished: write back, K5 epilogue, fetch the next problem
@@ -293,8 +298,9 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm, const Solve
             }
         }
         b = next();
-        fresh = true;
         QW_TICK(10);
+        if (b >= 0) bind(b);
+        QW_TICK(9);
     }
 }
 

@@ -525,14 +525,17 @@ int qspush_prepare(qspush_solver* s) {
 // parallel-in-time; 0 = one problem per thread (any horizon)
 static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, int ppw, int apply) {
     const int C = qp_warp_chunk(s->N);
-    // auto (2): the warp-per-problem kernel wins while the batch cannot fill the GPU with one problem per thread
-    // (measured crossover on B200 at N = 40: ~12k problems; 1.0M it/s flat vs 0.37M -> 2.0M it/s), DESIGN.md 4.1
-    const bool want_warp = s->opts.qp_kernel == 1 || (s->opts.qp_kernel == 2 && s->B < 12288);
+    // auto (2): the warp-per-problem kernel wins until the batch is large enough for the one-problem-per-thread
+    // kernel to fill the GPU.  Measured crossovers on B200: N = 40: ~50k problems (2.2M it/s flat
+    // from 8k on vs 0.4M -> 2.3M it/s); N = 10 and N = 100: between 4k and 32k
+    const int warp_below = (C == 2) ? 49152 : 16384;
+    const bool want_warp = s->opts.qp_kernel == 1 || (s->opts.qp_kernel == 2 && s->B < warp_below);
     // resident problems (= warps) per CTA: bounded by shared memory (one CTA per SM), by the register file
     // (8 warps of 255 registers) and by TMEM (8 blocks of 32 lanes x 256 columns)
     const int pwd = (int)((qp_warp_smem_doubles(s->N) + 1) / 2 * 2);
     const size_t smem_cap = 227 * 1024 - 1024;                                       // static __shared__ + reserve
-    const int W = (int)std::min<size_t>(QW_MAX_WARPS, smem_cap / ((size_t)pwd * sizeof(double)));
+    int W = (int)std::min<size_t>(QW_MAX_WARPS, smem_cap / ((size_t)pwd * sizeof(double)));
+    if (C * QW_TM_STAGE > 128) W = std::min(W, 4);          // more than 256 TMEM columns per warp: one warp per lane quarter
     const bool warp = want_warp && C <= 4 && W >= 2;
     if (!warp && s->opts.qp_kernel == 2 && s->opts.problems_per_warp == 0) ppw = (s->B >= 12288) ? 32 : ppw;
     if (!warp) {
