@@ -58,6 +58,11 @@ typedef struct {
     int    matlab_single_quirk;     /* reproduce MATLAB `single` rounding of mod(s,b) in prepare */
     int    problems_per_warp;       /* thread-per-problem QP kernel packing: 32, 16, 8, 4 (0 = auto) */
     int    qp_kernel;               /* 2 = auto by batch size (default); 1 = warp per problem, parallel-in-time Riccati (N <= 127); 0 = one problem per thread */
+    int    h_variant;               /* constraint set h of the OCP: 0 = [s; u_n; u_t] (NMPC_controller.m:237, default);
+                                       1 = the authors' parked set [u_n; u_t - v_bound(s); u_t + v_bound(s)] (:226-238) with
+                                       v_bound from qspush_ctrl; selecting it resets constr_lh / constr_uh to
+                                       [u_n_lb, -2 u_t_ub, 0] / [u_n_ub(0.03), 0, 2 u_t_ub] (:247-248).  Needs the warp QP kernel
+                                       (N <= 127): qspush_solve fails with QSPUSH_ERR_ARG otherwise                          */
 } qspush_opts;
 
 /* controller-side constants of NMPC_controller (NMPC_controller.m:23-26, 98-100) */

@@ -60,6 +60,10 @@ def lib():
         L.orc_ocp_set_bounds.argtypes = [C.c_void_p, _dp, _dp]
         L.orc_ocp_set_opts.argtypes = [C.c_void_p, _dp]
         L.orc_ocp_set_ctrl.argtypes = [C.c_void_p] + [C.c_double] * 5
+        L.orc_ocp_set_h_variant.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 4
+        L.orc_v_bound_sym.argtypes = [C.c_void_p, C.c_double, _dp]
+        L.orc_v_bound_sym.restype = C.c_double
+        L.orc_constraints_batch.argtypes = [C.c_void_p, C.c_int] + [_dp] * 4
         L.orc_linearise_batch.argtypes = [C.c_void_p, C.c_int] + [_dp] * 10
         L.orc_qp_batch.argtypes = [C.c_void_p, C.c_int] + [_dp] * 5 + [C.c_int] + [_dp] * 5 + [_ip, _ip, _dp]
         L.orc_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_int] + [_dp] * 7 + [C.c_int, _ip, _dp]
@@ -203,6 +207,27 @@ class Ocp:
     def set_bounds(self, lh, uh):
         lh, uh = _c(lh), _c(uh)
         lib().orc_ocp_set_bounds(self.h, _d(lh), _d(uh))
+
+    def set_h_variant(self, variant=1, v_alpha=1.0, d_v_bound=0.0, t_angle0=3.0, u_t_ub=0.05,
+                      u_n_lb=0.0, u_n_ub=0.03, u_t_lb=-0.05):
+        """variant 1: h = [u_n; u_t - v_bound(s); u_t + v_bound(s)] with lh = [u_n_lb, 2 u_t_lb, 0],
+        uh = [u_n_ub, 0, 2 u_t_ub] (the parked constraint set of NMPC_controller.m:226-248)."""
+        lib().orc_ocp_set_h_variant(self.h, int(variant), v_alpha, d_v_bound, t_angle0, u_t_ub)
+        if variant:
+            self.set_bounds([u_n_lb, 2 * u_t_lb, 0.0], [u_n_ub, 0.0, 2 * u_t_ub])
+        self.h_variant = int(variant)
+
+    def v_bound_sym(self, s):
+        dv = C.c_double(0.0)
+        v = lib().orc_v_bound_sym(self.h, float(s), C.byref(dv))
+        return v, dv.value
+
+    def constraints(self, x, u):
+        x, u = _c(x), _c(u)
+        nb, N = x.shape[0], self.N
+        h = np.zeros((nb, N, 3)); beta = np.zeros((nb, N, 3))
+        lib().orc_constraints_batch(self.h, nb, _d(x), _d(u), _d(h), _d(beta))
+        return h, beta
 
     def set_ctrl(self, v_alpha=1.0, d_v_bound=0.0, t_angle0=3.0, u_t_ub=0.05, u_n_lb=0.0):
         lib().orc_ocp_set_ctrl(self.h, v_alpha, d_v_bound, t_angle0, u_t_ub, u_n_lb)

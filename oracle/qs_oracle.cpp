@@ -208,6 +208,31 @@ static double angle_dot(const Model& m, double s, bool local) {
     return a.d[0];
 }
 
+// kappa(s) and d kappa / ds from the first and second AD derivative of FC_dot through the recursion:
+// kappa = (x y' - y x') / (x^2 + y^2) with (x, y) = FC_dot(s)  (the closed form of gradient(atan2(y, x), s)).
+static void angle_dot_d(const Model& m, double s, bool local, double* kappa, double* dkappa) {
+    Dual2 sd = Dual2::seed(s);
+    Dual2 d[2]; FC_dot(m, sd, local, d);
+    const double x = d[0].v, y = d[1].v, xp = d[0].d, yp = d[1].d, xpp = d[0].dd, ypp = d[1].dd;
+    const double num = x * yp - y * xp, den = x * x + y * y;
+    *kappa = num / den;
+    *dkappa = ((x * ypp - y * xpp) * den - num * 2.0 * (x * xp + y * yp)) / (den * den);
+}
+
+// v_bound(s) of the parked constraint variant (NMPC_controller.m:226-230) and its derivative with CasADi's AD rules
+// (comparisons are constants, d fmod = 1, d|a| = sign(a), d fmin(a, c) = [a < c]):
+//   s_mod = (s<0)*b + mod(s,b);  t = |kappa(s_mod)|;  v = min(v_alpha / (|t - t0| + 1e-4) + d_v_bound, u_t_ub)
+static double v_bound_sym(const Model& m, const Ocp& ocp, double s, bool local, double* dv) {
+    const double sw = std::fmod(s, m.b) + ((s < 0.0) ? m.b : 0.0);
+    double kap, dkap;
+    angle_dot_d(m, sw, local, &kap, &dkap);
+    const double t = std::fabs(kap), e = std::fabs(t - ocp.vb_t0) + 0.0001;
+    const double a = ocp.vb_alpha / e + ocp.vb_d;
+    const double sg1 = (double)((kap > 0.0) - (kap < 0.0)), sg2 = (double)((t - ocp.vb_t0 > 0.0) - (t - ocp.vb_t0 < 0.0));
+    if (dv) *dv = (a < ocp.vb_ub) ? -ocp.vb_alpha / (e * e) * sg2 * sg1 * dkap : 0.0;
+    return std::fmin(a, ocp.vb_ub);
+}
+
 // MATLAB mod(s, b) for b > 0: result in [0, b).  With the single quirk the result is single
 // (mod(double, single) -> single), bspline_shape.m:147,155,193; NMPC_controller.m:320,332.
 static double matlab_mod(const Model& m, double s) {
@@ -379,6 +404,8 @@ struct StageQP {
     double A[4][4], B[4][2], b[4];   // dx+ = A dx + B du + b
     double dl[3], du[3];             // lh - h , uh - h
     bool   on[3];                    // constraint present (s-bound is dropped at k=0: x0 is fixed)
+    int    ci[3];                    // constraint row c = e_{ci[c]} + beta[c] * e_5 in z = [u_n,u_t,x,y,theta,s]
+    double beta[3];                  // (h_variant 0: rows are selections, beta = 0; h_variant 1: beta = -+ v_bound'(s))
 };
 struct QP {
     int N = 0;
@@ -400,7 +427,7 @@ struct RiccatiFactor {
 };
 
 // Backward matrix recursion with the barrier-augmented Hessian diag term Hb (N x 6).
-static bool riccati_factor(const QP& qp, const std::vector<double>& Hb, RiccatiFactor& F) {
+static bool riccati_factor(const QP& qp, const std::vector<double>& Hb, const std::vector<double>& Hx, RiccatiFactor& F) {
     const int N = qp.N;
     F.K.assign((size_t)N * 8, 0.0); F.Linv.assign((size_t)N * 3, 0.0); F.P.assign((size_t)(N + 1) * 16, 0.0);
     for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) F.P[(size_t)N * 16 + 4 * i + j] = qp.QN[i][j];
@@ -416,6 +443,7 @@ static bool riccati_factor(const QP& qp, const std::vector<double>& Hb, RiccatiF
         for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) {
             double a = s.H[i][j]; for (int l = 0; l < 4; ++l) a += BA[l][i] * PBA[l][j]; M[i][j] = a; }
         for (int i = 0; i < 6; ++i) M[i][i] += Hb[(size_t)k * 6 + i];
+        M[5][1] += Hx[k]; M[1][5] += Hx[k];                  // barrier cross term (s, u_t) of the coupled rows
         // Cholesky of the 2x2 input block
         double l00 = std::sqrt(M[0][0]);
         if (!(l00 > 0.0)) return false;
@@ -501,13 +529,13 @@ static void qp_solve_ipm(const QP& qp, const OcpOpts& o, QPSol& sol) {
             on[(size_t)k * 6 + c] = act; on[(size_t)k * 6 + 3 + c] = act;
             if (!act) continue;
             m_on += 2;
-            double v = z[(size_t)k * 6 + CIDX[c]];
+            double v = z[(size_t)k * 6 + qp.st[k].ci[c]] + qp.st[k].beta[c] * z[(size_t)k * 6 + 5];
             double tl = v - qp.st[k].dl[c], tu = qp.st[k].du[c] - v;
             tl = std::max(tl, o.qp_thr); tu = std::max(tu, o.qp_thr);
             t[(size_t)k * 6 + c] = tl; t[(size_t)k * 6 + 3 + c] = tu;
             lam[(size_t)k * 6 + c] = o.qp_mu0 / tl; lam[(size_t)k * 6 + 3 + c] = o.qp_mu0 / tu;
         }
-    std::vector<double> rg(nz + 4), rb((size_t)N * 4), rd(nc), rm(nc), Hb(nz), rgt(nz + 4);
+    std::vector<double> rg(nz + 4), rb((size_t)N * 4), rd(nc), rm(nc), Hb(nz), Hx((size_t)N), rgt(nz + 4);
     std::vector<double> dz, dxN, dpi, dlam(nc), dt_(nc), dz2, dxN2, dpi2;
     RiccatiFactor F;
     sol.status = 1;
@@ -528,8 +556,11 @@ static void qp_solve_ipm(const QP& qp, const OcpOpts& o, QPSol& sol) {
             for (int j = 0; j < 2; ++j) for (int l = 0; l < 4; ++l) rg[(size_t)k * 6 + j] += s.B[l][j] * pk1[l];
             for (int j = 0; j < 4; ++j) for (int l = 0; l < 4; ++l) rg[(size_t)k * 6 + 2 + j] += s.A[l][j] * pk1[l];
             if (k > 0) for (int j = 0; j < 4; ++j) rg[(size_t)k * 6 + 2 + j] -= pi[(size_t)(k - 1) * 4 + j];
-            for (int c = 0; c < 3; ++c) if (s.on[c])
-                rg[(size_t)k * 6 + CIDX[c]] += -lam[(size_t)k * 6 + c] + lam[(size_t)k * 6 + 3 + c];
+            for (int c = 0; c < 3; ++c) if (s.on[c]) {
+                const double dlm = -lam[(size_t)k * 6 + c] + lam[(size_t)k * 6 + 3 + c];
+                rg[(size_t)k * 6 + s.ci[c]] += dlm;
+                rg[(size_t)k * 6 + 5] += s.beta[c] * dlm;
+            }
             for (int i = 0; i < 4; ++i) {
                 double a = s.b[i] - xn[i];
                 for (int l = 0; l < 4; ++l) a += s.A[i][l] * zk[2 + l];
@@ -538,7 +569,7 @@ static void qp_solve_ipm(const QP& qp, const OcpOpts& o, QPSol& sol) {
             }
             for (int c = 0; c < 3; ++c) {
                 if (!s.on[c]) { rd[(size_t)k * 6 + c] = 0; rd[(size_t)k * 6 + 3 + c] = 0; continue; }
-                double v = zk[CIDX[c]];
+                double v = zk[s.ci[c]] + s.beta[c] * zk[5];
                 rd[(size_t)k * 6 + c] = v - s.dl[c] - t[(size_t)k * 6 + c];
                 rd[(size_t)k * 6 + 3 + c] = s.du[c] - v - t[(size_t)k * 6 + 3 + c];
             }
@@ -565,22 +596,29 @@ static void qp_solve_ipm(const QP& qp, const OcpOpts& o, QPSol& sol) {
         }
         if (it >= o.qp_max_iter) { sol.status = 1; break; }
         // ---- factorise with barrier diagonal
-        std::fill(Hb.begin(), Hb.end(), 0.0);
-        for (int k = 0; k < N; ++k) for (int c = 0; c < 3; ++c) if (qp.st[k].on[c])
-            Hb[(size_t)k * 6 + CIDX[c]] += lam[(size_t)k * 6 + c] / t[(size_t)k * 6 + c] + lam[(size_t)k * 6 + 3 + c] / t[(size_t)k * 6 + 3 + c];
-        if (!riccati_factor(qp, Hb, F)) { sol.status = 2; break; }
+        std::fill(Hb.begin(), Hb.end(), 0.0); std::fill(Hx.begin(), Hx.end(), 0.0);
+        for (int k = 0; k < N; ++k) for (int c = 0; c < 3; ++c) if (qp.st[k].on[c]) {
+            const double D = lam[(size_t)k * 6 + c] / t[(size_t)k * 6 + c] + lam[(size_t)k * 6 + 3 + c] / t[(size_t)k * 6 + 3 + c];
+            const double be = qp.st[k].beta[c];
+            Hb[(size_t)k * 6 + qp.st[k].ci[c]] += D;          // D a a' with a = e_ci + beta e_5
+            Hb[(size_t)k * 6 + 5] += be * be * D;
+            Hx[k] += be * D;                                   // (beta != 0 only for rows on u_t: ci = 1)
+        }
+        if (!riccati_factor(qp, Hb, Hx, F)) { sol.status = 2; break; }
         const double zero4[4] = {0, 0, 0, 0};
         auto solve_with = [&](const std::vector<double>& rmv, std::vector<double>& dz_, std::vector<double>& dxN_, std::vector<double>& dpi_) {
             rgt = rg;
             for (int k = 0; k < N; ++k) for (int c = 0; c < 3; ++c) if (qp.st[k].on[c]) {
                 const size_t il = (size_t)k * 6 + c, iu = il + 3;
-                rgt[(size_t)k * 6 + CIDX[c]] += (rmv[il] + lam[il] * rd[il]) / t[il] - (rmv[iu] + lam[iu] * rd[iu]) / t[iu];
+                const double w = (rmv[il] + lam[il] * rd[il]) / t[il] - (rmv[iu] + lam[iu] * rd[iu]) / t[iu];
+                rgt[(size_t)k * 6 + qp.st[k].ci[c]] += w;
+                rgt[(size_t)k * 6 + 5] += qp.st[k].beta[c] * w;
             }
             riccati_solve(qp, Hb, F, rgt, rb, zero4, dz_, dxN_, dpi_);
             for (int k = 0; k < N; ++k) for (int c = 0; c < 3; ++c) {
                 const size_t il = (size_t)k * 6 + c, iu = il + 3;
                 if (!qp.st[k].on[c]) { dt_[il] = dt_[iu] = dlam[il] = dlam[iu] = 0.0; continue; }
-                double dv = dz_[(size_t)k * 6 + CIDX[c]];
+                double dv = dz_[(size_t)k * 6 + qp.st[k].ci[c]] + qp.st[k].beta[c] * dz_[(size_t)k * 6 + 5];
                 dt_[il] = dv + rd[il]; dt_[iu] = -dv + rd[iu];
                 dlam[il] = -(rmv[il] + lam[il] * dt_[il]) / t[il];
                 dlam[iu] = -(rmv[iu] + lam[iu] * dt_[iu]) / t[iu];
@@ -636,8 +674,16 @@ struct RefData {            // per problem
     const double* yref_e;   // 4
 };
 
-static double h_of(const Traj& tr, int k, int c) {   // h = [s; u_n; u_t]  NMPC_controller.m:237
-    return c == 0 ? tr.x[(size_t)k * 4 + 3] : tr.u[(size_t)k * 2 + (c - 1)];
+// h = [s; u_n; u_t] (NMPC_controller.m:237) or, h_variant 1, [u_n; u_t - v_bound(s); u_t + v_bound(s)] (:238).
+// beta (optional) = d h_c / d s.
+static double h_of(const Ocp& ocp, const Traj& tr, int k, int c, bool local, double* beta = nullptr) {
+    if (beta) *beta = 0.0;
+    if (ocp.h_variant == 0) return c == 0 ? tr.x[(size_t)k * 4 + 3] : tr.u[(size_t)k * 2 + (c - 1)];
+    if (c == 0) return tr.u[(size_t)k * 2];
+    double dv;
+    const double vb = v_bound_sym(*ocp.model, ocp, tr.x[(size_t)k * 4 + 3], local, &dv);
+    if (beta) *beta = (c == 1) ? -dv : dv;
+    return tr.u[(size_t)k * 2 + 1] + ((c == 1) ? -vb : vb);
 }
 
 static void linearise(const Ocp& ocp, const RefData& rd, const Traj& tr, bool local, QP& qp) {
@@ -669,9 +715,10 @@ static void linearise(const Ocp& ocp, const RefData& rd, const Traj& tr, bool lo
             s.g[i] = a;
         }
         for (int c = 0; c < 3; ++c) {
-            double h = h_of(tr, k, c);
+            double h = h_of(ocp, tr, k, c, local, &s.beta[c]);
             s.dl[c] = ocp.lh[c] - h; s.du[c] = ocp.uh[c] - h;
-            s.on[c] = !(k == 0 && c == 0);
+            s.on[c] = ocp.h_variant ? true : !(k == 0 && c == 0);
+            s.ci[c] = ocp.h_variant ? (c == 0 ? 0 : 1) : CIDX[c];
         }
     }
     for (int i = 0; i < 4; ++i) {
@@ -743,7 +790,8 @@ static void nlp_residuals(const Ocp& ocp, const QP& qp, const Traj& tr, double r
         for (int j = 0; j < 4; ++j) for (int l = 0; l < 4; ++l) g[2 + j] += s.A[l][j] * tr.pi[(size_t)k * 4 + l];
         if (k > 0) for (int j = 0; j < 4; ++j) g[2 + j] -= tr.pi[(size_t)(k - 1) * 4 + j];
         for (int c = 0; c < 3; ++c) if (s.on[c]) {
-            g[CIDX[c]] += -tr.lam[(size_t)k * 6 + c] + tr.lam[(size_t)k * 6 + 3 + c];
+            const double dlm = -tr.lam[(size_t)k * 6 + c] + tr.lam[(size_t)k * 6 + 3 + c];
+            g[s.ci[c]] += dlm; g[5] += s.beta[c] * dlm;
             double sl = -s.dl[c], su = s.du[c];   // slacks h-lh, uh-h
             r_in = std::max(r_in, std::max(-sl, 0.0)); r_in = std::max(r_in, std::max(-su, 0.0));
             r_cp = std::max(r_cp, std::fabs(tr.lam[(size_t)k * 6 + c] * sl));
@@ -767,8 +815,8 @@ static double merit(const Ocp& ocp, const RefData& rd, const Traj& tr, bool loca
         erk4(*ocp.model, &tr.x[(size_t)k * 4], &tr.u[(size_t)k * 2], ocp.dt, local, Phi);
         for (int i = 0; i < 4; ++i) mval += wpi[(size_t)k * 4 + i] * std::fabs(Phi[i] - tr.x[(size_t)(k + 1) * 4 + i]);
         for (int c = 0; c < 3; ++c) {
-            if (k == 0 && c == 0) continue;
-            double h = h_of(tr, k, c);
+            if (ocp.h_variant == 0 && k == 0 && c == 0) continue;
+            double h = h_of(ocp, tr, k, c, local);
             mval += wlam[(size_t)k * 6 + c] * std::max(0.0, ocp.lh[c] - h);
             mval += wlam[(size_t)k * 6 + 3 + c] * std::max(0.0, h - ocp.uh[c]);
         }
@@ -806,6 +854,7 @@ static void sqp_solve(const Ocp& ocp, const RefData& rd, Traj& tr, bool local, S
                     double a = s.g[2 + j];
                     for (int l = 0; l < 6; ++l) a += s.H[2 + j][l] * (l < 2 ? qs.du[l] : qs.dx[l - 2]);
                     for (int l = 0; l < 4; ++l) a += s.A[l][j] * qs.pi[l];
+                    if (j == 3) for (int c = 0; c < 3; ++c) a += s.beta[c] * (qs.lam[3 + c] - qs.lam[c]);
                     a = std::fabs(a);
                     wx0[j] = (it == 0) ? a : std::max(a, 0.5 * (wx0[j] + a));
                 }
@@ -1081,6 +1130,17 @@ void orc_ocp_set_opts(void* o_, const double* v) {
     p.alpha_min = v[10]; p.alpha_reduction = v[11]; p.eps_sufficient_descent = v[12]; p.globalization = (int)v[13];
     o->local = v[14] != 0.0;
 }
+// h_variant 1: h = [u_n; u_t - v_bound(s); u_t + v_bound(s)]; the caller sets the matching lh / uh
+// ([u_n_lb, 2 u_t_lb, 0] / [u_n_ub, 0, 2 u_t_ub], NMPC_controller.m:247-248) with orc_ocp_set_bounds.
+void orc_ocp_set_h_variant(void* o_, int variant, double v_alpha, double d_v_bound, double t_angle0, double u_t_ub) {
+    OrcOcp* o = (OrcOcp*)o_;
+    o->ocp.h_variant = variant; o->ocp.vb_alpha = v_alpha; o->ocp.vb_d = d_v_bound; o->ocp.vb_t0 = t_angle0; o->ocp.vb_ub = u_t_ub;
+}
+// v_bound of the variant and its derivative (test hook)
+double orc_v_bound_sym(void* o_, double s, double* dv) {
+    OrcOcp* o = (OrcOcp*)o_;
+    return v_bound_sym(*o->ocp.model, o->ocp, s, o->local, dv);
+}
 void orc_ocp_set_ctrl(void* o_, double v_alpha, double d_v_bound, double t_angle0, double u_t_ub, double u_n_lb) {
     OrcOcp* o = (OrcOcp*)o_;
     o->cp.v_alpha = v_alpha; o->cp.d_v_bound = d_v_bound; o->cp.t_angle0 = t_angle0; o->cp.u_t_ub = u_t_ub; o->cp.u_n_lb = u_n_lb;
@@ -1118,6 +1178,17 @@ void orc_linearise_batch(void* o_, int nb, const double* x0bar, const double* yr
             for (int i = 0; i < 6; ++i) g[((size_t)b * N + k) * 6 + i] = qp.st[k].g[i];
         }
         for (int i = 0; i < 4; ++i) qN[4 * b + i] = qp.qN[i];
+    }
+}
+
+// constraint function and its s-derivative at (x,u): h [nb][N][3], beta [nb][N][3] (beta = d h_c / d s beyond the
+// selection entry; zero for h_variant 0)
+void orc_constraints_batch(void* o_, int nb, const double* x, const double* u, double* h, double* beta) {
+    OrcOcp* o = (OrcOcp*)o_; const int N = o->ocp.N;
+    for (int b = 0; b < nb; ++b) {
+        Traj tr; load_traj(o, b, x, u, nullptr, nullptr, tr);
+        for (int k = 0; k < N; ++k) for (int c = 0; c < 3; ++c)
+            h[((size_t)b * N + k) * 3 + c] = h_of(o->ocp, tr, k, c, o->local, &beta[((size_t)b * N + k) * 3 + c]);
     }
 }
 

@@ -78,6 +78,27 @@ template <int ND> inline double ge(const Dual<ND>& a, double b) { return a.v >= 
 inline double lt(double a, double b) { return a < b ? 1.0 : 0.0; }
 inline double ge(double a, double b) { return a >= b ? 1.0 : 0.0; }
 template <int ND> inline double val(const Dual<ND>& a) { return a.v; }
+
+// Second-order Taylor scalar in ONE direction (value, first and second derivative): used to differentiate the
+// curvature kappa(s) = d/ds atan2(C'_y, C'_x) once more through the same Cox-de Boor recursion (h_variant 1).
+struct Dual2 {
+    double v, d, dd;
+    Dual2() : v(0.0), d(0.0), dd(0.0) {}
+    Dual2(double x) : v(x), d(0.0), dd(0.0) {}  // NOLINT implicit
+    static Dual2 seed(double x) { Dual2 r(x); r.d = 1.0; return r; }
+};
+inline Dual2 operator+(const Dual2& a, const Dual2& b) { Dual2 r; r.v = a.v + b.v; r.d = a.d + b.d; r.dd = a.dd + b.dd; return r; }
+inline Dual2 operator-(const Dual2& a, const Dual2& b) { Dual2 r; r.v = a.v - b.v; r.d = a.d - b.d; r.dd = a.dd - b.dd; return r; }
+inline Dual2 operator*(const Dual2& a, const Dual2& b) {
+    Dual2 r; r.v = a.v * b.v; r.d = a.d * b.v + a.v * b.d; r.dd = a.dd * b.v + 2.0 * a.d * b.d + a.v * b.dd; return r; }
+inline Dual2 operator*(const Dual2& a, double b) { Dual2 r; r.v = a.v * b; r.d = a.d * b; r.dd = a.dd * b; return r; }
+inline Dual2 operator*(double a, const Dual2& b) { return b * a; }
+inline Dual2 operator/(const Dual2& a, double b) { Dual2 r; r.v = a.v / b; r.d = a.d / b; r.dd = a.dd / b; return r; }
+inline Dual2 operator-(const Dual2& a, double b) { Dual2 r = a; r.v -= b; return r; }
+inline Dual2 operator-(double a, const Dual2& b) { Dual2 r; r.v = a - b.v; r.d = -b.d; r.dd = -b.dd; return r; }
+inline double lt(const Dual2& a, double b) { return a.v < b ? 1.0 : 0.0; }
+inline double ge(const Dual2& a, double b) { return a.v >= b ? 1.0 : 0.0; }
+inline double val(const Dual2& a) { return a.v; }
 inline double val(double a) { return a; }
 inline double fmod(double a, double m) { return std::fmod(a, m); }
 using std::sqrt; using std::sin; using std::cos; using std::atan2;
@@ -123,6 +144,10 @@ struct Ocp {
     std::vector<double> W;      // N x 36, per-stage 6x6 column-major in y=[x;u] order (NMPC_controller.m:157)
     double We[16];              // terminal 4x4 column-major            (NMPC_controller.m:154)
     double lh[3], uh[3];        // bounds on h=[s;u_n;u_t]              (NMPC_controller.m:251-252)
+    // h_variant 1 = the authors' parked constraint set (NMPC_controller.m:226-238, commented expr_h at :238):
+    // h = [u_n; u_t - v_bound(s); u_t + v_bound(s)] with v_bound of :229 built from the parameters below
+    int    h_variant = 0;
+    double vb_alpha = 1.0, vb_d = 0.0, vb_t0 = 3.0, vb_ub = 0.05;   // v_alpha :98, d_v_bound :99, t_angle0 :100, u_t_ub :24
     OcpOpts opts;
 };
 

@@ -20,6 +20,11 @@ for N, B, kern, mode in ((40, 7, 1, "rti"), (10, 5, 1, "rti"), (100, 3, 1, "rti"
     r = hs.solve(mhs, N, 0.05, wl["x0"], wl["yref"], wl["yref_e"], np.zeros((B, N + 1, 4)), wl["u_init"], objid=wl["object_id"],
                  mode=mode, prepare=True, shift=True, qp_kernel=kern, max_sqp_iter=3)
     assert np.isfinite(r["u"]).all()
+for N, B, mode in ((40, 5, "rti"), (70, 3, "rti"), (100, 2, "rti"), (10, 4, "sqp")):   # parked constraint set h = [u_n; u_t -+ v_bound(s)]
+    wl = make_rti_workload(None, batch=B, N=N, seed=3, n_objects=4)
+    r = hs.solve(mhs, N, 0.05, wl["x0"], wl["yref"], wl["yref_e"], np.zeros((B, N + 1, 4)), wl["u_init"], objid=wl["object_id"],
+                 mode=mode, prepare=True, shift=True, qp_kernel=1, max_sqp_iter=3, h_variant=1, lh=(0.0, -0.1, 0.0), uh=(0.03, 0.0, 0.1))
+    assert np.isfinite(r["u"]).all()
 x = np.random.default_rng(0).uniform(-0.7, 0.7, (500, 4)); u = np.random.default_rng(1).uniform(-0.05, 0.05, (500, 2))
 mhs[3].eval_spline(x[:, 3], wrap=2); mhs[3].dynamics(x, u); mhs[3].erk4_sens(x, u, 0.05); mhs[3].v_bound(x[:, 3])
 print("ASAN-DRIVER-OK")

@@ -143,11 +143,16 @@ static void warp_job_body(int lane, void* arg) {
     WarpCtxHost w{lane};
     // work queue of the emulated warp: exactly one problem (every lane sees the same sequence b, -1)
     auto next = [j, lane]() -> int { return j->handed[lane]++ == 0 ? j->b : -1; };
-    switch (j->C) {
-        case 1: qp_warp_persistent<WarpCtxHost, 1>(w, j->sm, *j->S, *j->io, j->apply, next); break;
-        case 2: qp_warp_persistent<WarpCtxHost, 2>(w, j->sm, *j->S, *j->io, j->apply, next); break;
-        case 3: qp_warp_persistent<WarpCtxHost, 3>(w, j->sm, *j->S, *j->io, j->apply, next); break;
-        default: qp_warp_persistent<WarpCtxHost, 4>(w, j->sm, *j->S, *j->io, j->apply, next); break;
+    const int hv = j->S->h_variant ? 1 : 0;
+    switch (j->C * 2 + hv) {
+        case 2: qp_warp_persistent<WarpCtxHost, 1, 0>(w, j->sm, *j->S, *j->io, j->apply, next); break;
+        case 3: qp_warp_persistent<WarpCtxHost, 1, 1>(w, j->sm, *j->S, *j->io, j->apply, next); break;
+        case 4: qp_warp_persistent<WarpCtxHost, 2, 0>(w, j->sm, *j->S, *j->io, j->apply, next); break;
+        case 5: qp_warp_persistent<WarpCtxHost, 2, 1>(w, j->sm, *j->S, *j->io, j->apply, next); break;
+        case 6: qp_warp_persistent<WarpCtxHost, 3, 0>(w, j->sm, *j->S, *j->io, j->apply, next); break;
+        case 7: qp_warp_persistent<WarpCtxHost, 3, 1>(w, j->sm, *j->S, *j->io, j->apply, next); break;
+        case 8: qp_warp_persistent<WarpCtxHost, 4, 0>(w, j->sm, *j->S, *j->io, j->apply, next); break;
+        default: qp_warp_persistent<WarpCtxHost, 4, 1>(w, j->sm, *j->S, *j->io, j->apply, next); break;
     }
 }
 // mirrors k_qp_warp: one emulated warp per problem
@@ -244,7 +249,7 @@ void hs_eval_vbound(void* m_, int cnt, const double* s, const double* ctrl5, int
 
 // Whole solver pipeline in kernel order on host slabs.
 //   opts_d: [qp_tol, qp_mu0, qp_thr, qp_tau, tol_stat, tol_eq, tol_ineq, tol_comp, alpha_min, alpha_red, eps_sd]
-//   opts_i: [mode(0 rti,1 sqp,2 qp-only), qp_max_iter, max_sqp_iter, globalization, single_quirk, do_prepare, do_shift, qp_kernel(0 thread,1 warp)]
+//   opts_i: [mode(0 rti,1 sqp,2 qp-only), qp_max_iter, max_sqp_iter, globalization, single_quirk, do_prepare, do_shift, qp_kernel(0 thread,1 warp), h_variant]
 //   ctrl5 : [v_alpha, d_v_bound, t_angle0, u_t_ub, u_n_lb]
 // AoS in/out: x0 [nb][4] (in/out: wrapped by prepare), yref [nb][N][6], yref_e [nb][4], x [nb][N+1][4], u [nb][N][2],
 //             pi [nb][N][4], lam [nb][N][6], cold [nb]
@@ -267,13 +272,13 @@ int hs_solve(void* const* models, int nmodels, int N, double dt, int nb, const i
     S.cold = v_cold.data(); S.done = v_done.data(); S.qpstat = v_qpstat.data(); S.ndone = v_ndone.data();
     auto slab = [&](size_t rows) { return std::vector<double>(rows * Bp, 0.0); };
     auto sx = slab((N + 1) * 4), su = slab(N * 2), spi = slab(N * 4), slam = slab(N * 6), sx0 = slab(4), syr = slab(N * 6), sye = slab(4);
-    auto sA = slab(N * 8), sB = slab(N * 8), sb = slab(N * 4), sg = slab(N * 6), sqN = slab(4), sdx0 = slab(4);
+    auto sA = slab(N * 8), sB = slab(N * 8), sb = slab(N * 4), sg = slab(N * 6), sqN = slab(4), sdx0 = slab(4), shv = slab(N * 4);
     auto sz = slab((N + 1) * 6), szp = slab((N + 1) * 6), szc = slab(N * 3), slq = slab(N * 6), st = slab(N * 6);
     auto sK = slab(N * 8), sLi = slab(N * 3), sPb = slab(N * 4), skf = slab(N * 2), spq = slab(N * 4);
     auto srg = slab((N + 1) * 6), srb = slab(N * 4), srgs = slab(N);
     auto scost = slab(1), sres = slab(4), salpha = slab(1), swpi = slab(N * 4), swlam = slab(N * 6), swx0 = slab(4);
     S.x = sx.data(); S.u = su.data(); S.pi = spi.data(); S.lam = slam.data(); S.x0 = sx0.data(); S.yref = syr.data(); S.yref_e = sye.data();
-    S.A = sA.data(); S.Bm = sB.data(); S.b = sb.data(); S.g = sg.data(); S.qN = sqN.data(); S.dx0 = sdx0.data();
+    S.A = sA.data(); S.Bm = sB.data(); S.b = sb.data(); S.g = sg.data(); S.qN = sqN.data(); S.dx0 = sdx0.data(); S.hv = shv.data();
     S.z = sz.data(); S.zp = szp.data(); S.zc = szc.data(); S.lamq = slq.data(); S.t = st.data();
     S.K = sK.data(); S.Li = sLi.data(); S.Pb = sPb.data(); S.kff = skf.data(); S.piq = spq.data();
     S.rg = srg.data(); S.rb = srb.data(); S.rgs = srgs.data();
@@ -289,6 +294,9 @@ int hs_solve(void* const* models, int nmodels, int N, double dt, int nb, const i
     for (int i = 0; i < 4; ++i) for (int j = 0; j <= i; ++j) QN[LT(i, j)] = 0.5 * (We[i + 4 * j] + We[j + 4 * i]);
     S.Wdt = Wdt.data(); S.We = Wev.data(); S.H = H.data(); S.QN = QN.data();
     for (int i = 0; i < 3; ++i) { S.lh[i] = lh[i]; S.uh[i] = uh[i]; }
+    S.h_variant = opts_i[8];                                     // like apply_variant() in qspush_capi.cu
+    for (int i = 0; i < 4; ++i) S.vbp[i] = ctrl5[i];
+    if (S.h_variant && !(opts_i[7] && qp_warp_chunk(N) <= 4)) { g_err = "h_variant 1 needs the warp QP kernel"; return -1; }
     // AoS -> SoA (k_aos_to_soa)
     auto in = [&](const double* src, std::vector<double>& dst, int R) { for (int b = 0; b < nb; ++b) for (int r = 0; r < R; ++r) dst[(size_t)r * Bp + b] = src[(size_t)b * R + r]; };
     auto out = [&](const std::vector<double>& src, double* dst, int R) { if (!dst) return; for (int b = 0; b < nb; ++b) for (int r = 0; r < R; ++r) dst[(size_t)b * R + r] = src[(size_t)r * Bp + b]; };

@@ -112,7 +112,7 @@ def solve(models, N, dt, x0, yref, yref_e, x, u, pi=None, lam=None, cold=None, o
           lh=(-0.06, 0.0, -0.05), uh=(0.011, 0.03, 0.05), mode="rti", prepare=False, shift=False,
           qp_tol=1e-12, qp_mu0=0.1, qp_thr=1e-3, qp_tau=0.9995, qp_max_iter=50, max_sqp_iter=30,
           tol=(1e-6, 1e-6, 1e-6, 1e-6), globalization=1, alpha_min=0.05, alpha_red=0.7, eps_sd=1e-4,
-          single_quirk=True, ctrl=(1.0, 0.0, 3.0, 0.05, 0.0), qp_kernel=1):
+          single_quirk=True, ctrl=(1.0, 0.0, 3.0, 0.05, 0.0), qp_kernel=1, h_variant=0):
     nb = np.asarray(x0).shape[0]
     if W is None:
         W = np.tile(np.diag([1.0, 1.0, 1e-3, 0.0, 1e-3, 1e-3]).reshape(1, 36), (N, 1))
@@ -125,15 +125,17 @@ def solve(models, N, dt, x0, yref, yref_e, x, u, pi=None, lam=None, cold=None, o
     cold = np.zeros(nb, dtype=np.int32) if cold is None else _c(cold, np.int32).copy()
     objid = np.zeros(nb, dtype=np.int32) if objid is None else _c(objid, np.int32)
     od = _c([qp_tol, qp_mu0, qp_thr, qp_tau, *tol, alpha_min, alpha_red, eps_sd])
-    oi = _c([{"rti": 0, "sqp": 1, "qp": 2}[mode], qp_max_iter, max_sqp_iter, globalization, int(single_quirk), int(prepare), int(shift), int(qp_kernel)], np.int32)
+    oi = _c([{"rti": 0, "sqp": 1, "qp": 2}[mode], qp_max_iter, max_sqp_iter, globalization, int(single_quirk), int(prepare), int(shift), int(qp_kernel), int(h_variant)], np.int32)
     c5 = _c(ctrl); lh = _c(lh); uh = _c(uh)
     si = np.zeros((nb, 3), dtype=np.int32); sd = np.zeros((nb, 6))
     z = np.zeros((nb, N + 1, 6)); qpi = np.zeros((nb, N, 4)); qlam = np.zeros((nb, N, 6))
     A = np.zeros((nb, N, 8)); B = np.zeros((nb, N, 8)); bb = np.zeros((nb, N, 4)); g = np.zeros((nb, N, 6))
     arr = (C.c_void_p * len(models))(*[m.h for m in models])
-    lib().hs_solve(arr, len(models), N, float(dt), nb, _i(objid), _d(W), We.ctypes.data_as(_dp), _d(lh), _d(uh),
+    rc = lib().hs_solve(arr, len(models), N, float(dt), nb, _i(objid), _d(W), We.ctypes.data_as(_dp), _d(lh), _d(uh),
                    _d(od), _i(oi), _d(c5), _d(x0), _d(yref), _d(yref_e), _d(x), _d(u), _d(pi), _d(lam), _i(cold),
                    _i(si), _d(sd), _d(z), _d(qpi), _d(qlam), _d(A), _d(B), _d(bb), _d(g))
+    if rc != 0:
+        raise RuntimeError("hs_solve: " + lib().hs_last_error().decode())
     return dict(x0=x0, x=x, u=u, pi=pi, lam=lam, cold=cold, status=si[:, 0], sqp_iter=si[:, 1], qp_iter=si[:, 2],
                 cost=sd[:, 0], res=sd[:, 1:5], alpha=sd[:, 5], du=z[:, :N, :2], dx=z[:, :, 2:], qp_pi=qpi, qp_lam=qlam,
                 A=A, B=B, b=bb, g=g)

@@ -302,3 +302,68 @@ def test_open_loop_driver():
     for k in range(len(t) - 1):
         x = x + 0.05 * om.dynamics([x], [[0.01, 0.0]])[0]
     assert len(t) == 21 and abs(x_s[-1] - x[0]) < 1e-12 and abs(y_s[-1] - x[1]) < 1e-12 and abs(th_s[-1] - x[2]) < 1e-12
+
+
+def test_velocity_constraint_variant_vs_oracle():
+    """h_variant 1 = the constraint set the authors parked in comments (NMPC_controller.m:226-238, :247-248):
+    h = [u_n; u_t - v_bound(s); u_t + v_bound(s)], rows that couple ds and du_t.  k_linearise writes h and v_bound'(s),
+    the warp QP kernel solves the coupled QP; RTI and full SQP vs the oracle, error path of the thread kernel, and
+    the NMPC_controller mirror option."""
+    from tests.workloads import VARIANT_LH, VARIANT_UH, make_vbound_workload
+    gm, om = packaged_model_pair("santal")
+    for N, B in ((40, 64), (10, 32), (70, 16)):
+        wl = make_vbound_workload(B, N)
+        ocp = orc.Ocp(om, N, 0.05); ocp.set_h_variant(1)
+        pr = ocp.prepare(wl["x0"], np.zeros(B, dtype=np.int32), np.zeros((B, N + 1, 4)), wl["u_init"])
+        ro = ocp.solve("rti", pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"], nthreads=8)
+        s = q.Solver([gm], N, 0.05, B, h_variant=1)
+        assert np.allclose(s.get("lh"), VARIANT_LH) and np.allclose(s.get("uh"), VARIANT_UH)     # defaults of :247-248
+        _load(s, wl); s.prepare(); s.solve()
+        it = s.get_int("qp_iter")
+        assert (s.get_int("status") == 0).all() and np.abs(it - ro["qp_iter"]).max() <= 4
+        same = it == ro["qp_iter"]
+        assert same.mean() > 0.7 and np.abs(s.get("u")[same] - ro["u"][same]).max() < 1e-6
+        assert np.abs(s.get("u") - ro["u"]).max() < (2e-5 if N <= 40 else 2e-4)
+        lam = s.get("lam")
+        assert (np.abs(lam[:, 1:, [1, 2, 4, 5]]).max(axis=(1, 2)) > 1e-3).sum() >= B // 4     # the v_bound rows are active
+        assert rel_err(s.get("cost"), ro["cost"]) < 1e-8 and s.get("res").max() < 1e-6
+        u = s.get("u"); x = s.get("x")
+        # the linearised constraint holds at the new point: |u_t| <= v_bound(s) up to the linearisation error
+        assert u[:, :, 0].min() > -1e-9 and np.abs(u[:, :, 1]).max() < 0.05 + 1e-9
+    # full SQP
+    N, B = 10, 16
+    wl = make_vbound_workload(B, N)
+    ocp = orc.Ocp(om, N, 0.05); ocp.set_h_variant(1)
+    pr = ocp.prepare(wl["x0"], np.zeros(B, dtype=np.int32), np.zeros((B, N + 1, 4)), wl["u_init"])
+    so = ocp.solve("sqp", pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"])
+    s = q.Solver([gm], N, 0.05, B, h_variant=1, mode=1)
+    _load(s, wl); s.prepare(); s.solve()
+    same = (s.get_int("status") == so["status"]) & (s.get_int("sqp_iter") == so["sqp_iter"])
+    assert same.mean() >= 0.7 and (so["status"] == 0).any()
+    assert np.abs(s.get("u")[same] - so["u"][same]).max() < 1e-6
+    # converged problems satisfy the NONLINEAR constraint |u_t| <= v_bound(s)
+    conv = s.get_int("status") == 0
+    u, x = s.get("u")[conv], s.get("x")[conv]
+    vb = np.array([[ocp.v_bound_sym(sv)[0] for sv in row] for row in x[:, :N, 3]])
+    assert (np.abs(u[:, :, 1]) <= vb + 1e-6).all()
+    # the thread-per-problem kernel implements h = [s; u_n; u_t] only
+    s0 = q.Solver([gm], N, 0.05, B, h_variant=1, qp_kernel=0)
+    _load(s0, wl); s0.prepare()
+    with pytest.raises(q.QspushError):
+        s0.solve()
+    # switching the set on an existing solver resets the bounds
+    s.set_opts(h_variant=0)
+    assert np.allclose(s.get("lh"), [-0.06, 0.0, -0.05]) and np.allclose(s.get("uh"), [0.011, 0.03, 0.05])
+    # MATLAB-shaped mirror
+    sel = q.object_selection("santal")
+    p = q.PusherSliderModel("real_plant", sel, 0, sel.cad_model_path, 3, sel.pcl_path, "santal")
+    p.symbolic_model_variable_shape()
+    c = q.NMPC_controller("NMPC", p, 0.05, 10, nlp_solver="sqp_rti", velocity_constraint_in_ocp=True)
+    c.create_ocp_solver()
+    assert c.ocp_solver.solver.opts.h_variant == 1 and np.allclose(c.ocp_solver.solver.get("lh"), VARIANT_LH)
+    c.initial_condition_update(np.array([0.0, 0.0, 0.0, 0.003]))
+    T = 60; traj = np.zeros((6, T)); traj[0] = 0.01 * 0.05 * np.arange(T); traj[1] = 0.02 * np.sin(np.arange(T) / 8.0)
+    c.set_reference_trajectory(traj)
+    out = q.helper.closed_loop_matlab(p, c, np.array([0.0, 0.0, 0.0, 0.003]), 20 * 0.05)
+    u_t, s_s = np.asarray(out[7]), np.asarray(out[3])
+    assert np.isfinite(u_t).all() and np.abs(u_t).max() <= 0.05 + 1e-9

@@ -173,3 +173,35 @@ def test_full_sqp_iterates():
     conv = (so["status"] == 0) & (sh["status"] == 0)
     assert conv.sum() >= 1 and (so["status"] == sh["status"]).mean() >= 0.75
     assert np.abs(sh["u"][conv] - so["u"][conv]).max() < 1e-6
+
+
+@pytest.mark.parametrize("N", [10, 40])
+def test_velocity_constraint_variant_vs_oracle(N):
+    """h_variant 1: h = [u_n; u_t - v_bound(s); u_t + v_bound(s)] (the authors' parked constraint set,
+    NMPC_controller.m:226-238): rows couple ds and du_t.  Warp-kernel bodies (emulated warp) vs the oracle for the QP,
+    one RTI step and full SQP; the thread-per-problem kernel refuses the variant."""
+    from tests.workloads import VARIANT_LH, VARIANT_UH, make_vbound_workload
+    om, hm = oracle_model("santal"), hostsim_model("santal")
+    B, dt = 16, 0.05
+    wl = make_vbound_workload(B, N)
+    ocp = orc.Ocp(om, N, dt); ocp.set_h_variant(1)
+    pr = ocp.prepare(wl["x0"], np.zeros(B, dtype=np.int32), np.zeros((B, N + 1, 4)), wl["u_init"])
+    kw = dict(h_variant=1, lh=VARIANT_LH, uh=VARIANT_UH)
+    q = ocp.qp(pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"])
+    r = hs.solve([hm], N, dt, pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"], mode="qp", **kw)
+    assert (q["status"] == 0).all() and np.abs(r["qp_iter"] - q["iters"]).max() <= 1
+    assert (np.abs(q["lam"][:, 1:, [1, 2, 4, 5]]).max(axis=(1, 2)) > 1e-3).sum() >= B // 2     # the coupled rows are active
+    assert np.abs(r["du"] - q["du"]).max() < 1e-9 and np.abs(r["dx"] - q["dx"]).max() < 1e-9
+    assert np.abs(r["qp_lam"] - q["lam"]).max() < 1e-7 * max(1.0, np.abs(q["lam"]).max())
+    ro = ocp.solve("rti", pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"])
+    r = hs.solve([hm], N, dt, pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"], mode="rti", **kw)
+    assert np.abs(r["u"] - ro["u"]).max() < 1e-9 and rel_err(r["cost"], ro["cost"]) < 1e-9
+    if N == 10:
+        so = ocp.solve("sqp", pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"])
+        r = hs.solve([hm], N, dt, pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"], mode="sqp", **kw)
+        same = (so["status"] == r["status"]) & (so["sqp_iter"] == r["sqp_iter"])
+        assert same.mean() >= 0.75 and (so["status"] == 0).any()
+        assert np.abs(r["u"][same] - so["u"][same]).max() < 1e-8
+    import ctypes
+    with pytest.raises(Exception):
+        hs.solve([hm], N, dt, pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"], mode="qp", qp_kernel=0, **kw)

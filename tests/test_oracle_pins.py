@@ -270,3 +270,52 @@ def test_golden_fixtures_match_oracle():
         Phi, A, B = m.erk4_sens(g["x"], g["u"], 0.05)
         assert np.array_equal(np.nan_to_num(Phi, nan=7.0), np.nan_to_num(g["Phi"], nan=7.0))
         assert np.array_equal(np.nan_to_num(A, nan=7.0), np.nan_to_num(g["A"], nan=7.0))
+
+
+def test_velocity_constraint_variant_derivative_and_kkt_certificate():
+    """h_variant 1 (the parked constraint set h = [u_n; u_t -+ v_bound(s)], NMPC_controller.m:226-238): v_bound'(s)
+    vs central differences, the symbolic v_bound vs the numeric one of update_tangential_velocity_bounds, and a
+    dense KKT certificate of QP solutions whose coupled rows (ds and du_t in one inequality) are active."""
+    from tests.workloads import VARIANT_LH, VARIANT_UH, make_vbound_workload
+    om = oracle_model("santal")
+    B, N, dt = 16, 40, 0.05
+    ocp = orc.Ocp(om, N, dt); ocp.set_h_variant(1)
+    nact = 0
+    for s in np.linspace(-0.02, 0.02, 81):
+        v, dv = ocp.v_bound_sym(s)
+        assert abs(v - om.v_bound(s)[0]) < 1e-6 * max(v, 1e-3)        # numeric path wraps in float32 (MATLAB single)
+        e = 1e-7
+        vp, vm = ocp.v_bound_sym(s + e)[0], ocp.v_bound_sym(s - e)[0]
+        if v < 0.05 and vp < 0.05 and vm < 0.05 and abs(dv) < 50:      # away from the min() kink and the 1e-4 pole
+            assert abs(dv - (vp - vm) / (2 * e)) < 1e-4 * max(1.0, abs(dv)), (s, dv)
+            nact += 1
+        if v == 0.05:
+            assert dv == 0.0
+    assert nact >= 5
+    wl = make_vbound_workload(B, N)
+    pr = ocp.prepare(wl["x0"], np.zeros(B, dtype=np.int32), np.zeros((B, N + 1, 4)), wl["u_init"])
+    h, beta = ocp.constraints(pr["x"], pr["u"])
+    assert np.abs(beta).max() > 5.0 and np.array_equal(beta[:, :, 1], -beta[:, :, 2]) and not beta[:, :, 0].any()
+    lin = ocp.linearise(pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"])
+    q = ocp.qp(pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"])
+    assert (q["status"] == 0).all() and q["iters"].max() <= 25
+    W = np.diag([1.0, 1.0, 1e-3, 0.0, 1e-3, 1e-3]); We = np.diag([2e5, 2e5, 20.0, 0.0])
+    perm = [4, 5, 0, 1, 2, 3]; H = dt * W[np.ix_(perm, perm)]
+    worst, active = 0.0, 0
+    for b in range(B):
+        dx, du, pi, lam = q["dx"][b], q["du"][b], q["pi"][b], q["lam"][b]
+        for k in range(N):
+            z = np.concatenate([du[k], dx[k]]); BA = np.concatenate([lin["B"][b, k], lin["A"][b, k]], axis=1)
+            g = H @ z + lin["g"][b, k] + BA.T @ pi[k]
+            if k > 0:
+                g[2:] -= pi[k - 1]
+            for c in range(3):
+                a = np.zeros(6); a[0 if c == 0 else 1] = 1.0; a[5] = beta[b, k, c]
+                g += a * (lam[k, 3 + c] - lam[k, c]); v = a @ z
+                sl, su = v - (VARIANT_LH[c] - h[b, k, c]), (VARIANT_UH[c] - h[b, k, c]) - v
+                worst = max(worst, -min(sl, 0), -min(su, 0), abs(lam[k, c] * sl), abs(lam[k, 3 + c] * su))
+                active += int(c > 0 and max(lam[k, c], lam[k, 3 + c]) > 1e-3 and k > 0 and abs(beta[b, k, c]) > 1.0)
+            worst = max(worst, np.abs(g[:2]).max(), np.abs(g[2:]).max() if k > 0 else 0.0)
+            worst = max(worst, np.abs(lin["A"][b, k] @ dx[k] + lin["B"][b, k] @ du[k] + lin["b"][b, k] - dx[k + 1]).max())
+        worst = max(worst, np.abs(We @ dx[N] + lin["qN"][b] - pi[N - 1]).max())
+    assert worst < 5e-12 and active >= 10, (worst, active)

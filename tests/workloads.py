@@ -5,6 +5,8 @@ from __future__ import annotations
 import os
 import sys
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -38,3 +40,16 @@ def packaged_model_pair(name):
 
 def make_rti_workload(om=None, batch=64, N=10, seed=2, dt=0.05, **kw):
     return _mk(batch, N, dt=dt, seed=seed, **kw)
+
+
+def make_vbound_workload(batch, N, seed=2):
+    """Config-3-like workload that makes the parked constraint set h = [u_n; u_t -+ v_bound(s)] (NMPC_controller.m:238)
+    bite: contact points spread over the high-curvature zone of the santal outline (v_bound < u_t_ub there, and
+    v_bound'(s) up to +-30 1/s) and a large tangential velocity in the initial guess."""
+    wl = make_rti_workload(None, batch=batch, N=N, seed=seed)
+    wl["x0"][:, 3] = np.linspace(-0.004, 0.0045, batch)
+    wl["u_init"][:, :, 1] = 0.03 * np.sign(np.linspace(-1.0, 1.0, batch))[:, None]
+    return wl
+
+
+VARIANT_LH, VARIANT_UH = (0.0, -0.1, 0.0), (0.03, 0.0, 0.1)       # [u_n_lb, 2 u_t_lb, 0] / [u_n_ub, 0, 2 u_t_ub]

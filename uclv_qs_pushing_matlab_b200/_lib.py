@@ -32,6 +32,7 @@ class Opts(C.Structure):
         ("qp_tau", C.c_double), ("globalization", C.c_int),
         ("alpha_min", C.c_double), ("alpha_reduction", C.c_double), ("eps_sufficient_descent", C.c_double),
         ("matlab_single_quirk", C.c_int), ("problems_per_warp", C.c_int), ("qp_kernel", C.c_int),
+        ("h_variant", C.c_int),
     ]
 
 

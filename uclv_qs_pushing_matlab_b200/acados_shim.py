@@ -67,10 +67,19 @@ class acados_ocp:
             qp_max_iter=int(opts.get("qp_solver_iter_max", 50)),
             globalization=1 if str(opts.get("globalization", "fixed_step")) == "merit_backtracking" else 0,
         )
-        for k in ("qp_tol", "qp_mu0", "qp_thr", "qp_tau", "problems_per_warp", "matlab_single_quirk"):
+        expr_h = model.get("constr_expr_h")
+        if expr_h is not None:
+            expr_h = tuple(str(e).replace(" ", "") for e in expr_h)
+            if expr_h == ("u_n", "u_t-v_bound(s)", "u_t+v_bound(s)"):
+                kw["h_variant"] = 1                              # NMPC_controller.m:238 (the authors' parked constraint set)
+            elif expr_h != ("s", "u_n", "u_t"):
+                raise L.QspushError(f"constr_expr_h {expr_h!r} is not one of the two constraint sets of the reference")
+        for k in ("qp_tol", "qp_mu0", "qp_thr", "qp_tau", "problems_per_warp", "matlab_single_quirk", "qp_kernel"):
             if opts.get(k) is not None:
                 kw[k] = opts.get(k)
         self.solver = Solver([p._model for p in plants], self.N, self.dt, self.batch, device=device, **kw)
+        if model.get("constr_v_bound") is not None:
+            self.solver.set_ctrl(**model.get("constr_v_bound"))
         W = model.get("cost_W")
         if W is not None:
             self.solver.set("W", np.asarray(W, dtype=np.float64), stage=-1)

@@ -208,6 +208,10 @@ class Solver:
 
     def get(self, field, stage=-1, lo=0, hi=None, out=None):
         hi = self.batch if hi is None else hi
+        if field in ("lh", "uh"):
+            a = np.zeros(3)
+            L.check(L.lib().qspush_get(self._h, _FIELDS[field], -1, 0, 0, a.ctypes.data, L.MEM_HOST))
+            return a
         shape = self._shape(field, stage, hi - lo)
         if out is None:
             out = np.zeros(shape)

@@ -122,6 +122,35 @@ QS_HD double v_bound_of(const double* __restrict__ M, double s, double v_alpha, 
     return fmin(v_alpha / (fabs(ta - t_angle0) + 0.0001) + d_v_bound, u_t_ub);
 }
 
+// kappa(sigma) and d kappa / d sigma from the pp-form of FC_dot: (x, y) = FC_dot, kappa = (x y' - y x') / (x^2 + y^2).
+QS_HD void angle_rate_d(const double* __restrict__ M, double sg, double& kap, double& dkap) {
+    bool valid;
+    const int q = span_of(M, sg, valid);
+    if (!valid) { kap = 0.0 / 0.0; dkap = 0.0 / 0.0; return; }     // every basis function is 0: atan2(0, 0)' = 0/0
+    const double tau = sg - M[HDR + q];
+    const double* k = M + COEF_OFF + q * COEF_STRIDE;
+    const double x = fma(fma(k[10], tau, k[9]), tau, k[8]), y = fma(fma(k[13], tau, k[12]), tau, k[11]);
+    const double xp = fma(2.0 * k[10], tau, k[9]), yp = fma(2.0 * k[13], tau, k[12]);
+    const double xpp = 2.0 * k[10], ypp = 2.0 * k[13];
+    const double num = x * yp - y * xp, den = x * x + y * y;
+    kap = num / den;
+    dkap = ((x * ypp - y * xpp) * den - num * 2.0 * (x * xp + y * yp)) / (den * den);
+}
+
+// v_bound(s) of the parked constraint variant h = [u_n; u_t -+ v_bound(s)] (NMPC_controller.m:226-230, :238) and
+// its derivative with CasADi's AD rules (comparisons constant, d fmod = 1, d|a| = sign a, d fmin(a, c) = [a < c]):
+//   s_mod = (s<0)*b + mod(s,b);  t = |kappa(s_mod)|;  v = min(v_alpha / (|t - t0| + 1e-4) + d_v_bound, u_t_ub)
+QS_HD double v_bound_sym(const double* __restrict__ M, double s, const double vbp[4], double* dv) {
+    const double sw = wrap_dyn(s, M[1]);
+    double kap, dkap;
+    angle_rate_d(M, sw, kap, dkap);
+    const double t = fabs(kap), e = fabs(t - vbp[2]) + 0.0001;
+    const double a = vbp[0] / e + vbp[1];
+    const double sg1 = (double)((kap > 0.0) - (kap < 0.0)), sg2 = (double)((t - vbp[2] > 0.0) - (t - vbp[2] < 0.0));
+    if (dv) *dv = (a < vbp[3]) ? -vbp[0] / (e * e) * sg2 * sg1 * dkap : 0.0;
+    return fmin(a, vbp[3]);
+}
+
 // ---- dynamics ----------------------------------------------------------------------------------
 struct Dyn {
     double f[4];     // xdot

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(32) k_qp(SolverDev S, IpmOpts o, int ppw, int 
 // the dynamic shared memory; the read-only linearisation lives in tensor memory: the CTA allocates all 512 TMEM
 // columns, warp w owns TMEM lanes 32*(w%4).. (the quarter the hardware lets it address) and columns 256*(w/4)..
 constexpr int QW_MAX_WARPS = 8;
-template <int C>
+template <int C, int HV>
 __global__ void __launch_bounds__(32 * QW_MAX_WARPS, 1) k_qp_warp(SolverDev S, IpmOpts o, int apply, int per_warp_doubles) {
     extern __shared__ __align__(16) double qw_smem[];
     __shared__ unsigned tmem_base;
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(32 * QW_MAX_WARPS, 1) k_qp_warp(SolverDev S, I
             if (!(S.done && S.done[b])) return b;                // full SQP: skip problems that already converged
         }
     };
-    qp_warp_persistent<WarpCtxDev, C>(w, qw_smem + (size_t)wid * per_warp_doubles, S, o, apply, next);
+    qp_warp_persistent<WarpCtxDev, C, HV>(w, qw_smem + (size_t)wid * per_warp_doubles, S, o, apply, next);
     // every warp left the loop through the same CTA-wide vote: no TMEM access is in flight any more
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

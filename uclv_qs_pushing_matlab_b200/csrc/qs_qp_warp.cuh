@@ -376,12 +376,19 @@ QS_HD void qw_ld_lin(const Ctx& w, int j, StageLin& L) {
 // 1/t_l (0..2) and 1/t_u (4..6) of local stage j, as left by phase (2) of the current iteration
 template <class Ctx>
 QS_HD void qw_ld_it(const Ctx& w, int j, double* it8) { w.template tm_ld<8>(j * QW_TM_STAGE + QW_TM_IT, it8); }
-// h_k = (s, u_n, u_t) at the linearisation point
+// h_k (3 values) at the linearisation point and beta_k = v_bound'(s_k) (0 unless h_variant 1): 4 doubles
 template <class Ctx>
-QS_HD void qw_ld_h(const Ctx& w, int j, double* h) {
-    double v[4];
-    w.template tm_ld<4>(j * QW_TM_STAGE + QW_TM_HH, v);
-    h[0] = v[0]; h[1] = v[1]; h[2] = v[2];
+QS_HD void qw_ld_h(const Ctx& w, int j, double* h4) { w.template tm_ld<4>(j * QW_TM_STAGE + QW_TM_HH, h4); }
+// value of constraint row c on a stage vector z6 = [u_n, u_t, x, y, theta, s]
+// (the coupling term sits behind a warp-uniform branch: the default constraint set pays nothing for it)
+QS_HD double qw_row(int hv, int c, double beta, const double* z6) {
+    if (!hv) return z6[cidx(c)];
+    return z6[c == 0 ? 0 : 1] + h_bcoef(1, c, beta) * z6[5];
+}
+// scatter w * row c into a stage gradient
+QS_HD void qw_row_add(int hv, int c, double beta, double w, double* g6) {
+    if (!hv) { g6[cidx(c)] += w; return; }
+    g6[c == 0 ? 0 : 1] += w; g6[5] += h_bcoef(1, c, beta) * w;
 }
 
 // One Newton solve with the current factorisation: rhs gt (R_GT rows) and r_b (R_RB) ->
@@ -584,7 +591,7 @@ struct QwState {
 };
 
 // ---- load the linearisation of problem V into the warp's shared memory, initial point
-template <class Ctx, int C>
+template <class Ctx, int C, int HV>
 QS_HD void qw_init(const Ctx& w, double* __restrict__ sm, const QpConst& Q, const QpView& V, QwState& st) {
     const int N = Q.N;
     const int lane = w.lane();
@@ -613,7 +620,8 @@ QS_HD void qw_init(const Ctx& w, double* __restrict__ sm, const QpConst& Q, cons
             }
 #pragma unroll
             for (int i = 0; i < 6; ++i) v[QW_TM_G + i] = QS_AT(V.g, k, 6, i);
-            v[QW_TM_HH + 0] = QS_AT(V.x, k, 4, 3); v[QW_TM_HH + 1] = QS_AT(V.u, k, 2, 0); v[QW_TM_HH + 2] = QS_AT(V.u, k, 2, 1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[QW_TM_HH + i] = QS_AT(V.hv, k, 4, i);     // h_k (3) and v_bound'(s_k)
         }
         w.tm_st16(j * QW_TM_STAGE, v);                      // warp-collective: every lane stores (zeros when idle)
         w.tm_st16(j * QW_TM_STAGE + 16, v + 16);
@@ -624,9 +632,13 @@ QS_HD void qw_init(const Ctx& w, double* __restrict__ sm, const QpConst& Q, cons
                 for (int i = 0; i < 4; ++i) QW_SM(R_Z + 2 + i, j) = V.dx0[i * V.stride];
             }
 #pragma unroll
+            double z6[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) z6[i] = QW_SM(R_Z + i, j);
+#pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const bool bon = !(k == 0 && c == 0);
-                const double z = QW_SM(R_Z + cidx(c), j);
+                const bool bon = h_on(HV, k, c);
+                const double z = qw_row(HV, c, h[3], z6);
                 double tl = fmax(z - (Q.lh[c] - h[c]), Q.thr), tu = fmax((Q.uh[c] - h[c]) - z, Q.thr);
                 double ll = Q.mu0 / tl, lu = Q.mu0 / tu;
                 if (!bon) { tl = 1.0; tu = 1.0; ll = 0.0; lu = 0.0; }
@@ -645,13 +657,14 @@ QS_HD void qw_init(const Ctx& w, double* __restrict__ sm, const QpConst& Q, cons
 
 // ---- one IPM iteration: true residuals + stopping tests, factorisation (parallel-in-time), predictor,
 // corrector, step.  Returns 0 to continue, 1 when the problem is finished (st.status set).
-template <class Ctx, int C>
+template <class Ctx, int C, int HV>
 QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, QwState& st) {
     const int N = Q.N;
     const int lane = w.lane();
     const int Lw_ = qp_warp_lanes(N, C);
     const bool act = lane < Lw_;
-    const int m_on = 6 * N - 2;
+    constexpr int hvar = HV;                            // constraint set: compile-time, the default set pays nothing for the coupled rows
+    const int m_on = hvar ? 6 * N : 6 * N - 2;
     int& status = st.status; int& it = st.it; int& stall = st.stall;
     double& rmax_prev = st.rmax_prev; double& r_stat = st.r_stat; double& r_eq = st.r_eq; double& r_in = st.r_in; double& r_cp = st.r_cp;
     const double* qN = st.qN;
@@ -705,10 +718,10 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                 for (int i = 0; i < 4; ++i) rg[2 + i] -= pik[i];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    if (k == 0 && c == 0) continue;
-                    const double h = hk[c], v = z6[cidx(c)];
+                    if (!h_on(hvar, k, c)) continue;
+                    const double h = hk[c], v = qw_row(hvar, c, hk[3], z6);
                     const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
-                    rg[cidx(c)] += lu - ll;
+                    qw_row_add(hvar, c, hk[3], lu - ll, rg);
                     const double rdl = v - (Q.lh[c] - h) - tl, rdu = (Q.uh[c] - h) - v - tu;
                     l_in = fmax(l_in, fmax(fabs(rdl), fabs(rdu)));
                     l_cp = fmax(l_cp, fmax(ll * tl, lu * tu));
@@ -749,7 +762,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
         for (int j = C - 1; j >= 0; --j) {
             const int k = lane * C + j;
             StageLin L;
-            double hk[3];
+            double hk[4];
             qw_ld_lin(w, j, L);
             qw_ld_h(w, j, hk);
             // barrier terms first: slack reciprocals and D go to the TMEM block (warp-collective store), affine rhs to R_GT
@@ -759,20 +772,23 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
 #pragma unroll
             for (int i = 0; i < 4; ++i) D[i] = 0.0;
             if (act && k < N) {
-                double gt[6];
+                double gt[6], z6[6], Dc[3];
 #pragma unroll
-                for (int i = 0; i < 6; ++i) gt[i] = QW_SM(R_RG + i, j);
+                for (int i = 0; i < 6; ++i) { gt[i] = QW_SM(R_RG + i, j); z6[i] = QW_SM(R_Z + i, j); }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const double h = hk[c], v = QW_SM(R_Z + cidx(c), j);
+                    const double h = hk[c], v = qw_row(hvar, c, hk[3], z6);
                     const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
                     const double itl = 1.0 / tl, itu = 1.0 / tu;
-                    const bool on = !(k == 0 && c == 0);
+                    const bool on = h_on(hvar, k, c);
                     const double rdl = on ? v - (Q.lh[c] - h) - tl : 0.0, rdu = on ? (Q.uh[c] - h) - v - tu : 0.0;
                     it8[c] = itl; it8[4 + c] = itu;
-                    D[c] = ll * itl + lu * itu;
-                    gt[cidx(c)] += (ll + ll * rdl * itl) - (lu + lu * rdu * itu);
+                    Dc[c] = ll * itl + lu * itu;
+                    qw_row_add(hvar, c, hk[3], (ll + ll * rdl * itl) - (lu + lu * rdu * itu), gt);
                 }
+                // barrier Hessian sum_c D_c a_c a_c' as (D_ss, D_unun, D_utut, D_s,ut)
+                if (hvar) { const double be = hk[3]; D[0] = be * be * (Dc[1] + Dc[2]); D[1] = Dc[0]; D[2] = Dc[1] + Dc[2]; D[3] = be * (Dc[2] - Dc[1]); }
+                else { D[0] = Dc[0]; D[1] = Dc[1]; D[2] = Dc[2]; D[3] = 0.0; }
 #pragma unroll
                 for (int i = 0; i < 6; ++i) QW_SM(R_GT + i, j) = gt[i];
             }
@@ -796,7 +812,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 bh0[i] = L.b1[i] * i00; bh1[i] = (L.b2[i] - l10 * bh0[i]) * i11;
-                const double s0 = Hk[LT(2 + i, 0)], s1 = Hk[LT(2 + i, 1)];
+                const double s0 = Hk[LT(2 + i, 0)], s1 = Hk[LT(2 + i, 1)] + (i == 3 ? D[3] : 0.0);
                 sh0[i] = s0 * i00; sh1[i] = (s1 - l10 * sh0[i]) * i11;
             }
             Elem e;
@@ -874,7 +890,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
 #pragma unroll
             for (int i = 0; i < 4; ++i) rb[i] = QW_SM(R_RB + i, j);
             sym4_mul(P, rb, Pb);
-            ok = riccati_factor_stage(L, Q.H + (size_t)k * 21, D, P, K0, K1, Li) && ok;
+            ok = riccati_factor_stage(L, Q.H + (size_t)k * 21, D, P, K0, K1, Li, D[3]) && ok;
 #pragma unroll
             for (int i = 0; i < 4; ++i) { QW_SM(R_K + i, j) = K0[i]; QW_SM(R_K + 4 + i, j) = K1[i]; QW_SM(R_PB + i, j) = Pb[i]; }
 #pragma unroll
@@ -894,23 +910,23 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
 #pragma unroll 1
             for (int j = 0; j < C; ++j) {
                 const int k = lane * C + j;
-                double hk[3], it8[8];
+                double hk[4], it8[8];
                 qw_ld_h(w, j, hk);
                 qw_ld_it(w, j, it8);
                 if (!act || k >= N) continue;
-                double gt[6];
+                double gt[6], z6[6];
 #pragma unroll
-                for (int i = 0; i < 6; ++i) gt[i] = QW_SM(R_RG + i, j);
+                for (int i = 0; i < 6; ++i) { gt[i] = QW_SM(R_RG + i, j); z6[i] = QW_SM(R_Z + i, j); }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    if (k == 0 && c == 0) continue;
-                    const double h = hk[c], v = QW_SM(R_Z + cidx(c), j), dva = QW_SM(R_DZA + c, j);
+                    if (!h_on(hvar, k, c)) continue;
+                    const double h = hk[c], v = qw_row(hvar, c, hk[3], z6), dva = QW_SM(R_DZA + c, j);
                     const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
                     const double rdl = v - (Q.lh[c] - h) - tl, rdu = (Q.uh[c] - h) - v - tu;
                     const double dtl = dva + rdl, dtu = -dva + rdu;
                     const double itl = it8[c], itu = it8[4 + c];
                     const double cl = (-ll - ll * dtl * itl) * dtl, cu = (-lu - lu * dtu * itu) * dtu;
-                    gt[cidx(c)] += (ll * tl - smu + cl + ll * rdl) * itl - (lu * tu - smu + cu + lu * rdu) * itu;
+                    qw_row_add(hvar, c, hk[3], (ll * tl - smu + cl + ll * rdl) * itl - (lu * tu - smu + cu + lu * rdu) * itu, gt);
                 }
 #pragma unroll
                 for (int i = 0; i < 6; ++i) QW_SM(R_GT + i, j) = gt[i];
@@ -926,16 +942,19 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
 #pragma unroll 1
                 for (int j = 0; j < C; ++j) {
                     const int k = lane * C + j;
-                    double hk[3], it8[8];
+                    double hk[4], it8[8];
                     qw_ld_h(w, j, hk);
                     qw_ld_it(w, j, it8);
                     if (!act || k >= N) continue;
+                    double z6[6], dz6[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) { z6[i] = QW_SM(R_Z + i, j); dz6[i] = QW_SM(R_GT + i, j); }
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        const double dva = QW_SM(R_GT + cidx(c), j);
+                        const double dva = qw_row(hvar, c, hk[3], dz6);
                         QW_SM(R_DZA + c, j) = dva;
-                        if (k == 0 && c == 0) continue;
-                        const double h = hk[c], v = QW_SM(R_Z + cidx(c), j);
+                        if (!h_on(hvar, k, c)) continue;
+                        const double h = hk[c], v = qw_row(hvar, c, hk[3], z6);
                         const double ll = QW_SM(R_LAM + c, j), lu = QW_SM(R_LAM + 3 + c, j), tl = QW_SM(R_T + c, j), tu = QW_SM(R_T + 3 + c, j);
                         const double dtl = dva + (v - (Q.lh[c] - h) - tl), dtu = -dva + ((Q.uh[c] - h) - v - tu);
                         const double dll = -ll - ll * dtl * it8[c], dlu = -lu - lu * dtu * it8[4 + c];
@@ -960,14 +979,17 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
 #pragma unroll 1
         for (int j = 0; j < C; ++j) {
             const int k = lane * C + j;
-            double hk[3], it8[8];
+            double hk[4], it8[8];
             qw_ld_h(w, j, hk);
             qw_ld_it(w, j, it8);
             if (!act || k >= N) continue;
+            double z6[6], dz6[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { z6[i] = QW_SM(R_Z + i, j); dz6[i] = QW_SM(R_GT + i, j); }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                if (k == 0 && c == 0) continue;
-                IneqStep s_ = ineq_step(QW_SM(R_Z + cidx(c), j), QW_SM(R_DZA + c, j), QW_SM(R_GT + cidx(c), j),
+                if (!h_on(hvar, k, c)) continue;
+                IneqStep s_ = ineq_step(qw_row(hvar, c, hk[3], z6), QW_SM(R_DZA + c, j), qw_row(hvar, c, hk[3], dz6),
                                         QW_SM(R_LAM + c, j), QW_SM(R_LAM + 3 + c, j), QW_SM(R_T + c, j), QW_SM(R_T + 3 + c, j),
                                         it8[c], it8[4 + c], Q.lh[c] - hk[c], Q.uh[c] - hk[c], smu);
                 ratio_min(QW_SM(R_T + c, j), s_.dtl, m_num, m_den); ratio_min(QW_SM(R_T + 3 + c, j), s_.dtu, m_num, m_den);
@@ -982,7 +1004,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
 #pragma unroll 1
         for (int j = 0; j < C; ++j) {
             const int k = lane * C + j;
-            double hk[3], it8[8];
+            double hk[4], it8[8];
             qw_ld_h(w, j, hk);
             qw_ld_it(w, j, it8);
             if (!act || k > N) continue;
@@ -999,9 +1021,13 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             }
             if (k < N) {
 #pragma unroll
+                double z6[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) z6[i] = QW_SM(R_Z + i, j);
+#pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    if (k == 0 && c == 0) continue;
-                    IneqStep s_ = ineq_step(QW_SM(R_Z + cidx(c), j), QW_SM(R_DZA + c, j), dz[cidx(c)],
+                    if (!h_on(hvar, k, c)) continue;
+                    IneqStep s_ = ineq_step(qw_row(hvar, c, hk[3], z6), QW_SM(R_DZA + c, j), qw_row(hvar, c, hk[3], dz),
                                             QW_SM(R_LAM + c, j), QW_SM(R_LAM + 3 + c, j), QW_SM(R_T + c, j), QW_SM(R_T + 3 + c, j),
                                             it8[c], it8[4 + c], Q.lh[c] - hk[c], Q.uh[c] - hk[c], smu);
                     QW_SM(R_T + c, j) = fma(alpha, s_.dtl, QW_SM(R_T + c, j));

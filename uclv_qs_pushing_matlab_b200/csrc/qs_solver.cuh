@@ -24,6 +24,7 @@ struct SolverDev {
     double *x0, *yref, *yref_e;          // [4] [N*6] [4]
     // linearisation
     double *A, *Bm, *b, *g, *qN, *dx0;   // [N*8] [N*8] [N*4] [N*6] [4] [4]
+    double *hv;                          // [N*4] constraint function h_k (3) and v_bound'(s_k) (h_variant 1; else 0)
     // QP work
     double *z, *zp, *zc, *lamq, *t, *K, *Li, *Pb, *kff, *piq, *rg, *rb, *rgs;
     // cost / constraint constants
@@ -32,6 +33,8 @@ struct SolverDev {
     const double *H;        // [N][21] packed, z order
     const double *QN;       // [10]
     double lh[3], uh[3];
+    int h_variant;          // 0: h = [s; u_n; u_t]   1: h = [u_n; u_t - v_bound(s); u_t + v_bound(s)]  (NMPC_controller.m:237/238)
+    double vbp[4];          // v_alpha, d_v_bound, t_angle0, u_t_ub of v_bound(s) (:229)
     // bookkeeping
     int *status, *sqp_iter, *qp_iter, *cold, *done, *qpstat, *ndone;   // ndone[0]: SQP finished count, ndone[1]: QP work-queue head
     double *cost, *res, *alpha;
@@ -95,6 +98,13 @@ QS_HD void prepare_one(const SolverDev& S, const CtrlDev& cp, const double* __re
     for (int i = 0; i < 4; ++i) QS_EL(S.x, N * 4 + i, b) = x[i];
 }
 
+// constraint function of one stage at (s, u_n, u_t); beta = v_bound'(s) (rows 1 / 2 carry -beta / +beta on ds)
+QS_HD void h_eval(const SolverDev& S, const double* __restrict__ M, double s, double un, double ut, double h[3], double* beta) {
+    if (S.h_variant == 0) { h[0] = s; h[1] = un; h[2] = ut; if (beta) *beta = 0.0; return; }
+    const double vb = v_bound_sym(M, s, S.vbp, beta);
+    h[0] = un; h[1] = ut - vb; h[2] = ut + vb;
+}
+
 // K2 + K3 linearise, one (problem, stage) pair; stage index N does the terminal terms.
 //   A_k, B_k, b_k = Phi(x_k,u_k) - x_{k+1}   (ERK4 + forward sensitivities)
 //   g_k = dt * W_k ([x_k;u_k] - yref_k) in z = [u;x] order ; q_N = W_e (x_N - yref_e) ; dx0 = x0 - x_0
@@ -133,6 +143,13 @@ QS_HD void linearise_one(const SolverDev& S, const double* __restrict__ Mall, in
         QS_EL(S.Bm, k * 8 + i, b) = Sm[4 * i + 2];
         QS_EL(S.Bm, k * 8 + 4 + i, b) = Sm[4 * i + 3];
         QS_EL(S.b, k * 4 + i, b) = Phi[i] - xn[i];
+    }
+    {
+        double h[3], beta;
+        h_eval(S, M, x[3], un, ut, h, &beta);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) QS_EL(S.hv, k * 4 + c, b) = h[c];
+        QS_EL(S.hv, k * 4 + 3, b) = beta;
     }
     const double r[6] = {x[0] - yr[0], x[1] - yr[1], x[2] - yr[2], x[3] - yr[3], un - yr[4], ut - yr[5]};
     const double* W = S.Wdt + (size_t)k * 36;
@@ -183,9 +200,11 @@ QS_HD void qp_one(const SolverDev& S, const IpmOpts& o, int b, int apply) {
     C.N = S.N; C.H = S.H; C.QN = S.QN;
 #pragma unroll
     for (int i = 0; i < 3; ++i) { C.lh[i] = S.lh[i]; C.uh[i] = S.uh[i]; }
+    C.h_variant = 0;                           // the thread-per-problem kernel implements h = [s; u_n; u_t] only
     C.max_iter = o.max_iter; C.tol = o.tol; C.mu0 = o.mu0; C.thr = o.thr; C.tau = o.tau;
     QpView V;
     V.stride = (size_t)S.Bp;
+    V.hv = S.hv + b;
     V.A = S.A + b; V.B = S.Bm + b; V.b = S.b + b; V.g = S.g + b; V.qN = S.qN + b; V.dx0 = S.dx0 + b;
     V.x = S.x + b; V.u = S.u + b;
     V.z = S.z + b; V.zp = S.zp + b; V.zc = S.zc + b; V.t = S.t + b;
@@ -224,12 +243,13 @@ QS_HD void qp_one(const SolverDev& S, const IpmOpts& o, int b, int apply) {
 // time and pulls the next one from a work queue when it finishes (`next` returns a warp-uniform problem
 // index or -1), while one CTA-wide vote per IPM iteration keeps the warps in lockstep (shared instruction
 // fetches).  sm = the warp's shared-memory state (qp_warp_smem_doubles(N) doubles).
-template <class Ctx, int C, class NextFn>
+template <class Ctx, int C, int HV, class NextFn>
 QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm, const SolverDev& S, const IpmOpts& o, int apply, NextFn next) {
     QpConst Qc;
     Qc.N = S.N; Qc.H = S.H; Qc.QN = S.QN;
 #pragma unroll
     for (int i = 0; i < 3; ++i) { Qc.lh[i] = S.lh[i]; Qc.uh[i] = S.uh[i]; }
+    Qc.h_variant = HV;
     Qc.max_iter = o.max_iter; Qc.tol = o.tol; Qc.mu0 = o.mu0; Qc.thr = o.thr; Qc.tau = o.tau;
     const int lane = w.lane();
     const int N = S.N;
@@ -241,13 +261,13 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm, const Solve
     auto bind = [&](int b_) {
         V.stride = (size_t)S.Bp;
         V.A = S.A + b_; V.B = S.Bm + b_; V.b = S.b + b_; V.g = S.g + b_; V.qN = S.qN + b_; V.dx0 = S.dx0 + b_;
-        V.x = S.x + b_; V.u = S.u + b_;
+        V.x = S.x + b_; V.u = S.u + b_; V.hv = S.hv + b_;
         V.z = S.z + b_; V.zp = S.zp + b_; V.zc = S.zc + b_; V.t = S.t + b_;
         V.K = S.K + b_; V.Li = S.Li + b_; V.Pb = S.Pb + b_; V.kff = S.kff + b_;
         V.rg = S.rg + b_; V.rb = S.rb + b_; V.rgs = S.rgs + b_;
         V.lam = (apply ? S.lam : S.lamq) + b_;
         V.pi = (apply ? S.pi : S.piq) + b_;
-        qw_init<Ctx, C>(w, sm, Qc, V, st);
+        qw_init<Ctx, C, HV>(w, sm, Qc, V, st);
     };
     int b = next();
     {
@@ -262,7 +282,7 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm, const Solve
         if (w.cta_all(b < 0)) break;
         QW_TICK(0);
         if (b < 0) continue;
-        const int fin = qw_iterate<Ctx, C>(w, sm, Qc, st);
+        const int fin = qw_iterate<Ctx, C, HV>(w, sm, Qc, st);
         if (fin == 0) continue;
         // ---- problem b is finished: write back, K5 epilogue, fetch the next problem
         qw_writeback<Ctx, C>(w, sm, Qc, V);
@@ -325,12 +345,14 @@ QS_HD int nlp_res_one(const SolverDev& S, const SqpOpts& o, int it, int b) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) g[2 + i] -= QS_EL(S.pi, (k - 1) * 4 + i, b);
         }
-        const double h[3] = {QS_EL(S.x, k * 4 + 3, b), QS_EL(S.u, k * 2, b), QS_EL(S.u, k * 2 + 1, b)};
+        const double h[3] = {QS_EL(S.hv, k * 4, b), QS_EL(S.hv, k * 4 + 1, b), QS_EL(S.hv, k * 4 + 2, b)};
+        const double beta = QS_EL(S.hv, k * 4 + 3, b);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            if (k == 0 && c == 0) continue;
+            if (!h_on(S.h_variant, k, c)) continue;
             const double ll = QS_EL(S.lam, k * 6 + c, b), lu = QS_EL(S.lam, k * 6 + 3 + c, b);
-            g[cidx(c)] += lu - ll;
+            g[h_pidx(S.h_variant, c)] += lu - ll;
+            g[5] += h_bcoef(S.h_variant, c, beta) * (lu - ll);
             const double sl = h[c] - S.lh[c], su = S.uh[c] - h[c];
             r_in = fmax(r_in, fmax(fmax(-sl, 0.0), fmax(-su, 0.0)));
             r_cp = fmax(r_cp, fmax(fabs(ll * sl), fabs(lu * su)));
@@ -387,10 +409,11 @@ QS_HD double merit_at(const SolverDev& S, const double* M, int b, double alpha) 
         erk4_plain(M, x, un, ut, S.dt, Phi);
 #pragma unroll
         for (int i = 0; i < 4; ++i) mval += QS_EL(S.wpi, k * 4 + i, b) * fabs(Phi[i] - xn[i]);
-        const double h[3] = {x[3], un, ut};
+        double h[3];
+        h_eval(S, M, x[3], un, ut, h, nullptr);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            if (k == 0 && c == 0) continue;
+            if (!h_on(S.h_variant, k, c)) continue;
             mval += QS_EL(S.wlam, k * 6 + c, b) * fmax(0.0, S.lh[c] - h[c]);
             mval += QS_EL(S.wlam, k * 6 + 3 + c, b) * fmax(0.0, h[c] - S.uh[c]);
         }
@@ -428,13 +451,13 @@ QS_HD int linesearch_one(const SolverDev& S, const SqpOpts& o, const double* __r
                 QS_EL(S.wpi, k * 4 + i, b) = w;
                 dinf += w * fabs(QS_EL(S.b, k * 4 + i, b));
             }
-            const double h[3] = {QS_EL(S.x, k * 4 + 3, b), QS_EL(S.u, k * 2, b), QS_EL(S.u, k * 2 + 1, b)};
+            const double h[3] = {QS_EL(S.hv, k * 4, b), QS_EL(S.hv, k * 4 + 1, b), QS_EL(S.hv, k * 4 + 2, b)};
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
                 const double a = fabs(QS_EL(S.lamq, k * 6 + c, b));
                 const double w = (it == 0) ? a : fmax(a, 0.5 * (QS_EL(S.wlam, k * 6 + c, b) + a));
                 QS_EL(S.wlam, k * 6 + c, b) = w;
-                if (k == 0 && (c % 3) == 0) continue;
+                if (!h_on(S.h_variant, k, c % 3)) continue;
                 const int cc = c % 3;
                 dinf += w * (c < 3 ? fmax(0.0, S.lh[cc] - h[cc]) : fmax(0.0, h[cc] - S.uh[cc]));
             }
@@ -458,6 +481,11 @@ QS_HD int linesearch_one(const SolverDev& S, const SqpOpts& o, const double* __r
                 m[i] = a;
             }
             m[2] += pk1[0]; m[3] += pk1[1]; m[4] += dot4(a3, pk1); m[5] += dot4(a4, pk1);
+            if (S.h_variant) {
+                const double beta = QS_EL(S.hv, 3, b);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) m[5] += h_bcoef(1, c, beta) * (QS_EL(S.lamq, 3 + c, b) - QS_EL(S.lamq, c, b));
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const double a = fabs(m[2 + i]);

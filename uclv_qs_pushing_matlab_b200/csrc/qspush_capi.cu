@@ -252,6 +252,24 @@ void qspush_opts_default(qspush_opts* o) {
     o->matlab_single_quirk = 1;
     o->problems_per_warp = 0;
     o->qp_kernel = 2;
+    o->h_variant = 0;
+}
+
+// default bounds of the selected constraint set (NMPC_controller.m:251-252 with :23-26, 83-84; variant: :247-248)
+static void reset_bounds(qspush_solver* s) {
+    SolverDev& D = s->dev;
+    if (s->opts.h_variant) {
+        const double lh[3] = {s->ctrl.u_n_lb, -2.0 * s->ctrl.u_t_ub, 0.0}, uh[3] = {0.03, 0.0, 2.0 * s->ctrl.u_t_ub};
+        for (int i = 0; i < 3; ++i) { D.lh[i] = lh[i]; D.uh[i] = uh[i]; }
+    } else {
+        const double lh[3] = {-0.06, 0.0, -0.05}, uh[3] = {0.011, 0.03, 0.05};
+        for (int i = 0; i < 3; ++i) { D.lh[i] = lh[i]; D.uh[i] = uh[i]; }
+    }
+}
+// constraint-set selection and the v_bound parameters travel with every launch
+static void apply_variant(const qspush_solver* s, SolverDev& D) {
+    D.h_variant = s->opts.h_variant ? 1 : 0;
+    D.vbp[0] = s->ctrl.v_alpha; D.vbp[1] = s->ctrl.d_v_bound; D.vbp[2] = s->ctrl.t_angle0; D.vbp[3] = s->ctrl.u_t_ub;
 }
 
 static size_t al(size_t doubles) { return (doubles + 31) / 32 * 32; }   // 256-byte granules
@@ -279,6 +297,7 @@ int qspush_solver_create(const qspush_model* const* models, int nmodels, int N, 
         {&D.x, (size_t)(N + 1) * 4}, {&D.u, (size_t)N * 2}, {&D.pi, (size_t)N * 4}, {&D.lam, (size_t)N * 6},
         {&D.x0, 4}, {&D.yref, (size_t)N * 6}, {&D.yref_e, 4},
         {&D.A, (size_t)N * 8}, {&D.Bm, (size_t)N * 8}, {&D.b, (size_t)N * 4}, {&D.g, (size_t)N * 6}, {&D.qN, 4}, {&D.dx0, 4},
+        {&D.hv, (size_t)N * 4},
         {&D.z, (size_t)(N + 1) * 6}, {&D.zp, (size_t)(N + 1) * 6}, {&D.zc, (size_t)N * 3}, {&D.lamq, (size_t)N * 6}, {&D.t, (size_t)N * 6},
         {&D.K, (size_t)N * 8}, {&D.Li, (size_t)N * 3}, {&D.Pb, (size_t)N * 4}, {&D.kff, (size_t)N * 2}, {&D.piq, (size_t)N * 4},
         {&D.rg, (size_t)(N + 1) * 6}, {&D.rb, (size_t)N * 4}, {&D.rgs, (size_t)N},
@@ -323,8 +342,7 @@ int qspush_solver_create(const qspush_model* const* models, int nmodels, int N, 
         for (int i = 0; i < 2; ++i) s->W[(size_t)k * 36 + 7 * (4 + i)] = wu[i];
     }
     for (int i = 0; i < 4; ++i) s->We[5 * i] = we[i];
-    const double lh[3] = {-0.06, 0.0, -0.05}, uh[3] = {0.011, 0.03, 0.05};
-    for (int i = 0; i < 3; ++i) { D.lh[i] = lh[i]; D.uh[i] = uh[i]; }
+    reset_bounds(s);
     s->cost_dirty = true;
     // dynamic shared memory for the model tables
     const int smem = (int)model_smem_bytes(nmodels);
@@ -350,7 +368,10 @@ void qspush_solver_free(qspush_solver* s) {
 
 int qspush_solver_set_opts(qspush_solver* s, const qspush_opts* o) {
     if (!s || !o) return fail(QSPUSH_ERR_ARG, "NULL argument");
-    s->opts = *o; return QSPUSH_OK;
+    const bool changed = (o->h_variant != 0) != (s->opts.h_variant != 0);
+    s->opts = *o;
+    if (changed) reset_bounds(s);
+    return QSPUSH_OK;
 }
 int qspush_solver_set_ctrl(qspush_solver* s, const qspush_ctrl* c) {
     if (!s || !c) return fail(QSPUSH_ERR_ARG, "NULL argument");
@@ -529,7 +550,7 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
     // kernel to fill the GPU.  Measured crossovers on B200: N = 40: ~50k problems (2.2M it/s flat
     // from 8k on vs 0.4M -> 2.3M it/s); N = 10 and N = 100: between 4k and 32k
     const int warp_below = (C == 2) ? 49152 : 16384;
-    const bool want_warp = s->opts.qp_kernel == 1 || (s->opts.qp_kernel == 2 && s->B < warp_below);
+    const bool want_warp = s->opts.qp_kernel == 1 || (s->opts.qp_kernel == 2 && (s->B < warp_below || D.h_variant));
     // resident problems (= warps) per CTA: bounded by shared memory (one CTA per SM), by the register file
     // (8 warps of 255 registers) and by TMEM (8 blocks of 32 lanes x 256 columns)
     const int pwd = (int)((qp_warp_smem_doubles(s->N) + 1) / 2 * 2);
@@ -539,6 +560,7 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
     const bool warp = want_warp && C <= 4 && W >= 2;
     if (!warp && s->opts.qp_kernel == 2 && s->opts.problems_per_warp == 0) ppw = (s->B >= 12288) ? 32 : ppw;
     if (!warp) {
+        if (D.h_variant) return fail(QSPUSH_ERR_ARG, "h_variant 1 needs the warp QP kernel (qp_kernel 1 or 2, N <= 127)");
         k_qp<<<(unsigned)((s->B + ppw - 1) / ppw), 32, 0, s->stream>>>(D, io, ppw, apply);
         return QSPUSH_OK;
     }
@@ -550,14 +572,18 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
     const int Wl = std::max(1, std::min(W, (s->B + nsm - 1) / nsm));
     const unsigned blocks = (unsigned)std::min((s->B + Wl - 1) / Wl, nsm);             // persistent: one CTA per SM
     CK(cudaMemsetAsync(D.ndone + 1, 0, sizeof(int), s->stream));                       // work-queue head
-#define QW_LAUNCH(CC)                                                                                              \
-    CK(cudaFuncSetAttribute(k_qp_warp<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
-    k_qp_warp<CC><<<blocks, 32 * Wl, smem, s->stream>>>(D, io, apply, pwd)
-    switch (C) {
-        case 1: QW_LAUNCH(1); break;
-        case 2: QW_LAUNCH(2); break;
-        case 3: QW_LAUNCH(3); break;
-        default: QW_LAUNCH(4); break;
+#define QW_LAUNCH(CC, HV)                                                                                          \
+    CK(cudaFuncSetAttribute(k_qp_warp<CC, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    k_qp_warp<CC, HV><<<blocks, 32 * Wl, smem, s->stream>>>(D, io, apply, pwd)
+    switch (C * 2 + (D.h_variant ? 1 : 0)) {
+        case 2: QW_LAUNCH(1, 0); break;
+        case 3: QW_LAUNCH(1, 1); break;
+        case 4: QW_LAUNCH(2, 0); break;
+        case 5: QW_LAUNCH(2, 1); break;
+        case 6: QW_LAUNCH(3, 0); break;
+        case 7: QW_LAUNCH(3, 1); break;
+        case 8: QW_LAUNCH(4, 0); break;
+        default: QW_LAUNCH(4, 1); break;
     }
 #undef QW_LAUNCH
     return QSPUSH_OK;
@@ -585,6 +611,7 @@ int qspush_solve(qspush_solver* s) {
     CK(cudaEventRecord(s->ev[0], s->stream));
     if (o.mode == QSPUSH_MODE_RTI) {
         SolverDev D = s->dev; D.done = nullptr;
+        apply_variant(s, D);
         k_linearise<<<lin_blocks, 128, smem, s->stream>>>(D);
         CK(cudaEventRecord(s->ev[1], s->stream));
         RET(launch_qp(s, D, io, ppw, 1));
@@ -597,6 +624,7 @@ int qspush_solve(qspush_solver* s) {
     // ---- full SQP (NMPC_controller.m:271-276): host-driven loop, per-problem convergence on the device
     SqpOpts so{o.max_sqp_iter, {o.tol_stat, o.tol_eq, o.tol_ineq, o.tol_comp}, o.globalization, o.alpha_min, o.alpha_reduction, o.eps_sufficient_descent};
     SolverDev D = s->dev;
+    apply_variant(s, D);
     CK(cudaMemsetAsync(D.done, 0, s->Bp * sizeof(int), s->stream));
     CK(cudaMemsetAsync(D.qp_iter, 0, s->Bp * sizeof(int), s->stream));
     CK(cudaMemsetAsync(D.ndone, 0, sizeof(int), s->stream));

@@ -24,7 +24,8 @@ def _blkdiag(a, b):
 
 
 class NMPC_controller:
-    def __init__(self, name, plant, sample_time, Hp, batch=1, device=0, nlp_solver="sqp", **solver_opts):
+    def __init__(self, name, plant, sample_time, Hp, batch=1, device=0, nlp_solver="sqp",
+                 velocity_constraint_in_ocp=False, **solver_opts):
         # NMPC_controller.m:16-26
         self.W_x = 0.01 * np.diag([100, 100, 0.1, 0])
         self.W_x_e = 200 * np.diag([1000, 1000, 0.1, 0])
@@ -33,6 +34,9 @@ class NMPC_controller:
         self.name = name
         self.batch, self.device = int(batch), int(device)
         self.nlp_solver = nlp_solver           # "sqp" (reference, :272) or "sqp_rti"
+        # True = the constraint set the authors parked in comments (:226-238, :247-248):
+        # h = [u_n; u_t - v_bound(s); u_t + v_bound(s)] instead of [s; u_n; u_t] (:237)
+        self.velocity_constraint_in_ocp = bool(velocity_constraint_in_ocp)
         self.solver_opts = solver_opts
         self.plants = list(plant) if isinstance(plant, (list, tuple)) else [plant]
         self.plant = self.plants[0]
@@ -76,8 +80,9 @@ class NMPC_controller:
             xk_sim = xk_sim + self.sample_time * x_dot_sim
         return xk_sim
 
-    # :122-142 (dead code path in the reference: the call in main.m:91 is commented out, and the sizes it
-    # passes, 4 values for nh = 3, are inconsistent; the same inconsistency raises here)
+    # :122-142 (dead code path in the reference: the call in main.m:91 is commented out; the bounds it sets,
+    # [u_n_lb, 2 u_t_lb, 0] / [u_n_ub, 0, 2 u_t_ub], are those of the parked constraint set
+    # h = [u_n; u_t -+ v_bound(s)], i.e. of velocity_constraint_in_ocp=True)
     def update_constraints(self, u_n_ub, u_t_ub, u_n_lb, u_t_lb):
         self.u_n_lb, self.u_n_ub, self.u_t_lb, self.u_t_ub = u_n_lb, u_n_ub, u_t_lb, u_t_ub
         self.h_constr_ub = [self.h_constr_ub[0], self.u_n_ub, self.u_t_ub]
@@ -128,9 +133,16 @@ class NMPC_controller:
         ocp_model.set("dyn_type", "explicit")
         ocp_model.set("dyn_expr_f", self.plants)          # the compiled dynamics travel with the plant(s)
         ocp_model.set("constr_type", "bgh")
-        ocp_model.set("constr_expr_h", ("s", "u_n", "u_t"))                    # :237
-        ocp_model.set("constr_lh", [-0.06, *self.h_constr_lb[1:]])              # :251
-        ocp_model.set("constr_uh", [0.011, *self.h_constr_ub[1:]])              # :252
+        if self.velocity_constraint_in_ocp:
+            ocp_model.set("constr_expr_h", ("u_n", "u_t-v_bound(s)", "u_t+v_bound(s)"))          # :238 (commented)
+            ocp_model.set("constr_lh", [*self.h_constr_lb[1:-1], 2 * self.u_t_lb, -0.0])       # :247
+            ocp_model.set("constr_uh", [*self.h_constr_ub[1:-1], 0.0, 2 * self.u_t_ub])        # :248
+            ocp_model.set("constr_v_bound", dict(v_alpha=self.v_alpha, d_v_bound=self.d_v_bound,
+                                                 t_angle0=self.t_angle0, u_t_ub=self.u_t_ub))  # :229
+        else:
+            ocp_model.set("constr_expr_h", ("s", "u_n", "u_t"))                    # :237
+            ocp_model.set("constr_lh", [-0.06, *self.h_constr_lb[1:]])              # :251
+            ocp_model.set("constr_uh", [0.011, *self.h_constr_ub[1:]])              # :252
         ocp_model.set("constr_x0", self.initial_condition)                     # :265
         return ocp_model
 
