@@ -320,7 +320,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ppw", type=int, default=0, help="QP kernel packing (problems per warp), 0 = auto")
     ap.add_argument("--qp-kernel", type=int, default=1, help="1 = warp per problem (parallel-in-time; what auto picks at 4096/GPU), 0 = one problem per thread")
-    ap.add_argument("--latency-solves", type=int, default=200, help="solves per B=1 latency measurement")
+    ap.add_argument("--latency-solves", type=int, default=1000, help="solves per B=1 latency measurement")
     ap.add_argument("--cpu-passes", type=int, default=3, help="passes of the oracle over the batch for cpu_baseline")
     args = ap.parse_args()
     if args.impl == "reference":

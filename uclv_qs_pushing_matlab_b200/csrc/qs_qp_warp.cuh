@@ -3,8 +3,9 @@
 // Same QP and the same Mehrotra predictor-corrector IPM in Newton-step form as qs_qp.cuh (true residuals
 // every iteration, centering floor, stall exit), but the horizon is spread over the 32 lanes of a warp:
 // lane l owns the C consecutive stages l*C .. l*C+C-1 (C = ceil((N+1)/32)); the whole IPM state of the
-// problem lives in shared memory (no HBM traffic inside the iteration loop) and every "sweep" of the
-// serial algorithm becomes either lane-local work or a warp scan built from shuffles:
+// problem lives on chip — shared memory records plus a lane-private block of tensor memory (no HBM traffic
+// inside the iteration loop) — and every "sweep" of the serial algorithm becomes either lane-local work or a
+// warp scan (operands exchanged through shared memory, reductions through shuffles):
 //
 //   * Riccati matrices P_k: suffix scan of conditional value functions V_{i->j}(x_i, x_j), each an element
 //     (A, C, J) with  V = max_lam 1/2 x'Jx - 1/2 lam'C lam + lam'(x_j - A x_i)  [vector parts omitted]
@@ -16,11 +17,14 @@
 //     over its own C stages: gains K_k, Cholesky factors, P_k;
 //   * the vector recursions p_k = Abar_k' p_{k+1} + d_k (backward) and dx_{k+1} = Abar_k dx_k + bbar_k
 //     (forward), Abar = A - B K, are suffix / prefix scans of affine maps — twice per iteration
-//     (predictor and corrector share the matrix scan);
+//     (predictor and corrector run through ONE copy of the solve code: instruction-cache footprint);
 //   * residual norms, step lengths and complementarity sums are warp reductions.
 //
-// The code is written against a tiny warp context (lane id, shfl, reductions) so that tests/hostsim can
-// run the identical source on the CPU with a fiber-based warp emulator.
+// Constraint rows: the default set h = [s; u_n; u_t] (selection rows) or, template flag HV = 1, the reference's
+// parked set h = [u_n; u_t - v_bound(s); u_t + v_bound(s)] whose rows couple ds and du_t (barrier cross term).
+//
+// The code is written against a tiny warp context (lane id, reductions, TMEM block, CTA vote) so that
+// tests/hostsim can run the identical source on the CPU with a fiber-based warp emulator.
 #pragma once
 #include "qs_qp.cuh"
 
@@ -394,7 +398,7 @@ QS_HD void qw_row_add(int hv, int c, double beta, double w, double* g6) {
 // One Newton solve with the current factorisation: rhs gt (R_GT rows) and r_b (R_RB) ->
 // step dz (R_GT rows, aliased), costate offsets p_k (R_PV), feed-forward k_ff (R_KFF).
 template <class Ctx, int C>
-QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, const double* __restrict__ QNp) {
+QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_) {
     const int lane = w.lane();
     const bool act = lane < Lw_;
     // ---- (a) local: d_k, kff0_k and the chunk's composed backward map  p_start = M p_end + d
@@ -580,7 +584,6 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
             for (int i = 0; i < 4; ++i) QW_SM(R_GT + 2 + i, j) = xk[i];
         }
     }
-    (void)QNp;
 }
 
 // Per-problem IPM state kept in registers across iterations (everything else lives in shared memory).
@@ -831,9 +834,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                     e.J[LT(i, q)] = Hk[LT(2 + i, 2 + q)] - fma(sh0[i], sh0[q], sh1[i] * sh1[q]);
                 }
             e.J[LT(3, 3)] += D[0];
-            if (k == 0) {
-                // x_0 is fixed (dx_0 = 0): only the reachable-set part matters; keep J finite and PSD
-            }
+            // (stage 0 needs no special case: dx_0 = 0 is imposed by the forward scan, the element of stage 0 only feeds lanes left of it)
             if (!E_is_identity) elem_combine(e, E.A, E.C, E.J);   // E <- e (x) E
             E = e;
             E_is_identity = false;
@@ -933,7 +934,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             }
         }
         QW_TICK(5);
-        qp_warp_solve<Ctx, C>(w, sm, N, Lw_, Q.QN);
+        qp_warp_solve<Ctx, C>(w, sm, N, Lw_);
         QW_TICK(6);
         if (pass == 0) {
             // step to the boundary of the affine step, mu_aff, centering parameter
