@@ -17,7 +17,7 @@ for tag, B, N, mode, mixed, seed in (("config4_share", 8192, 40, 0, False, 3), (
     wl = make_rti_workload(B, N, seed=seed, n_objects=4, mixed_modes=mixed)
     order = np.argsort(wl["object_id"], kind="stable")                    # contiguous per-object buckets per GPU
     wl = {k: v[order] for k, v in wl.items()}
-    s = q.Solver(gms, N, 0.05, B, mode=mode)
+    s = q.Solver(gms, N, 0.05, B, mode=mode, qp_kernel=int(sys.argv[1]) if len(sys.argv) > 1 else 2)
     d = {k: torch.from_numpy(np.ascontiguousarray(wl[k])).to(dev) for k in ("x0", "yref", "yref_e", "u_init")}
     oid = torch.from_numpy(wl["object_id"]).to(dev); cold = torch.zeros(B, dtype=torch.int32, device=dev)
     ts = []

@@ -24,13 +24,14 @@ __device__ __forceinline__ const double* stage_models(const double* __restrict__
     const uint32_t bytes = (uint32_t)nmodels * MODEL_DOUBLES * 8u;
     const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(mbar);
     const uint32_t dst_s = (uint32_t)__cvta_generic_to_shared(dst);
-    if (threadIdx.x == 0) {
+    const bool leader = (threadIdx.x | threadIdx.y | threadIdx.z) == 0;     // one thread of the CTA (2-D blocks: k_linesearch)
+    if (leader) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (leader) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(dst_s), "l"(gmodels), "r"(bytes), "r"(mbar_s) : "memory");
@@ -235,11 +236,30 @@ __global__ void __launch_bounds__(64) k_nlp_res(SolverDev S, SqpOpts o, int it) 
     if (nlp_res_one(S, o, it, b)) atomicAdd(S.ndone, 1);
 }
 
-__global__ void __launch_bounds__(64) k_linesearch(SolverDev S, SqpOpts o, int it) {
+// Line search: CTA = 32 problems (threadIdx.x, coalesced slab accesses) x LS_CHUNKS stage chunks (threadIdx.y): the
+// N ERK4 evaluations of every merit-function trial are spread over the chunk threads and summed through shared
+// memory, instead of one serial loop per problem (which was 59 % of a full-SQP solve at N = 100).
+constexpr int LS_CHUNKS = 8;
+struct ChunkCta {
+    int y, ny;
+    double* red;                                   // [ny][32]
+    __device__ __forceinline__ double sum(double v) const {
+        red[y * 32 + threadIdx.x] = v;
+        __syncthreads();
+        double t = 0.0;
+        for (int i = 0; i < ny; ++i) t += red[i * 32 + threadIdx.x];      // same order in every chunk thread: identical totals
+        __syncthreads();
+        return t;
+    }
+    __device__ __forceinline__ bool any(bool p) const { return __syncthreads_or(p ? 1 : 0) != 0; }
+};
+__global__ void __launch_bounds__(32 * LS_CHUNKS) k_linesearch(SolverDev S, SqpOpts o, int it) {
+    __shared__ double red[LS_CHUNKS * 32];
     const double* Mall = stage_models(S.models, S.nmodels);
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= S.B || S.done[b]) return;
-    if (linesearch_one(S, o, Mall, it, b)) atomicAdd(S.ndone, 1);
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    const bool live = b < S.B && !S.done[b];
+    ChunkCta ch{(int)threadIdx.y, LS_CHUNKS, red};
+    if (linesearch_one(S, o, Mall, it, live ? b : 0, ch, live)) atomicAdd(S.ndone, 1);
 }
 
 __global__ void k_cost(SolverDev S) {

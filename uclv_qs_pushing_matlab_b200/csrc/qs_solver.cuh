@@ -374,137 +374,173 @@ QS_HD int nlp_res_one(const SolverDev& S, const SqpOpts& o, int it, int b) {
     return 0;
 }
 
-QS_HD double merit_at(const SolverDev& S, const double* M, int b, double alpha) {
-    // L1 merit of the trial point w + alpha*dw (dw in S.z), SURVEY A2.5
+// Stage-chunk context of the line search: the horizon of one problem is split over `ny` cooperating threads
+// (chunk y handles stages y, y + ny, ...); sum() adds the chunks' partial results and hands the total to all of
+// them, any() is a vote over the whole thread group.  The serial version (one thread per problem: host simulation)
+// is ny = 1 with identity reductions; the kernel uses a CTA of 32 problems x 8 chunks (qs_kernels.cuh).
+struct ChunkSerial {
+    int y = 0, ny = 1;
+    QS_HD double sum(double v) const { return v; }
+    QS_HD bool any(bool p) const { return p; }
+};
+
+// L1 merit of the trial point w + alpha*dw (dw in S.z), SURVEY A2.5.  `active` = this problem still needs the value
+// (inactive threads only take part in the reduction).
+template <class Chunk>
+QS_HD double merit_at(const SolverDev& S, const double* M, int b, double alpha, const Chunk& ch, bool active) {
     const int N = S.N;
     double mval = 0.0;
-    double x[4];
+    if (active) {
+        if (ch.y == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        x[i] = fma(alpha, QS_EL(S.z, 2 + i, b), QS_EL(S.x, i, b));
-        mval += QS_EL(S.wx0, i, b) * fabs(QS_EL(S.x0, i, b) - x[i]);
-    }
-    for (int k = 0; k < N; ++k) {
-        const double un = fma(alpha, QS_EL(S.z, k * 6 + 0, b), QS_EL(S.u, k * 2 + 0, b));
-        const double ut = fma(alpha, QS_EL(S.z, k * 6 + 1, b), QS_EL(S.u, k * 2 + 1, b));
-        double xn[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) xn[i] = fma(alpha, QS_EL(S.z, (k + 1) * 6 + 2 + i, b), QS_EL(S.x, (k + 1) * 4 + i, b));
-        // stage cost
-        double r[6];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) r[i] = x[i] - QS_EL(S.yref, k * 6 + i, b);
-        r[4] = un - QS_EL(S.yref, k * 6 + 4, b); r[5] = ut - QS_EL(S.yref, k * 6 + 5, b);
-        const double* W = S.Wdt + (size_t)k * 36;
-        double q = 0.0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            double a = 0.0;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) a = fma(W[i + 6 * j], r[j], a);
-            q = fma(r[i], a, q);
+            for (int i = 0; i < 4; ++i) {
+                const double x0i = fma(alpha, QS_EL(S.z, 2 + i, b), QS_EL(S.x, i, b));
+                mval += QS_EL(S.wx0, i, b) * fabs(QS_EL(S.x0, i, b) - x0i);
+            }
         }
-        mval += 0.5 * q;
-        double Phi[4];
-        erk4_plain(M, x, un, ut, S.dt, Phi);
+        for (int k = ch.y; k < N; k += ch.ny) {
+            const double un = fma(alpha, QS_EL(S.z, k * 6 + 0, b), QS_EL(S.u, k * 2 + 0, b));
+            const double ut = fma(alpha, QS_EL(S.z, k * 6 + 1, b), QS_EL(S.u, k * 2 + 1, b));
+            double x[4], xn[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) mval += QS_EL(S.wpi, k * 4 + i, b) * fabs(Phi[i] - xn[i]);
-        double h[3];
-        h_eval(S, M, x[3], un, ut, h, nullptr);
+            for (int i = 0; i < 4; ++i) {
+                x[i] = fma(alpha, QS_EL(S.z, k * 6 + 2 + i, b), QS_EL(S.x, k * 4 + i, b));
+                xn[i] = fma(alpha, QS_EL(S.z, (k + 1) * 6 + 2 + i, b), QS_EL(S.x, (k + 1) * 4 + i, b));
+            }
+            // stage cost
+            double r[6];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            if (!h_on(S.h_variant, k, c)) continue;
-            mval += QS_EL(S.wlam, k * 6 + c, b) * fmax(0.0, S.lh[c] - h[c]);
-            mval += QS_EL(S.wlam, k * 6 + 3 + c, b) * fmax(0.0, h[c] - S.uh[c]);
+            for (int i = 0; i < 4; ++i) r[i] = x[i] - QS_EL(S.yref, k * 6 + i, b);
+            r[4] = un - QS_EL(S.yref, k * 6 + 4, b); r[5] = ut - QS_EL(S.yref, k * 6 + 5, b);
+            const double* W = S.Wdt + (size_t)k * 36;
+            double q = 0.0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                double a = 0.0;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) a = fma(W[i + 6 * j], r[j], a);
+                q = fma(r[i], a, q);
+            }
+            mval += 0.5 * q;
+            double Phi[4];
+            erk4_plain(M, x, un, ut, S.dt, Phi);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mval += QS_EL(S.wpi, k * 4 + i, b) * fabs(Phi[i] - xn[i]);
+            double h[3];
+            h_eval(S, M, x[3], un, ut, h, nullptr);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (!h_on(S.h_variant, k, c)) continue;
+                mval += QS_EL(S.wlam, k * 6 + c, b) * fmax(0.0, S.lh[c] - h[c]);
+                mval += QS_EL(S.wlam, k * 6 + 3 + c, b) * fmax(0.0, h[c] - S.uh[c]);
+            }
         }
+        if (ch.y == 0) {
+            double r[4], q = 0.0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) x[i] = xn[i];
+            for (int i = 0; i < 4; ++i) r[i] = fma(alpha, QS_EL(S.z, N * 6 + 2 + i, b), QS_EL(S.x, N * 4 + i, b)) - QS_EL(S.yref_e, i, b);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double a = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) a = fma(S.We[i + 4 * j], r[j], a);
+                q = fma(r[i], a, q);
+            }
+            mval += 0.5 * q;
+        }
     }
-    double r[4], q = 0.0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) r[i] = x[i] - QS_EL(S.yref_e, i, b);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        double a = 0.0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) a = fma(S.We[i + 4 * j], r[j], a);
-        q = fma(r[i], a, q);
-    }
-    return mval + 0.5 * q;
+    return ch.sum(mval);
 }
 
-// merit-function backtracking line search and iterate update of one SQP iteration;
-// returns 1 when problem b finishes (QP failure)
-QS_HD int linesearch_one(const SolverDev& S, const SqpOpts& o, const double* __restrict__ Mall, int it, int b) {
+// merit-function backtracking line search and iterate update of one SQP iteration, executed by
+// the `ch.ny` chunk threads of problem b together (every thread of the group calls it, `live` = problem b exists and
+// is not finished); returns 1 on chunk 0 when problem b finishes here (QP failure)
+template <class Chunk>
+QS_HD int linesearch_one(const SolverDev& S, const SqpOpts& o, const double* __restrict__ Mall, int it, int b, const Chunk& ch, bool live) {
     const int N = S.N;
-    if (S.qpstat[b] == 2) { S.status[b] = 4; S.done[b] = 1; S.sqp_iter[b] = it + 1; return 1; }
-    const double* M = Mall + (size_t)S.objid[b] * MODEL_DOUBLES;
+    int fin = 0;
+    if (live && S.qpstat[b] == 2) {
+        if (ch.y == 0) { S.status[b] = 4; S.done[b] = 1; S.sqp_iter[b] = it + 1; fin = 1; }
+        live = false;
+    }
+    const double* M = Mall + (size_t)(live ? S.objid[b] : 0) * MODEL_DOUBLES;
     double alpha = 1.0;
     if (o.globalization == 1) {
         // merit weights: |multipliers_qp| first, then max(|m|, (w + |m|)/2); directional derivative
         double dcost = 0.0, dinf = 0.0;
-        for (int k = 0; k < N; ++k) {
+        if (live) {
+            for (int k = ch.y; k < N; k += ch.ny) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double a = fabs(QS_EL(S.piq, k * 4 + i, b));
-                const double w = (it == 0) ? a : fmax(a, 0.5 * (QS_EL(S.wpi, k * 4 + i, b) + a));
-                QS_EL(S.wpi, k * 4 + i, b) = w;
-                dinf += w * fabs(QS_EL(S.b, k * 4 + i, b));
+                for (int i = 0; i < 4; ++i) {
+                    const double a = fabs(QS_EL(S.piq, k * 4 + i, b));
+                    const double w = (it == 0) ? a : fmax(a, 0.5 * (QS_EL(S.wpi, k * 4 + i, b) + a));
+                    QS_EL(S.wpi, k * 4 + i, b) = w;
+                    dinf += w * fabs(QS_EL(S.b, k * 4 + i, b));
+                }
+                const double h[3] = {QS_EL(S.hv, k * 4, b), QS_EL(S.hv, k * 4 + 1, b), QS_EL(S.hv, k * 4 + 2, b)};
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    const double a = fabs(QS_EL(S.lamq, k * 6 + c, b));
+                    const double w = (it == 0) ? a : fmax(a, 0.5 * (QS_EL(S.wlam, k * 6 + c, b) + a));
+                    QS_EL(S.wlam, k * 6 + c, b) = w;
+                    if (!h_on(S.h_variant, k, c % 3)) continue;
+                    const int cc = c % 3;
+                    dinf += w * (c < 3 ? fmax(0.0, S.lh[cc] - h[cc]) : fmax(0.0, h[cc] - S.uh[cc]));
+                }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) dcost = fma(QS_EL(S.g, k * 6 + i, b), QS_EL(S.z, k * 6 + i, b), dcost);
             }
-            const double h[3] = {QS_EL(S.hv, k * 4, b), QS_EL(S.hv, k * 4 + 1, b), QS_EL(S.hv, k * 4 + 2, b)};
+            if (ch.y == 0) {
 #pragma unroll
-            for (int c = 0; c < 6; ++c) {
-                const double a = fabs(QS_EL(S.lamq, k * 6 + c, b));
-                const double w = (it == 0) ? a : fmax(a, 0.5 * (QS_EL(S.wlam, k * 6 + c, b) + a));
-                QS_EL(S.wlam, k * 6 + c, b) = w;
-                if (!h_on(S.h_variant, k, c % 3)) continue;
-                const int cc = c % 3;
-                dinf += w * (c < 3 ? fmax(0.0, S.lh[cc] - h[cc]) : fmax(0.0, h[cc] - S.uh[cc]));
+                for (int i = 0; i < 4; ++i) dcost = fma(QS_EL(S.qN, i, b), QS_EL(S.z, N * 6 + 2 + i, b), dcost);
+                // multiplier of the x0 equality = stage-0 costate of the QP
+                double z0[6], m[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) z0[i] = QS_EL(S.z, i, b);
+                double pk1[4], a3[4], a4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { pk1[i] = QS_EL(S.piq, i, b); a3[i] = QS_EL(S.A, i, b); a4[i] = QS_EL(S.A, 4 + i, b); }
+#pragma unroll
+                for (int i = 2; i < 6; ++i) {
+                    double a = QS_EL(S.g, i, b);
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) a = fma(S.H[LT(i, j)], z0[j], a);
+                    m[i] = a;
+                }
+                m[2] += pk1[0]; m[3] += pk1[1]; m[4] += dot4(a3, pk1); m[5] += dot4(a4, pk1);
+                if (S.h_variant) {
+                    const double beta = QS_EL(S.hv, 3, b);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) m[5] += h_bcoef(1, c, beta) * (QS_EL(S.lamq, 3 + c, b) - QS_EL(S.lamq, c, b));
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double a = fabs(m[2 + i]);
+                    const double w = (it == 0) ? a : fmax(a, 0.5 * (QS_EL(S.wx0, i, b) + a));
+                    QS_EL(S.wx0, i, b) = w;
+                    dinf += w * fabs(QS_EL(S.dx0, i, b));
+                }
             }
-#pragma unroll
-            for (int i = 0; i < 6; ++i) dcost = fma(QS_EL(S.g, k * 6 + i, b), QS_EL(S.z, k * 6 + i, b), dcost);
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dcost = fma(QS_EL(S.qN, i, b), QS_EL(S.z, N * 6 + 2 + i, b), dcost);
-        {   // multiplier of the x0 equality = stage-0 costate of the QP
-            double z0[6], m[6];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) z0[i] = QS_EL(S.z, i, b);
-            double pk1[4], a3[4], a4[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { pk1[i] = QS_EL(S.piq, i, b); a3[i] = QS_EL(S.A, i, b); a4[i] = QS_EL(S.A, 4 + i, b); }
-#pragma unroll
-            for (int i = 2; i < 6; ++i) {
-                double a = QS_EL(S.g, i, b);
-#pragma unroll
-                for (int j = 0; j < 6; ++j) a = fma(S.H[LT(i, j)], z0[j], a);
-                m[i] = a;
-            }
-            m[2] += pk1[0]; m[3] += pk1[1]; m[4] += dot4(a3, pk1); m[5] += dot4(a4, pk1);
-            if (S.h_variant) {
-                const double beta = QS_EL(S.hv, 3, b);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) m[5] += h_bcoef(1, c, beta) * (QS_EL(S.lamq, 3 + c, b) - QS_EL(S.lamq, c, b));
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double a = fabs(m[2 + i]);
-                const double w = (it == 0) ? a : fmax(a, 0.5 * (QS_EL(S.wx0, i, b) + a));
-                QS_EL(S.wx0, i, b) = w;
-                dinf += w * fabs(QS_EL(S.dx0, i, b));
-            }
-        }
+        dcost = ch.sum(dcost); dinf = ch.sum(dinf);
         const double dmerit = dcost - dinf;
-        const double m0 = merit_at(S, M, b, 0.0);
+        const double m0 = merit_at(S, M, b, 0.0, ch, live);
+        bool searching = live;
         for (;;) {
-            const double m1 = merit_at(S, M, b, alpha);
-            if (m1 <= m0 + o.eps_sd * alpha * dmerit) break;
-            alpha *= o.alpha_red;
-            if (alpha < o.alpha_min) { alpha = o.alpha_min; break; }
+            const double m1 = merit_at(S, M, b, alpha, ch, searching);
+            if (searching) {
+                if (m1 <= m0 + o.eps_sd * alpha * dmerit) searching = false;
+                else {
+                    alpha *= o.alpha_red;
+                    if (alpha < o.alpha_min) { alpha = o.alpha_min; searching = false; }
+                }
+            }
+            if (!ch.any(searching)) break;
         }
     }
+    if (!live) return fin;
     // update: w += alpha dw ; pi <- (1-alpha) pi + alpha pi_qp ; lam likewise
-    for (int k = 0; k < N; ++k) {
+    for (int k = ch.y; k < N; k += ch.ny) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) QS_EL(S.u, k * 2 + i, b) = fma(alpha, QS_EL(S.z, k * 6 + i, b), QS_EL(S.u, k * 2 + i, b));
 #pragma unroll
@@ -519,10 +555,12 @@ QS_HD int linesearch_one(const SolverDev& S, const SqpOpts& o, const double* __r
             QS_EL(S.lam, k * 6 + i, b) = (1.0 - alpha) * lo + alpha * QS_EL(S.lamq, k * 6 + i, b);
         }
     }
+    if (ch.y == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) QS_EL(S.x, N * 4 + i, b) = fma(alpha, QS_EL(S.z, N * 6 + 2 + i, b), QS_EL(S.x, N * 4 + i, b));
-    S.alpha[b] = alpha;
-    return 0;
+        for (int i = 0; i < 4; ++i) QS_EL(S.x, N * 4 + i, b) = fma(alpha, QS_EL(S.z, N * 6 + 2 + i, b), QS_EL(S.x, N * 4 + i, b));
+        S.alpha[b] = alpha;
+    }
+    return fin;
 }
 
 QS_HD void cost_one(const SolverDev& S, int b) {

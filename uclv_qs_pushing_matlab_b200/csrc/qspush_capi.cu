@@ -550,7 +550,9 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
     // kernel to fill the GPU.  Measured crossovers on B200: N = 40: ~50k problems (2.2M it/s flat
     // from 8k on vs 0.4M -> 2.3M it/s); N = 10 and N = 100: between 4k and 32k
     const int warp_below = (C == 2) ? 49152 : 16384;
-    const bool want_warp = s->opts.qp_kernel == 1 || (s->opts.qp_kernel == 2 && (s->B < warp_below || D.h_variant));
+    // full SQP (apply == 0): always the warp kernel — its work queue skips the problems that already finished, while
+    // the thread kernel keeps mostly idle warps alive (config 5 share, 32 768 x N = 100: 0.87 s vs 2.3 s)
+    const bool want_warp = s->opts.qp_kernel == 1 || (s->opts.qp_kernel == 2 && (s->B < warp_below || D.h_variant || !apply));
     // resident problems (= warps) per CTA: bounded by shared memory (one CTA per SM), by the register file
     // (8 warps of 255 registers) and by TMEM (8 blocks of 32 lanes x 256 columns)
     const int pwd = (int)((qp_warp_smem_doubles(s->N) + 1) / 2 * 2);
@@ -637,7 +639,7 @@ int qspush_solve(qspush_solver* s) {
         CK(cudaStreamSynchronize(s->stream));
         if (*s->h_ndone >= s->B || it == o.max_sqp_iter) break;
         RET(launch_qp(s, D, io, ppw, 0));
-        k_linesearch<<<pb, 64, smem, s->stream>>>(D, so, it);
+        k_linesearch<<<(unsigned)((s->B + 31) / 32), dim3(32, LS_CHUNKS), smem, s->stream>>>(D, so, it);
         s->launches += 2;
     }
     CK(cudaEventRecord(s->ev[1], s->stream));
