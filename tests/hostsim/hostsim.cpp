@@ -317,7 +317,7 @@ int hs_solve(void* const* models, int nmodels, int N, double dt, int nb, const i
         for (int it = 0; it <= so.max_iter; ++it) {
             linearise_all();
             int nd = 0;
-            for (int b = 0; b < nb; ++b) { if (!S.done[b]) nlp_res_one(S, so, it, b); nd += S.done[b]; }
+            for (int b = 0; b < nb; ++b) { if (!S.done[b]) nlp_res_one(S, so, it, b, ChunkSerial(), true); nd += S.done[b]; }
             if (nd >= nb || it == so.max_iter) break;
             for (int b = 0; b < nb; ++b) if (!S.done[b]) { if (opts_i[7] && qp_warp_chunk(N) <= 4) qp_warp_host(S, io, b, 0); else qp_one(S, io, b, 0); }
             for (int b = 0; b < nb; ++b) if (!S.done[b]) linesearch_one(S, so, Mall, it, b, ChunkSerial(), true);

@@ -230,13 +230,8 @@ __global__ void __launch_bounds__(32 * QW_MAX_WARPS, 1) k_qp_warp(SolverDev S, I
     if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tbase) : "memory");
 }
 
-__global__ void __launch_bounds__(64) k_nlp_res(SolverDev S, SqpOpts o, int it) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= S.B || S.done[b]) return;
-    if (nlp_res_one(S, o, it, b)) atomicAdd(S.ndone, 1);
-}
-
-// Line search: CTA = 32 problems (threadIdx.x, coalesced slab accesses) x LS_CHUNKS stage chunks (threadIdx.y): the
+// SQP-level kernels: CTA = 32 problems (threadIdx.x, coalesced slab accesses) x LS_CHUNKS stage chunks (threadIdx.y).
+// Line search: the
 // N ERK4 evaluations of every merit-function trial are spread over the chunk threads and summed through shared
 // memory, instead of one serial loop per problem (which was 59 % of a full-SQP solve at N = 100).
 constexpr int LS_CHUNKS = 8;
@@ -251,8 +246,24 @@ struct ChunkCta {
         __syncthreads();
         return t;
     }
+    __device__ __forceinline__ double max(double v) const {
+        red[y * 32 + threadIdx.x] = v;
+        __syncthreads();
+        double t = red[threadIdx.x];
+        for (int i = 1; i < ny; ++i) t = fmax(t, red[i * 32 + threadIdx.x]);
+        __syncthreads();
+        return t;
+    }
     __device__ __forceinline__ bool any(bool p) const { return __syncthreads_or(p ? 1 : 0) != 0; }
 };
+// NLP residuals + convergence test: same CTA shape (the serial per-problem loop was 7 % of a full-SQP solve)
+__global__ void __launch_bounds__(32 * LS_CHUNKS) k_nlp_res(SolverDev S, SqpOpts o, int it) {
+    __shared__ double red[LS_CHUNKS * 32];
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    const bool live = b < S.B && !S.done[b];
+    ChunkCta ch{(int)threadIdx.y, LS_CHUNKS, red};
+    if (nlp_res_one(S, o, it, live ? b : 0, ch, live)) atomicAdd(S.ndone, 1);
+}
 __global__ void __launch_bounds__(32 * LS_CHUNKS) k_linesearch(SolverDev S, SqpOpts o, int it) {
     __shared__ double red[LS_CHUNKS * 32];
     const double* Mall = stage_models(S.models, S.nmodels);

@@ -325,12 +325,27 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm, const Solve
 }
 
 // NLP residuals (inf-norms) and the convergence test of one SQP iteration; returns 1 when problem b finishes
-QS_HD int nlp_res_one(const SolverDev& S, const SqpOpts& o, int it, int b) {
+// Stage-chunk context of the SQP-level kernels (residuals, line search): the horizon of one problem is split over
+// `ny` cooperating threads (chunk y handles stages y, y + ny, ...); sum() / max() combine the chunks' partial results
+// and hand the total to all of them, any() is a vote over the whole thread group.  The serial version (one thread
+// per problem: host simulation) is ny = 1 with identity reductions; the kernels use a CTA of 32 problems x 8 chunks
+// (qs_kernels.cuh).
+struct ChunkSerial {
+    int y = 0, ny = 1;
+    QS_HD double sum(double v) const { return v; }
+    QS_HD double max(double v) const { return v; }
+    QS_HD bool any(bool p) const { return p; }
+};
+
+template <class Chunk>
+QS_HD int nlp_res_one(const SolverDev& S, const SqpOpts& o, int it, int b, const Chunk& ch, bool live) {
     const int N = S.N;
     double r_stat = 0.0, r_eq = 0.0, r_in = 0.0, r_cp = 0.0;
+    if (live && ch.y == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) r_eq = fmax(r_eq, fabs(QS_EL(S.dx0, i, b)));
-    for (int k = 0; k < N; ++k) {
+        for (int i = 0; i < 4; ++i) r_eq = fmax(r_eq, fabs(QS_EL(S.dx0, i, b)));
+    }
+    for (int k = live ? ch.y : N; k < N; k += ch.ny) {
         double g[6], pk1[4];
 #pragma unroll
         for (int i = 0; i < 6; ++i) g[i] = QS_EL(S.g, k * 6 + i, b);
@@ -362,10 +377,16 @@ QS_HD int nlp_res_one(const SolverDev& S, const SqpOpts& o, int it, int b) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) r_eq = fmax(r_eq, fabs(QS_EL(S.b, k * 4 + i, b)));
     }
+    if (live && ch.y == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) r_stat = fmax(r_stat, fabs(QS_EL(S.qN, i, b) - QS_EL(S.pi, (N - 1) * 4 + i, b)));
+        for (int i = 0; i < 4; ++i) r_stat = fmax(r_stat, fabs(QS_EL(S.qN, i, b) - QS_EL(S.pi, (N - 1) * 4 + i, b)));
+    }
+    // NaN must survive the reductions (fmax drops it): carry it as +inf markers
+    const bool nan_p = !(r_stat == r_stat) || !(r_eq == r_eq) || !(r_in == r_in) || !(r_cp == r_cp);
+    r_stat = ch.max(r_stat); r_eq = ch.max(r_eq); r_in = ch.max(r_in); r_cp = ch.max(r_cp);
+    const bool nan = ch.max(nan_p ? 1.0 : 0.0) != 0.0;
+    if (!live || ch.y != 0) return 0;
     QS_EL(S.res, 0, b) = r_stat; QS_EL(S.res, 1, b) = r_eq; QS_EL(S.res, 2, b) = r_in; QS_EL(S.res, 3, b) = r_cp;
-    const bool nan = !(r_stat == r_stat) || !(r_eq == r_eq) || !(r_in == r_in) || !(r_cp == r_cp);
     int fin = -1;
     if (nan) fin = 1;
     else if (r_stat < o.tol[0] && r_eq < o.tol[1] && r_in < o.tol[2] && r_cp < o.tol[3]) fin = 0;
@@ -373,16 +394,6 @@ QS_HD int nlp_res_one(const SolverDev& S, const SqpOpts& o, int it, int b) {
     if (fin >= 0) { S.status[b] = fin; S.done[b] = 1; S.sqp_iter[b] = it; return 1; }
     return 0;
 }
-
-// Stage-chunk context of the line search: the horizon of one problem is split over `ny` cooperating threads
-// (chunk y handles stages y, y + ny, ...); sum() adds the chunks' partial results and hands the total to all of
-// them, any() is a vote over the whole thread group.  The serial version (one thread per problem: host simulation)
-// is ny = 1 with identity reductions; the kernel uses a CTA of 32 problems x 8 chunks (qs_kernels.cuh).
-struct ChunkSerial {
-    int y = 0, ny = 1;
-    QS_HD double sum(double v) const { return v; }
-    QS_HD bool any(bool p) const { return p; }
-};
 
 // L1 merit of the trial point w + alpha*dw (dw in S.z), SURVEY A2.5.  `active` = this problem still needs the value
 // (inactive threads only take part in the reduction).

@@ -630,10 +630,9 @@ int qspush_solve(qspush_solver* s) {
     CK(cudaMemsetAsync(D.done, 0, s->Bp * sizeof(int), s->stream));
     CK(cudaMemsetAsync(D.qp_iter, 0, s->Bp * sizeof(int), s->stream));
     CK(cudaMemsetAsync(D.ndone, 0, sizeof(int), s->stream));
-    const unsigned pb = (unsigned)((s->B + 63) / 64);
     for (int it = 0; it <= o.max_sqp_iter; ++it) {
         k_linearise<<<lin_blocks, 128, smem, s->stream>>>(D);
-        k_nlp_res<<<pb, 64, 0, s->stream>>>(D, so, it);
+        k_nlp_res<<<(unsigned)((s->B + 31) / 32), dim3(32, LS_CHUNKS), 0, s->stream>>>(D, so, it);
         s->launches += 2;
         CK(cudaMemcpyAsync(s->h_ndone, D.ndone, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
