@@ -104,7 +104,17 @@ QS_HD double matlab_mod(double s, double b, bool single) {
 }
 
 // fmod(s,b) + (s<0)*b   (PusherSliderModel.m:526; CasADi mod == C fmod)
-QS_HD double wrap_dyn(double s, double b) { return fmod(s, b) + ((s < 0.0) ? b : 0.0); }
+// fmod is exact, and for |s| < 2b it equals s or s -+ b — a subtraction that is itself exact (Sterbenz), so the fast
+// path returns bit-identical values while skipping the iterative library routine (every contact coordinate the
+// solver meets lies in (-b, 2b)); NaN and larger arguments take the library path.
+QS_HD double wrap_dyn(double s, double b) {
+    const double a = fabs(s);
+    double r;
+    if (a < b) r = s;
+    else if (a < 2.0 * b) r = (s > 0.0) ? s - b : s + b;
+    else r = fmod(s, b);
+    return r + ((s < 0.0) ? b : 0.0);
+}
 
 // gradient(atan2(C'_y, C'_x), s)  (bspline_shape.m:137-144) at sigma.
 QS_HD double angle_rate(const double* __restrict__ M, double sg) {

@@ -77,9 +77,10 @@ QS_HD void prepare_one(const SolverDev& S, const CtrlDev& cp, const double* __re
         S.cold[b] = 0;
     }
     double vb = v_bound_of(M, x[3], cp.v_alpha, cp.d_v_bound, cp.t_angle0, cp.u_t_ub, cp.single != 0, nullptr);   // :357
+    double un_nx = cold ? cp.u_n_lb : QS_EL(S.u, 0, b), ut_nx = cold ? 0.0 : QS_EL(S.u, 1, b);
     for (int k = 0; k < N; ++k) {
-        double un = cold ? cp.u_n_lb : QS_EL(S.u, k * 2 + 0, b);
-        double ut = cold ? 0.0 : QS_EL(S.u, k * 2 + 1, b);
+        double un = un_nx, ut = ut_nx;
+        if (!cold && k + 1 < N) { un_nx = QS_EL(S.u, (k + 1) * 2 + 0, b); ut_nx = QS_EL(S.u, (k + 1) * 2 + 1, b); }   // next stage's loads fly during this stage's arithmetic
         if (fabs(ut) > vb) {                                     // :358-364, :375-379
             const double old = ut;
             ut = (double)((old > 0.0) - (old < 0.0)) * vb;
