@@ -259,7 +259,7 @@ def run_ours(args):
     fp64_ach_tf = B * alg_flops_per_iter(k_ipm) / (qp_avg_ms * 1e-3 + sum(lin_ms) / len(lin_ms) * 1e-3) / 1e12
     # per-solve latency of a single NMPC instance (the MEX drop-in case): host buffers through the C-ABI, wall clock
     lat_b1 = {}
-    for tag, n1, mode in (("rti_N40", HORIZON, 0), ("rti_N10", 10, 0), ("sqp_N10", 10, 1)):
+    for tag, n1, mode in ((("rti_N40", HORIZON, 0), ("rti_N10", 10, 0), ("sqp_N10", 10, 1)) if world == 1 else ()):   # N = 1 runs only
         w1 = make_rti_workload(1, n1, dt=DT, seed=7)
         s1 = q.Solver([gm], n1, DT, 1, device=local_rank, qp_tol=QP_TOL, mode=mode)
         u1 = np.zeros((1, 2)); c1 = np.zeros(1, dtype=np.int32)
@@ -275,8 +275,11 @@ def run_ours(args):
                        "sqp_iter": int(s1.get_int("sqp_iter")[0])}
         del s1
     cores = os.cpu_count() or 1
-    cpu_t = cpu_oracle_rate(args.cpu_passes, cores)
-    cpu_rate = BATCH_PER_GPU * len(cpu_t) / sum(cpu_t)
+    cpu_base = None
+    if world == 1:                                           # the CPU baseline is timed on rank 0 of the N = 1 run only
+        cpu_t = cpu_oracle_rate(args.cpu_passes, cores)
+        cpu_base = {"value": BATCH_PER_GPU * len(cpu_t) / sum(cpu_t), "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{len(cpu_t)} pass(es) over the {BATCH_PER_GPU}-instance config-3 batch, restated oracle (not acados), {cores} threads"}
     srt = sorted(step_ms)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -298,8 +301,7 @@ def run_ours(args):
                                       "sm__pipe_fp64_cycles_active of the executed parallel-in-time algorithm (profiles/r01_v3_qp_ncu_summary.md)"},
                      "note": "the path is FP64-pipe / dependent-chain bound, not HBM bound (SURVEY 8d): the HBM fraction is reported "
                              "because the schema asks for it, the fp64 object is the relevant roofline (see DESIGN.md)"},
-        "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{len(cpu_t)} pass(es) over the {BATCH_PER_GPU}-instance config-3 batch, restated oracle (not acados), {cores} threads"},
+        "cpu_baseline": cpu_base,
         "k_ipm_mean": k_ipm, "k_ipm_max": int(it.max()), "status_ok_frac": float((st == 0).mean()),
         "phase_ms": {"prepare": sum(prep_ms) / len(prep_ms), "linearise": sum(lin_ms) / len(lin_ms), "qp": qp_avg_ms},
         "latency_ms": {"p50": srt[len(srt) // 2], "p99": srt[min(len(srt) - 1, int(0.99 * len(srt)))], "max": srt[-1],
