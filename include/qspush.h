@@ -166,6 +166,28 @@ int qspush_solve(qspush_solver* s);
 int qspush_shift(qspush_solver* s);
 /* one forward-Euler plant step x <- x + dt*f(x,u) on caller arrays [batch][4], [batch][2] (helper.m:294,307) */
 int qspush_plant_step(qspush_solver* s, double* x, const double* u, qspush_mem mem);
+/* Device-resident closed loop = helper.closed_loop_matlab (helper.m:219-313) for the whole batch, without host
+ * round trips: per control period i = 1..steps
+ *     disturbance (helper.m:221-236, optional) and state noise (:240-242, optional) on the plant state,
+ *     constr_x0 <- state, reference window of period idx0 + i - 1 (NMPC_controller.m:307-313, 343-348),
+ *     qspush_prepare, qspush_solve, u = get('u', 0) (:403), Euler plant step (helper.m:294, 307), qspush_shift.
+ * In RTI mode nothing synchronises with the host until the final copy-out.  Plant / controller input delays
+ * (helper.m:205-212, NMPC_controller.m:106-120) are not part of this entry point (host mirror only).
+ *   traj  [T][6]       reference columns [x_ref(4); u_ref(2)] shared by all problems
+ *   offset[batch][6]   added to every column per problem (NULL: none)
+ *   x     [batch][4]   plant state, in: initial, out: after `steps` periods
+ *   log_x [steps][batch][4] state handed to the controller, log_u [steps][batch][2], log_status [steps][batch] (each may be NULL)
+ * All arrays live in `mem`. */
+typedef struct {
+    int    idx0;                 /* reference index of the first period (1-based; helper.m: i = 1)            */
+    double noise_sigma[4];       /* helper.m:241 uses 1e-5, 1e-5, 1e-3, 1e-4; all zero = no noise             */
+    unsigned long long seed;     /* counter-based generator: same seed, same noise                            */
+    int    t_dist;               /* period of the lateral shove (1-based), 0 = none       helper.m:222        */
+    double amplitude_dist;       /* helper.m:224                                                               */
+    double xwidth;               /* slider_params.xwidth: contact target of the re-projection  helper.m:228   */
+} qspush_loop_opts;
+int qspush_closed_loop(qspush_solver* s, const double* traj, int T, const double* offset, double* x, int steps,
+                       const qspush_loop_opts* lo, double* log_x, double* log_u, int* log_status, qspush_mem mem);
 /* wait for everything queued on the solver's stream */
 int qspush_sync(qspush_solver* s);
 /* the solver's cudaStream_t (as void*) so callers can order their own work / events on it */

@@ -25,6 +25,10 @@ for N, B, mode in ((40, 5, "rti"), (70, 3, "rti"), (100, 2, "rti"), (10, 4, "sqp
     r = hs.solve(mhs, N, 0.05, wl["x0"], wl["yref"], wl["yref_e"], np.zeros((B, N + 1, 4)), wl["u_init"], objid=wl["object_id"],
                  mode=mode, prepare=True, shift=True, qp_kernel=1, max_sqp_iter=3, h_variant=1, lh=(0.0, -0.1, 0.0), uh=(0.03, 0.0, 0.1))
     assert np.isfinite(r["u"]).all()
+T = 60; traj = np.zeros((T, 6)); traj[:, 0] = 0.0005 * np.arange(T)                      # device-resident closed loop bodies
+r = hs.closed_loop(mhs, 10, 0.05, traj, np.zeros((5, 4)), 8, offset=np.zeros((5, 6)), objid=np.arange(5) % 4,
+                   t_dist=3, amplitude_dist=0.003, xwidth=0.068, noise_sigma=(1e-5, 1e-5, 1e-3, 1e-4), seed=3)
+assert np.isfinite(r["x"]).all()
 x = np.random.default_rng(0).uniform(-0.7, 0.7, (500, 4)); u = np.random.default_rng(1).uniform(-0.05, 0.05, (500, 2))
 mhs[3].eval_spline(x[:, 3], wrap=2); mhs[3].dynamics(x, u); mhs[3].erk4_sens(x, u, 0.05); mhs[3].v_bound(x[:, 3])
 print("ASAN-DRIVER-OK")

@@ -255,85 +255,140 @@ void hs_eval_vbound(void* m_, int cnt, const double* s, const double* ctrl5, int
 //             pi [nb][N][4], lam [nb][N][6], cold [nb]
 // outputs : stats_i [nb][3] (status, sqp_iter, qp_iter), stats_d [nb][6] (cost, res[4], alpha),
 //           step_z [nb][N+1][6] (QP solution du,dx), qp_pi [nb][N][4], qp_lam [nb][N][6], lin_* optional (A [nb][N][8] ...)
+struct HostRun {
+    int nb, Bp, N;
+    std::vector<double> blobs;
+    SolverDev S;
+    std::vector<int> v_obj, v_status, v_sqp, v_qpit, v_cold, v_done, v_qpstat, v_ndone;
+    std::vector<double> sx, su, spi, slam, sx0, syr, sye, sA, sB, sb, sg, sqN, sdx0, shv, sz, szp, szc, slq, st, sK, sLi, sPb, skf, spq,
+        srg, srb, srgs, scost, sres, salpha, swpi, swlam, swx0, Wdt, H, QN, Wev;
+    IpmOpts io; SqpOpts so; CtrlDev cp;
+    int mode, use_warp, single;
+    std::string err;
+
+    HostRun(void* const* models, int nmodels, int N_, double dt, int nb_, const int* objid, const double* W, const double* We,
+            const double* lh, const double* uh, const double* opts_d, const int* opts_i, const double* ctrl5, const int* cold)
+        : nb(nb_), Bp((nb_ + 31) / 32 * 32), N(N_) {
+        blobs.resize((size_t)nmodels * MODEL_DOUBLES);
+        for (int i = 0; i < nmodels; ++i) std::memcpy(&blobs[(size_t)i * MODEL_DOUBLES], ((HostModel*)models[i])->blob.data(), MODEL_DOUBLES * 8);
+        std::memset(&S, 0, sizeof S);
+        S.B = nb; S.Bp = Bp; S.N = N; S.nmodels = nmodels; S.dt = dt; S.models = blobs.data();
+        v_obj.assign(Bp, 0); v_status.assign(Bp, 0); v_sqp.assign(Bp, 0); v_qpit.assign(Bp, 0); v_cold.assign(Bp, 0); v_done.assign(Bp, 0);
+        v_qpstat.assign(Bp, 0); v_ndone.assign(32, 0);
+        for (int b = 0; b < nb; ++b) { v_obj[b] = objid ? objid[b] : 0; v_cold[b] = cold ? cold[b] : 0; }
+        S.objid = v_obj.data(); S.status = v_status.data(); S.sqp_iter = v_sqp.data(); S.qp_iter = v_qpit.data();
+        S.cold = v_cold.data(); S.done = v_done.data(); S.qpstat = v_qpstat.data(); S.ndone = v_ndone.data();
+        auto slab = [&](std::vector<double>& v, size_t rows) { v.assign(rows * Bp, 0.0); return v.data(); };
+        S.x = slab(sx, (N + 1) * 4); S.u = slab(su, N * 2); S.pi = slab(spi, N * 4); S.lam = slab(slam, N * 6);
+        S.x0 = slab(sx0, 4); S.yref = slab(syr, N * 6); S.yref_e = slab(sye, 4);
+        S.A = slab(sA, N * 8); S.Bm = slab(sB, N * 8); S.b = slab(sb, N * 4); S.g = slab(sg, N * 6); S.qN = slab(sqN, 4); S.dx0 = slab(sdx0, 4);
+        S.hv = slab(shv, N * 4);
+        S.z = slab(sz, (N + 1) * 6); S.zp = slab(szp, (N + 1) * 6); S.zc = slab(szc, N * 3); S.lamq = slab(slq, N * 6); S.t = slab(st, N * 6);
+        S.K = slab(sK, N * 8); S.Li = slab(sLi, N * 3); S.Pb = slab(sPb, N * 4); S.kff = slab(skf, N * 2); S.piq = slab(spq, N * 4);
+        S.rg = slab(srg, (N + 1) * 6); S.rb = slab(srb, N * 4); S.rgs = slab(srgs, N);
+        S.cost = slab(scost, 1); S.res = slab(sres, 4); S.alpha = slab(salpha, 1);
+        S.wpi = slab(swpi, N * 4); S.wlam = slab(swlam, N * 6); S.wx0 = slab(swx0, 4);
+        // cost constants exactly like flush_cost() in qspush_capi.cu
+        Wdt.resize((size_t)N * 36); H.resize((size_t)N * 21); QN.resize(10); Wev.assign(We, We + 16);
+        auto perm = [](int zi) { return zi < 2 ? 4 + zi : zi - 2; };
+        for (int k = 0; k < N; ++k) {
+            for (int i = 0; i < 36; ++i) Wdt[(size_t)k * 36 + i] = dt * W[(size_t)k * 36 + i];
+            for (int i = 0; i < 6; ++i) for (int j = 0; j <= i; ++j)
+                H[(size_t)k * 21 + LT(i, j)] = dt * 0.5 * (W[(size_t)k * 36 + perm(i) + 6 * perm(j)] + W[(size_t)k * 36 + perm(j) + 6 * perm(i)]);
+        }
+        for (int i = 0; i < 4; ++i) for (int j = 0; j <= i; ++j) QN[LT(i, j)] = 0.5 * (We[i + 4 * j] + We[j + 4 * i]);
+        S.Wdt = Wdt.data(); S.We = Wev.data(); S.H = H.data(); S.QN = QN.data();
+        for (int i = 0; i < 3; ++i) { S.lh[i] = lh[i]; S.uh[i] = uh[i]; }
+        S.h_variant = opts_i[8];                                     // like apply_variant() in qspush_capi.cu
+        for (int i = 0; i < 4; ++i) S.vbp[i] = ctrl5[i];
+        mode = opts_i[0];
+        io = IpmOpts{opts_i[1], opts_d[0], opts_d[1], opts_d[2], opts_d[3]};
+        so = SqpOpts{opts_i[2], {opts_d[4], opts_d[5], opts_d[6], opts_d[7]}, opts_i[3], opts_d[8], opts_d[9], opts_d[10]};
+        cp = CtrlDev{ctrl5[0], ctrl5[1], ctrl5[2], ctrl5[3], ctrl5[4], opts_i[4]};
+        single = opts_i[4];
+        use_warp = opts_i[7] && qp_warp_chunk(N) <= 4;
+        if (S.h_variant && !use_warp) err = "h_variant 1 needs the warp QP kernel";
+    }
+    // AoS <-> SoA (k_aos_to_soa / k_soa_to_aos)
+    void in(const double* src, std::vector<double>& dst, int R) { for (int b = 0; b < nb; ++b) for (int r = 0; r < R; ++r) dst[(size_t)r * Bp + b] = src[(size_t)b * R + r]; }
+    void out(const std::vector<double>& src, double* dst, int R) const { if (!dst) return; for (int b = 0; b < nb; ++b) for (int r = 0; r < R; ++r) dst[(size_t)b * R + r] = src[(size_t)r * Bp + b]; }
+    const double* Mall() const { return blobs.data(); }
+    void prepare() { for (int b = 0; b < nb; ++b) prepare_one(S, cp, Mall(), b); }
+    void qp(int b, int apply) { if (use_warp) qp_warp_host(S, io, b, apply); else qp_one(S, io, b, apply); }
+    void linearise_all() { for (int k = 0; k <= N; ++k) for (int b = 0; b < nb; ++b) if (!S.done[b]) linearise_one(S, Mall(), k, b); }
+    void solve() {                                                // qspush_solve
+        if (mode == 0 || mode == 2) {
+            linearise_all();
+            for (int b = 0; b < nb; ++b) qp(b, mode == 0 ? 1 : 0);
+        } else {
+            std::fill(v_done.begin(), v_done.end(), 0); std::fill(v_qpit.begin(), v_qpit.end(), 0);
+            for (int it = 0; it <= so.max_iter; ++it) {
+                linearise_all();
+                int nd = 0;
+                for (int b = 0; b < nb; ++b) { if (!S.done[b]) nlp_res_one(S, so, it, b, ChunkSerial(), true); nd += S.done[b]; }
+                if (nd >= nb || it == so.max_iter) break;
+                for (int b = 0; b < nb; ++b) if (!S.done[b]) qp(b, 0);
+                for (int b = 0; b < nb; ++b) if (!S.done[b]) linesearch_one(S, so, Mall(), it, b, ChunkSerial(), true);
+            }
+            for (int b = 0; b < nb; ++b) cost_one(S, b);
+        }
+    }
+    void shift() { for (int b = 0; b < nb; ++b) for (int c = 0; c < 16; ++c) shift_one(S, c, b); }
+};
+
 int hs_solve(void* const* models, int nmodels, int N, double dt, int nb, const int* objid,
              const double* W, const double* We, const double* lh, const double* uh,
              const double* opts_d, const int* opts_i, const double* ctrl5,
              double* x0, const double* yref, const double* yref_e, double* x, double* u, double* pi, double* lam, int* cold,
              int* stats_i, double* stats_d, double* step_z, double* qp_pi, double* qp_lam,
              double* lin_A, double* lin_B, double* lin_b, double* lin_g) {
-    const int Bp = (nb + 31) / 32 * 32;
-    std::vector<double> blobs((size_t)nmodels * MODEL_DOUBLES);
-    for (int i = 0; i < nmodels; ++i) std::memcpy(&blobs[(size_t)i * MODEL_DOUBLES], ((HostModel*)models[i])->blob.data(), MODEL_DOUBLES * 8);
-    SolverDev S; std::memset(&S, 0, sizeof S);
-    S.B = nb; S.Bp = Bp; S.N = N; S.nmodels = nmodels; S.dt = dt; S.models = blobs.data();
-    std::vector<int> v_obj(Bp, 0), v_status(Bp, 0), v_sqp(Bp, 0), v_qpit(Bp, 0), v_cold(Bp, 0), v_done(Bp, 0), v_qpstat(Bp, 0), v_ndone(32, 0);
-    for (int b = 0; b < nb; ++b) { v_obj[b] = objid ? objid[b] : 0; v_cold[b] = cold ? cold[b] : 0; }
-    S.objid = v_obj.data(); S.status = v_status.data(); S.sqp_iter = v_sqp.data(); S.qp_iter = v_qpit.data();
-    S.cold = v_cold.data(); S.done = v_done.data(); S.qpstat = v_qpstat.data(); S.ndone = v_ndone.data();
-    auto slab = [&](size_t rows) { return std::vector<double>(rows * Bp, 0.0); };
-    auto sx = slab((N + 1) * 4), su = slab(N * 2), spi = slab(N * 4), slam = slab(N * 6), sx0 = slab(4), syr = slab(N * 6), sye = slab(4);
-    auto sA = slab(N * 8), sB = slab(N * 8), sb = slab(N * 4), sg = slab(N * 6), sqN = slab(4), sdx0 = slab(4), shv = slab(N * 4);
-    auto sz = slab((N + 1) * 6), szp = slab((N + 1) * 6), szc = slab(N * 3), slq = slab(N * 6), st = slab(N * 6);
-    auto sK = slab(N * 8), sLi = slab(N * 3), sPb = slab(N * 4), skf = slab(N * 2), spq = slab(N * 4);
-    auto srg = slab((N + 1) * 6), srb = slab(N * 4), srgs = slab(N);
-    auto scost = slab(1), sres = slab(4), salpha = slab(1), swpi = slab(N * 4), swlam = slab(N * 6), swx0 = slab(4);
-    S.x = sx.data(); S.u = su.data(); S.pi = spi.data(); S.lam = slam.data(); S.x0 = sx0.data(); S.yref = syr.data(); S.yref_e = sye.data();
-    S.A = sA.data(); S.Bm = sB.data(); S.b = sb.data(); S.g = sg.data(); S.qN = sqN.data(); S.dx0 = sdx0.data(); S.hv = shv.data();
-    S.z = sz.data(); S.zp = szp.data(); S.zc = szc.data(); S.lamq = slq.data(); S.t = st.data();
-    S.K = sK.data(); S.Li = sLi.data(); S.Pb = sPb.data(); S.kff = skf.data(); S.piq = spq.data();
-    S.rg = srg.data(); S.rb = srb.data(); S.rgs = srgs.data();
-    S.cost = scost.data(); S.res = sres.data(); S.alpha = salpha.data(); S.wpi = swpi.data(); S.wlam = swlam.data(); S.wx0 = swx0.data();
-    // cost constants exactly like flush_cost() in qspush_capi.cu
-    std::vector<double> Wdt((size_t)N * 36), H((size_t)N * 21), QN(10), Wev(We, We + 16);
-    auto perm = [](int zi) { return zi < 2 ? 4 + zi : zi - 2; };
-    for (int k = 0; k < N; ++k) {
-        for (int i = 0; i < 36; ++i) Wdt[(size_t)k * 36 + i] = dt * W[(size_t)k * 36 + i];
-        for (int i = 0; i < 6; ++i) for (int j = 0; j <= i; ++j)
-            H[(size_t)k * 21 + LT(i, j)] = dt * 0.5 * (W[(size_t)k * 36 + perm(i) + 6 * perm(j)] + W[(size_t)k * 36 + perm(j) + 6 * perm(i)]);
-    }
-    for (int i = 0; i < 4; ++i) for (int j = 0; j <= i; ++j) QN[LT(i, j)] = 0.5 * (We[i + 4 * j] + We[j + 4 * i]);
-    S.Wdt = Wdt.data(); S.We = Wev.data(); S.H = H.data(); S.QN = QN.data();
-    for (int i = 0; i < 3; ++i) { S.lh[i] = lh[i]; S.uh[i] = uh[i]; }
-    S.h_variant = opts_i[8];                                     // like apply_variant() in qspush_capi.cu
-    for (int i = 0; i < 4; ++i) S.vbp[i] = ctrl5[i];
-    if (S.h_variant && !(opts_i[7] && qp_warp_chunk(N) <= 4)) { g_err = "h_variant 1 needs the warp QP kernel"; return -1; }
-    // AoS -> SoA (k_aos_to_soa)
-    auto in = [&](const double* src, std::vector<double>& dst, int R) { for (int b = 0; b < nb; ++b) for (int r = 0; r < R; ++r) dst[(size_t)r * Bp + b] = src[(size_t)b * R + r]; };
-    auto out = [&](const std::vector<double>& src, double* dst, int R) { if (!dst) return; for (int b = 0; b < nb; ++b) for (int r = 0; r < R; ++r) dst[(size_t)b * R + r] = src[(size_t)r * Bp + b]; };
-    in(x0, sx0, 4); in(yref, syr, N * 6); in(yref_e, sye, 4); in(x, sx, (N + 1) * 4); in(u, su, N * 2);
-    if (pi) in(pi, spi, N * 4);
-    if (lam) in(lam, slam, N * 6);
-    const int mode = opts_i[0];
-    IpmOpts io{opts_i[1], opts_d[0], opts_d[1], opts_d[2], opts_d[3]};
-    SqpOpts so{opts_i[2], {opts_d[4], opts_d[5], opts_d[6], opts_d[7]}, opts_i[3], opts_d[8], opts_d[9], opts_d[10]};
-    CtrlDev cp{ctrl5[0], ctrl5[1], ctrl5[2], ctrl5[3], ctrl5[4], opts_i[4]};
-    const double* Mall = blobs.data();
-    if (opts_i[5]) for (int b = 0; b < nb; ++b) prepare_one(S, cp, Mall, b);
-    auto linearise_all = [&]() { for (int k = 0; k <= N; ++k) for (int b = 0; b < nb; ++b) if (!S.done[b]) linearise_one(S, Mall, k, b); };
-    if (mode == 0 || mode == 2) {
-        linearise_all();
-        for (int b = 0; b < nb; ++b) { if (opts_i[7] && qp_warp_chunk(N) <= 4) qp_warp_host(S, io, b, mode == 0 ? 1 : 0); else qp_one(S, io, b, mode == 0 ? 1 : 0); }
-    } else {
-        for (int it = 0; it <= so.max_iter; ++it) {
-            linearise_all();
-            int nd = 0;
-            for (int b = 0; b < nb; ++b) { if (!S.done[b]) nlp_res_one(S, so, it, b, ChunkSerial(), true); nd += S.done[b]; }
-            if (nd >= nb || it == so.max_iter) break;
-            for (int b = 0; b < nb; ++b) if (!S.done[b]) { if (opts_i[7] && qp_warp_chunk(N) <= 4) qp_warp_host(S, io, b, 0); else qp_one(S, io, b, 0); }
-            for (int b = 0; b < nb; ++b) if (!S.done[b]) linesearch_one(S, so, Mall, it, b, ChunkSerial(), true);
-        }
-        for (int b = 0; b < nb; ++b) cost_one(S, b);
-    }
-    out(sz, step_z, (N + 1) * 6); out(mode == 0 ? spi : spq, qp_pi, N * 4); out(mode == 0 ? slam : slq, qp_lam, N * 6);
-    out(sA, lin_A, N * 8); out(sB, lin_B, N * 8); out(sb, lin_b, N * 4); out(sg, lin_g, N * 6);
-    if (opts_i[6]) for (int b = 0; b < nb; ++b) for (int c = 0; c < 16; ++c) shift_one(S, c, b);
-    out(sx0, x0, 4); out(sx, x, (N + 1) * 4); out(su, u, N * 2);
-    if (pi) out(spi, pi, N * 4);
-    if (lam) out(slam, lam, N * 6);
+    HostRun R(models, nmodels, N, dt, nb, objid, W, We, lh, uh, opts_d, opts_i, ctrl5, cold);
+    if (!R.err.empty()) { g_err = R.err; return -1; }
+    SolverDev& S = R.S;
+    const int Bp = R.Bp;
+    R.in(x0, R.sx0, 4); R.in(yref, R.syr, N * 6); R.in(yref_e, R.sye, 4); R.in(x, R.sx, (N + 1) * 4); R.in(u, R.su, N * 2);
+    if (pi) R.in(pi, R.spi, N * 4);
+    if (lam) R.in(lam, R.slam, N * 6);
+    const int mode = R.mode;
+    if (opts_i[5]) R.prepare();
+    R.solve();
+    R.out(R.sz, step_z, (N + 1) * 6); R.out(mode == 0 ? R.spi : R.spq, qp_pi, N * 4); R.out(mode == 0 ? R.slam : R.slq, qp_lam, N * 6);
+    R.out(R.sA, lin_A, N * 8); R.out(R.sB, lin_B, N * 8); R.out(R.sb, lin_b, N * 4); R.out(R.sg, lin_g, N * 6);
+    if (opts_i[6]) R.shift();
+    R.out(R.sx0, x0, 4); R.out(R.sx, x, (N + 1) * 4); R.out(R.su, u, N * 2);
+    if (pi) R.out(R.spi, pi, N * 4);
+    if (lam) R.out(R.slam, lam, N * 6);
     for (int b = 0; b < nb; ++b) {
         if (cold) cold[b] = S.cold[b];
         if (stats_i) { stats_i[3 * b] = S.status[b]; stats_i[3 * b + 1] = S.sqp_iter[b]; stats_i[3 * b + 2] = S.qp_iter[b]; }
-        if (stats_d) { stats_d[6 * b] = scost[b]; for (int i = 0; i < 4; ++i) stats_d[6 * b + 1 + i] = sres[(size_t)i * Bp + b]; stats_d[6 * b + 5] = salpha[b]; }
+        if (stats_d) { stats_d[6 * b] = R.scost[b]; for (int i = 0; i < 4; ++i) stats_d[6 * b + 1 + i] = R.sres[(size_t)i * Bp + b]; stats_d[6 * b + 5] = R.salpha[b]; }
+    }
+    return 0;
+}
+
+// mirrors qspush_closed_loop (qspush_capi.cu): the same kernel bodies in the same order on host slabs.
+//   loop_d: [sigma0..3, amplitude_dist, xwidth]   loop_i: [idx0, t_dist]   seed: noise seed
+int hs_closed_loop(void* const* models, int nmodels, int N, double dt, int nb, const int* objid,
+                   const double* W, const double* We, const double* lh, const double* uh,
+                   const double* opts_d, const int* opts_i, const double* ctrl5,
+                   const double* traj, int T, const double* offset, double* x, int steps,
+                   const double* loop_d, const int* loop_i, unsigned long long seed,
+                   double* log_x, double* log_u, int* log_status) {
+    std::vector<int> cold(nb, 1);
+    HostRun R(models, nmodels, N, dt, nb, objid, W, We, lh, uh, opts_d, opts_i, ctrl5, cold.data());
+    if (!R.err.empty()) { g_err = R.err; return -1; }
+    LoopDev L;
+    L.traj = traj; L.off = offset; L.T = T;
+    for (int i = 0; i < 4; ++i) L.sigma[i] = loop_d[i];
+    L.seed = seed; L.t_dist = loop_i[1]; L.amp = loop_d[4]; L.xwidth = loop_d[5]; L.single = R.single;
+    for (int i = 1; i <= steps; ++i) {
+        for (int b = 0; b < nb; ++b) loop_state_one(R.S, L, R.Mall(), i, x, log_x ? log_x + (size_t)(i - 1) * nb * 4 : nullptr, b);
+        for (int k = 0; k < N; ++k) for (int b = 0; b < nb; ++b) loop_window_one(R.S, L, loop_i[0] + i - 1, k, b);
+        R.prepare();
+        R.solve();
+        for (int b = 0; b < nb; ++b)
+            loop_post_one(R.S, R.Mall(), x, log_u ? log_u + (size_t)(i - 1) * nb * 2 : nullptr, log_status ? log_status + (size_t)(i - 1) * nb : nullptr, b);
+        R.shift();
     }
     return 0;
 }

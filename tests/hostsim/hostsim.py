@@ -139,3 +139,34 @@ def solve(models, N, dt, x0, yref, yref_e, x, u, pi=None, lam=None, cold=None, o
     return dict(x0=x0, x=x, u=u, pi=pi, lam=lam, cold=cold, status=si[:, 0], sqp_iter=si[:, 1], qp_iter=si[:, 2],
                 cost=sd[:, 0], res=sd[:, 1:5], alpha=sd[:, 5], du=z[:, :N, :2], dx=z[:, :, 2:], qp_pi=qpi, qp_lam=qlam,
                 A=A, B=B, b=bb, g=g)
+
+
+def closed_loop(models, N, dt, traj, x, steps, offset=None, objid=None, W=None, We=None,
+                lh=(-0.06, 0.0, -0.05), uh=(0.011, 0.03, 0.05), mode="rti",
+                qp_tol=1e-12, qp_mu0=0.1, qp_thr=1e-3, qp_tau=0.9995, qp_max_iter=50, max_sqp_iter=30,
+                tol=(1e-6, 1e-6, 1e-6, 1e-6), globalization=1, alpha_min=0.05, alpha_red=0.7, eps_sd=1e-4,
+                single_quirk=True, ctrl=(1.0, 0.0, 3.0, 0.05, 0.0), qp_kernel=1, h_variant=0,
+                idx0=1, noise_sigma=(0.0, 0.0, 0.0, 0.0), seed=0, t_dist=0, amplitude_dist=0.0, xwidth=0.0):
+    """Host mirror of qspush_closed_loop (same kernel bodies, same order)."""
+    x = _c(x).copy(); nb = x.shape[0]
+    if W is None:
+        W = np.tile(np.diag([1.0, 1.0, 1e-3, 0.0, 1e-3, 1e-3]).reshape(1, 36), (N, 1))
+    if We is None:
+        We = np.diag([2e5, 2e5, 20.0, 0.0])
+    W = _c(np.asarray(W).reshape(N, 36)); We = np.asfortranarray(We, dtype=np.float64)
+    traj = _c(traj); T = traj.shape[0]
+    objid = np.zeros(nb, dtype=np.int32) if objid is None else _c(objid, np.int32)
+    od = _c([qp_tol, qp_mu0, qp_thr, qp_tau, *tol, alpha_min, alpha_red, eps_sd])
+    oi = _c([{"rti": 0, "sqp": 1}[mode], qp_max_iter, max_sqp_iter, globalization, int(single_quirk), 1, 1, int(qp_kernel), int(h_variant)], np.int32)
+    c5 = _c(ctrl); lh = _c(lh); uh = _c(uh)
+    ld = _c([*noise_sigma, amplitude_dist, xwidth]); li = _c([idx0, t_dist], np.int32)
+    lx = np.zeros((steps, nb, 4)); lu = np.zeros((steps, nb, 2)); ls = np.zeros((steps, nb), dtype=np.int32)
+    off = None if offset is None else _c(offset)
+    arr = (C.c_void_p * len(models))(*[m.h for m in models])
+    f = lib().hs_closed_loop
+    f.restype = C.c_int
+    rc = f(arr, len(models), N, C.c_double(dt), nb, _i(objid), _d(W), We.ctypes.data_as(_dp), _d(lh), _d(uh), _d(od), _i(oi), _d(c5),
+           _d(traj), T, (_d(off) if off is not None else None), _d(x), steps, _d(ld), _i(li), C.c_ulonglong(seed), _d(lx), _d(lu), _i(ls))
+    if rc != 0:
+        raise RuntimeError("hs_closed_loop: " + lib().hs_last_error().decode())
+    return dict(x=x, x_log=lx, u_log=lu, status_log=ls)

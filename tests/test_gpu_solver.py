@@ -367,3 +367,65 @@ def test_velocity_constraint_variant_vs_oracle():
     out = q.helper.closed_loop_matlab(p, c, np.array([0.0, 0.0, 0.0, 0.003]), 20 * 0.05)
     u_t, s_s = np.asarray(out[7]), np.asarray(out[3])
     assert np.isfinite(u_t).all() and np.abs(u_t).max() <= 0.05 + 1e-9
+
+
+def test_device_resident_closed_loop():
+    """qspush_closed_loop (helper.closed_loop_matlab for a whole batch, on the device): identical to driving the same
+    solver step by step from the host, equal to the oracle's closed loop, torch-CUDA buffers without host round
+    trips, disturbance / noise options, and the helper.closed_loop_device mirror."""
+    import torch
+    from tests.hostsim import hostsim as hs
+    from tests.workloads import hostsim_model
+    gm, om = packaged_model_pair("santal")
+    N, dt, steps, T, B = 10, 0.05, 30, 201, 48
+    t = np.arange(T) * dt
+    traj = np.zeros((T, 6)); traj[:, 0] = np.minimum(0.01 * t, 0.10)
+    rng = np.random.default_rng(5)
+    x0s = np.stack([rng.uniform(-0.003, 0.003, B), rng.uniform(-0.003, 0.003, B), rng.uniform(-0.05, 0.05, B), rng.uniform(-0.02, 0.004, B)], 1)
+    off = np.zeros((B, 6)); off[:, :2] = x0s[:, :2]
+    # (a) host-driven loop through the per-step API
+    s = q.Solver([gm], N, dt, B)
+    x = x0s.copy(); u_host = np.zeros((steps, B, 2)); x_host = np.zeros((steps, B, 4))
+    s.set_int("cold", np.ones(B, dtype=np.int32))
+    for i in range(1, steps + 1):
+        cols = [min(i + k, T) - 1 for k in range(N)]
+        yref = np.ascontiguousarray(traj[cols][None] + off[:, None, :])
+        x_host[i - 1] = x
+        s.set("x0", x); s.set("yref", yref); s.set("yref_e", np.ascontiguousarray(yref[:, N - 1, :4]))
+        s.prepare(); s.solve()
+        u = s.get("u", stage=0); u_host[i - 1] = u
+        s.shift()
+        x = s.plant_step(np.ascontiguousarray(x.copy()), np.ascontiguousarray(u))
+    # (b) the same on the device, host arrays in / out
+    s2 = q.Solver([gm], N, dt, B)
+    r = s2.closed_loop(traj, x0s.copy(), steps, offset=off)
+    # (same kernels; the plant step is inlined into two different kernels, whose FMA contraction may differ by an ulp)
+    assert np.abs(r["u_log"] - u_host).max() < 1e-12 and np.abs(r["x_log"] - x_host).max() < 1e-12 and np.abs(r["x"] - x).max() < 1e-12
+    assert (r["status_log"] == 0).all()
+    # (c) torch CUDA buffers: no host copies at all
+    s3 = q.Solver([gm], N, dt, B)
+    xd = torch.from_numpy(x0s.copy()).cuda()
+    rd = s3.closed_loop(torch.from_numpy(traj).cuda(), xd, steps, offset=torch.from_numpy(off).cuda())
+    s3.sync()
+    assert np.array_equal(rd["u_log"].cpu().numpy(), r["u_log"]) and np.array_equal(xd.cpu().numpy(), r["x"])     # same launches: bitwise
+    # (d) oracle closed loop on a few problems
+    ocp = orc.Ocp(om, N, dt)
+    for b in (0, 7, 31):
+        cl = ocp.closed_loop("rti", x0s[b], traj + off[b][None, :], steps)
+        assert np.abs(r["u_log"][:, b] - cl["u"]).max() < 1e-6 and np.abs(r["x"][b] - cl["x"][-1]).max() < 1e-6
+    # (e) disturbance and noise vs the host execution of the same kernel bodies
+    kw = dict(t_dist=10, amplitude_dist=0.004, xwidth=0.068, noise_sigma=(1e-5, 1e-5, 1e-3, 1e-4), seed=11)
+    s4 = q.Solver([gm], N, dt, 8)
+    r4 = s4.closed_loop(traj, x0s[:8].copy(), 20, offset=off[:8], **kw)
+    h4 = hs.closed_loop([hostsim_model("santal")], N, dt, traj, x0s[:8], 20, offset=off[:8], **kw)
+    assert np.abs(r4["x_log"] - h4["x_log"]).max() < 1e-7 and np.abs(r4["u_log"] - h4["u_log"]).max() < 1e-5
+    assert np.abs(r4["x_log"][9, :, 1] - r4["x_log"][8, :, 1]).max() > 0.003        # the shove is there
+    # (f) MATLAB-shaped mirror
+    sel = q.object_selection("santal")
+    p = q.PusherSliderModel("real_plant", sel, 0, sel.cad_model_path, 3, sel.pcl_path, "santal")
+    p.symbolic_model_variable_shape()
+    c = q.NMPC_controller("NMPC", p, dt, N, batch=B, nlp_solver="sqp_rti")
+    c.create_ocp_solver(); c.set_delay_comp(0.0)
+    c.set_reference_trajectory(traj.T)
+    out = q.helper.closed_loop_device(p, c, x0s, (steps - 1) * dt, offset=off)
+    assert out[0].shape == (B, steps) and np.array_equal(np.stack([out[4], out[5]], -1), np.transpose(r["u_log"], (1, 0, 2))) and out[7].all()

@@ -205,3 +205,49 @@ def test_velocity_constraint_variant_vs_oracle(N):
     import ctypes
     with pytest.raises(Exception):
         hs.solve([hm], N, dt, pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"], mode="qp", qp_kernel=0, **kw)
+
+
+def test_closed_loop_bodies_vs_oracle():
+    """Bodies of the device-resident closed loop (qspush_closed_loop: state/noise/disturbance, reference window, prepare,
+    solve, plant step, shift) in kernel order on the host vs the oracle's closed loop (helper.m:219-313 restated)."""
+    om, hm = oracle_model("santal"), hostsim_model("santal")
+    N, dt, steps, T = 10, 0.05, 30, 201
+    t = np.arange(T) * dt
+    traj = np.zeros((T, 6)); traj[:, 0] = np.minimum(0.01 * t, 0.10)
+    x0s = np.array([[0, 0, 0, 0], [0.001, -0.002, 0.02, -0.01], [0, 0.003, -0.05, 0.004]], dtype=float)
+    off = np.zeros((3, 6)); off[1, :2] = [0.001, -0.002]; off[2, 1] = 0.003
+    ocp = orc.Ocp(om, N, dt)
+    for mode, tol_u in (("rti", 1e-8), ("sqp", 1e-6)):
+        r = hs.closed_loop([hm], N, dt, traj, x0s, steps, offset=off, mode=mode)
+        for b in range(3):
+            cl = ocp.closed_loop(mode, x0s[b], traj + off[b][None, :], steps)
+            same = (r["status_log"][:, b] == cl["status"])
+            assert same.mean() > 0.8
+            if mode == "rti":
+                assert same.all() and np.abs(r["u_log"][:, b] - cl["u"]).max() < tol_u
+                assert np.abs(r["x_log"][:, b] - cl["x"][:-1]).max() < 1e-8 and np.abs(r["x"][b] - cl["x"][-1]).max() < 1e-8
+            else:
+                k = int(np.argmin(same)) if not same.all() else steps       # compare up to the first diverging SQP path
+                assert k >= 5 and np.abs(r["u_log"][:k, b] - cl["u"][:k]).max() < tol_u
+    # lateral shove: y jumps by the amplitude, s is re-projected onto the outline next to the old contact point
+    r = hs.closed_loop([hm], N, dt, traj, x0s, steps, t_dist=10, amplitude_dist=0.004, xwidth=0.068)
+    r0 = hs.closed_loop([hm], N, dt, traj, x0s, steps)
+    assert np.array_equal(r["u_log"][:9], r0["u_log"][:9])
+    xl = r["x_log"]
+    assert np.allclose(xl[9, :, 1] - r0["x_log"][9, :, 1], 0.004, atol=1e-12)
+    grid = np.linspace(-0.5 * om.b, 0.5 * om.b, 40001)
+    Cg = om.eval_spline(grid, wrap=1)["C"]
+    for b in range(3):
+        c_old = om.eval_spline([r0["x_log"][9, b, 3]], wrap=1)["C"][0]
+        target = np.array([-0.5 * 0.068, c_old[1] - 0.004])                      # helper.m:226-228
+        c_new = om.eval_spline([xl[9, b, 3]], wrap=1)["C"][0]
+        d_new, d_min = ((c_new - target) ** 2).sum(), ((Cg - target[None]) ** 2).sum(1).min()
+        assert d_new <= d_min + 1e-12 and abs(xl[9, b, 3]) < 0.06              # global minimiser, representative next to 0
+    assert np.isfinite(r["u_log"]).all()
+    # noise: deterministic in the seed, right magnitude
+    ra = hs.closed_loop([hm], N, dt, traj, x0s, 5, noise_sigma=(1e-5, 1e-5, 1e-3, 1e-4), seed=7)
+    rb = hs.closed_loop([hm], N, dt, traj, x0s, 5, noise_sigma=(1e-5, 1e-5, 1e-3, 1e-4), seed=7)
+    rc = hs.closed_loop([hm], N, dt, traj, x0s, 5, noise_sigma=(1e-5, 1e-5, 1e-3, 1e-4), seed=8)
+    assert np.array_equal(ra["x_log"], rb["x_log"]) and not np.array_equal(ra["x_log"], rc["x_log"])
+    d0 = ra["x_log"][0] - x0s
+    assert 0 < np.abs(d0[:, 2]).max() < 6e-3 and np.abs(d0[:, 0]).max() < 6e-5

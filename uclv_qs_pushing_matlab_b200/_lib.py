@@ -42,6 +42,12 @@ class Ctrl(C.Structure):
                 ("u_t_ub", C.c_double), ("u_n_lb", C.c_double)]
 
 
+class LoopOpts(C.Structure):
+    """qspush_loop_opts (include/qspush.h)."""
+    _fields_ = [("idx0", C.c_int), ("noise_sigma", C.c_double * 4), ("seed", C.c_ulonglong), ("t_dist", C.c_int),
+                ("amplitude_dist", C.c_double), ("xwidth", C.c_double)]
+
+
 # qspush_field / qspush_mem / qspush_mode / qspush_stat
 X0, YREF, YREF_E, X, U, PI, LAM, COST, RES = 0, 1, 2, 3, 4, 5, 6, 7, 8
 W, LH, UH = 16, 17, 18
@@ -78,6 +84,7 @@ SIGNATURES = {
     "qspush_solve": (C.c_int, [vp]),
     "qspush_shift": (C.c_int, [vp]),
     "qspush_plant_step": (C.c_int, [vp, vp, vp, C.c_int]),
+    "qspush_closed_loop": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, C.POINTER(LoopOpts), vp, vp, vp, C.c_int]),
     "qspush_sync": (C.c_int, [vp]),
     "qspush_stream": (vp, [vp]),
     "qspush_get_stat": (C.c_int, [vp, C.c_int, dp]),

@@ -252,6 +252,45 @@ class Solver:
         L.check(L.lib().qspush_plant_step(self._h, px, pu, mem))
         return x
 
+    def closed_loop(self, traj, x, steps, offset=None, idx0=1, noise_sigma=(0.0, 0.0, 0.0, 0.0), seed=0, t_dist=0,
+                    amplitude_dist=0.0, xwidth=0.0, log=True):
+        """Device-resident closed loop (qspush_closed_loop; helper.closed_loop_matlab for the whole batch).
+
+        traj (T,6) reference columns [x_ref; u_ref]; x (batch,4) initial plant state (updated in place); offset
+        (batch,6) optional per-problem shift of the reference.  numpy arrays (host) or torch CUDA tensors (device, no
+        host round trip at all); returns dict(x=final state, x_log (steps,batch,4), u_log (steps,batch,2),
+        status_log (steps,batch)) in the same memory space."""
+        on_dev = torch is not None and isinstance(x, torch.Tensor) and x.is_cuda
+        B = self.batch
+        pt, mem_t, kt = _buf(traj)
+        px, mem, kx = _buf(x, writable=True)
+        T = (kt.shape[0] if hasattr(kt, "shape") else len(kt))
+        po = None
+        if offset is not None:
+            po, mem_o, ko = _buf(offset)
+            if mem_o != mem:
+                raise L.QspushError("offset and x must live in the same memory space")
+        if mem_t != mem:
+            raise L.QspushError("traj and x must live in the same memory space")
+        lx = lu = ls = None
+        plx = plu = pls = None
+        if log:
+            if on_dev:
+                lx = torch.empty(steps, B, 4, dtype=torch.float64, device=x.device)
+                lu = torch.empty(steps, B, 2, dtype=torch.float64, device=x.device)
+                ls = torch.empty(steps, B, dtype=torch.int32, device=x.device)
+                plx, plu, pls = lx.data_ptr(), lu.data_ptr(), ls.data_ptr()
+            else:
+                lx = np.zeros((steps, B, 4)); lu = np.zeros((steps, B, 2)); ls = np.zeros((steps, B), dtype=np.int32)
+                plx, plu, pls = lx.ctypes.data, lu.ctypes.data, ls.ctypes.data
+        lo = L.LoopOpts()
+        lo.idx0 = int(idx0); lo.seed = int(seed); lo.t_dist = int(t_dist)
+        lo.amplitude_dist = float(amplitude_dist); lo.xwidth = float(xwidth)
+        for i in range(4):
+            lo.noise_sigma[i] = float(noise_sigma[i])
+        L.check(L.lib().qspush_closed_loop(self._h, pt, int(T), po, px, int(steps), C.byref(lo), plx, plu, pls, mem))
+        return dict(x=x, x_log=lx, u_log=lu, status_log=ls)
+
     def sync(self):
         L.check(L.lib().qspush_sync(self._h))
 

@@ -300,4 +300,24 @@ __global__ void k_plant_step(SolverDev S, double* x, const double* u) {
     xp[1] = make_double2(fma(S.dt, d.f[2], x23.x), fma(S.dt, d.f[3], x23.y));
 }
 
+// ---- device-resident closed loop (qspush_closed_loop): thin wrappers, one thread per problem / per (stage, problem)
+__global__ void k_loop_window(SolverDev S, LoopDev L, int idx) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = (int)(tid / S.Bp), b = (int)(tid % S.Bp);
+    if (k >= S.N || b >= S.B) return;
+    loop_window_one(S, L, idx, k, b);
+}
+__global__ void __launch_bounds__(128) k_loop_state(SolverDev S, LoopDev L, int step, double* xs, double* log_x) {
+    const double* Mall = stage_models(S.models, S.nmodels);
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= S.B) return;
+    loop_state_one(S, L, Mall, step, xs, log_x, b);
+}
+__global__ void __launch_bounds__(128) k_loop_post(SolverDev S, double* xs, double* log_u, int* log_status) {
+    const double* Mall = stage_models(S.models, S.nmodels);
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= S.B) return;
+    loop_post_one(S, Mall, xs, log_u, log_status, b);
+}
+
 }  // namespace qs

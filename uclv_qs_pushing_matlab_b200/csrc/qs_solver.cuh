@@ -581,6 +581,114 @@ QS_HD void cost_one(const SolverDev& S, int b) {
     S.cost[b] = c + terminal_cost(S, b);
 }
 
+// ------------------------------------------------------------------------------------------------
+// device-resident closed loop (helper.closed_loop_matlab, helper.m:219-313, for a whole batch)
+// ------------------------------------------------------------------------------------------------
+struct LoopDev {
+    const double* traj;     // [T][6] reference columns [x_ref; u_ref] shared by the batch (controller.y_ref, :425-431)
+    const double* off;      // [B][6] per-problem offset added to every column (nullptr: none)
+    int T;
+    double sigma[4];        // state-noise standard deviations (helper.m:241), all 0 = off
+    unsigned long long seed;
+    int t_dist;             // 1-based step of the lateral shove (helper.m:222), 0 = none
+    double amp, xwidth;     // amplitude_dist, slider_params.xwidth
+    int single;             // MATLAB `single` rounding of mod(s, b) inside evalSpline
+};
+
+// reference window of control period `idx` (1-based, NMPC_controller.m:307-313, 343-348): stage k uses column
+// min(idx + k, T); the terminal reference is the x part of the last window column
+QS_HD void loop_window_one(const SolverDev& S, const LoopDev& L, int idx, int k, int b) {
+    int col = idx + k; if (col > L.T) col = L.T;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        const double v = L.traj[(size_t)(col - 1) * 6 + c] + (L.off ? L.off[(size_t)b * 6 + c] : 0.0);
+        QS_EL(S.yref, k * 6 + c, b) = v;
+        if (k == S.N - 1 && c < 4) QS_EL(S.yref_e, c, b) = v;
+    }
+}
+
+// counter-based standard normal: splitmix64 of (seed, step, problem, component) -> two uniforms -> Box-Muller
+QS_HD double loop_randn(unsigned long long seed, int step, int b, int c) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(((unsigned long long)step << 34) ^ ((unsigned long long)b << 3) ^ (unsigned long long)c);
+    auto mix = [](unsigned long long v) { v = (v ^ (v >> 30)) * 0xBF58476D1CE4E5B9ull; v = (v ^ (v >> 27)) * 0x94D049BB133111EBull; return v ^ (v >> 31); };
+    const unsigned long long a = mix(z), bq = mix(z + 0x9E3779B97F4A7C15ull);
+    const double u1 = ((double)(a >> 11) + 1.0) * (1.0 / 9007199254740993.0);      // (0, 1)
+    const double u2 = (double)(bq >> 11) * (1.0 / 9007199254740992.0);              // [0, 1)
+    return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+}
+
+// argmin_s |C(s) - target|^2 (helper.m:216-232; fminunc there): scan of 2048 grid points, then Newton on the
+// stationarity condition, C / C' / C'' evaluated like bspline_shape.evalSpline (argument wrapped by mod(s, b))
+QS_HD double loop_reproject(const double* __restrict__ M, double tx, double ty, bool single) {
+    const double bb = M[1];
+    double best = 1e300, s = 0.0;
+    for (int i = 0; i < 2048; ++i) {
+        const double g = bb * (double)i / 2048.0;
+        Curve c; curve_eval(M, matlab_mod(g, bb, single), c);
+        const double d2 = (c.cx - tx) * (c.cx - tx) + (c.cy - ty) * (c.cy - ty);
+        if (d2 < best) { best = d2; s = g; }
+    }
+    for (int it = 0; it < 20; ++it) {
+        const double sg = matlab_mod(s, bb, single);
+        Curve c; curve_eval(M, sg, c);
+        double ex, ey; curve_dd(M, sg, ex, ey);
+        const double rx = c.cx - tx, ry = c.cy - ty;
+        const double g1 = 2.0 * (rx * c.dx + ry * c.dy);
+        const double g2 = 2.0 * (c.dx * c.dx + c.dy * c.dy + rx * ex + ry * ey);
+        if (!(g2 > 0.0)) break;
+        const double step = g1 / g2;
+        s -= step;
+        if (fabs(step) < 1e-14) break;
+    }
+    // fminunc starts at s = 0 (helper.m:218) and walks to the nearby minimum on the pushed face: report the
+    // representative of the minimiser closest to 0, i.e. in (-b/2, b/2]
+    if (s > 0.5 * bb) s -= bb;
+    return s;
+}
+
+// start of control period `step` (1-based) for problem b: disturbance (helper.m:221-236), noise (:240-242) applied to
+// the plant state xs [B][4] in place; the state becomes the controller's x0 (constr_x0, NMPC_controller.m:334) and is logged
+QS_HD void loop_state_one(const SolverDev& S, const LoopDev& L, const double* __restrict__ Mall, int step, double* xs, double* log_x, int b) {
+    const double* M = Mall + (size_t)S.objid[b] * MODEL_DOUBLES;
+    double x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = xs[(size_t)b * 4 + i];
+    if (L.t_dist > 0 && step == L.t_dist) {
+        x[1] += L.amp;                                                      // :224
+        Curve c; curve_eval(M, matlab_mod(x[3], M[1], L.single != 0), c);   // :226 Sp = evalSpline(FC, x(4))
+        const double smin = loop_reproject(M, -0.5 * L.xwidth, c.cy - L.amp, L.single != 0);   // :227-230
+        const double fm = fmod(smin, M[1]);
+        double s0 = fm + ((smin < 0.0 && fm != 0.0) ? M[1] : 0.0);          // MATLAB mod(s, b)
+        s0 -= M[1] * (smin < 0.0 ? 1.0 : 0.0);                              // :232
+        x[3] = s0;
+    }
+    if (L.sigma[0] != 0.0 || L.sigma[1] != 0.0 || L.sigma[2] != 0.0 || L.sigma[3] != 0.0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] += L.sigma[i] * loop_randn(L.seed, step, b, i);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        xs[(size_t)b * 4 + i] = x[i];
+        QS_EL(S.x0, i, b) = x[i];
+        if (log_x) log_x[(size_t)b * 4 + i] = x[i];
+    }
+}
+
+// end of the control period: u = get('u', 0) (NMPC_controller.m:403), forward-Euler plant step (helper.m:294, 307), logs
+QS_HD void loop_post_one(const SolverDev& S, const double* __restrict__ Mall, double* xs, double* log_u, int* log_status, int b) {
+    const double* M = Mall + (size_t)S.objid[b] * MODEL_DOUBLES;
+    const double un = QS_EL(S.u, 0, b), ut = QS_EL(S.u, 1, b);
+    double x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = xs[(size_t)b * 4 + i];
+    Dyn d;
+    dyn_eval<false>(M, x[2], x[3], un, ut, d);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xs[(size_t)b * 4 + i] = fma(S.dt, d.f[i], x[i]);
+    if (log_u) { log_u[(size_t)b * 2] = un; log_u[(size_t)b * 2 + 1] = ut; }
+    if (log_status) log_status[b] = S.status[b];
+}
+
 // post-processing shift (NMPC_controller.m:397-399) of component c of problem b:
 // c = 0..3 x, 4..5 u, 6..9 pi, 10..15 lam
 QS_HD void shift_one(const SolverDev& S, int c, int b) {

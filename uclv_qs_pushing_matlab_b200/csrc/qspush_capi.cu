@@ -679,6 +679,66 @@ int qspush_plant_step(qspush_solver* s, double* x, const double* u, qspush_mem m
     return QSPUSH_OK;
 }
 
+int qspush_closed_loop(qspush_solver* s, const double* traj, int T, const double* offset, double* x, int steps,
+                       const qspush_loop_opts* lo, double* log_x, double* log_u, int* log_status, qspush_mem mem) {
+    if (!s || !traj || !x || !lo) return fail(QSPUSH_ERR_ARG, "NULL argument");
+    if (T < 1 || steps < 1 || lo->idx0 < 1) return fail(QSPUSH_ERR_ARG, "closed loop: need T >= 1, steps >= 1, idx0 >= 1");
+    CK(cudaSetDevice(s->device));
+    const size_t B = (size_t)s->B;
+    // device views of the caller arrays (host memory: staged once before and copied back once after the loop)
+    struct Tmp { std::vector<void*> p; ~Tmp() { for (void* q : p) cudaFree(q); } } tmp;
+    auto dev_in = [&](const void* h, size_t bytes, void** d) -> int {
+        if (!h) { *d = nullptr; return QSPUSH_OK; }
+        if (mem == QSPUSH_MEM_DEVICE) { *d = const_cast<void*>(h); return QSPUSH_OK; }
+        CK(cudaMalloc(d, bytes)); tmp.p.push_back(*d);
+        CK(cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, s->stream));
+        return QSPUSH_OK;
+    };
+    auto dev_out = [&](void* h, size_t bytes, void** d) -> int {
+        if (!h) { *d = nullptr; return QSPUSH_OK; }
+        if (mem == QSPUSH_MEM_DEVICE) { *d = h; return QSPUSH_OK; }
+        CK(cudaMalloc(d, bytes)); tmp.p.push_back(*d);
+        return QSPUSH_OK;
+    };
+    void *d_traj, *d_off, *d_x, *d_lx, *d_lu, *d_ls;
+    RET(dev_in(traj, (size_t)T * 6 * 8, &d_traj)); RET(dev_in(offset, B * 6 * 8, &d_off)); RET(dev_in(x, B * 4 * 8, &d_x));
+    RET(dev_out(log_x, (size_t)steps * B * 4 * 8, &d_lx)); RET(dev_out(log_u, (size_t)steps * B * 2 * 8, &d_lu));
+    RET(dev_out(log_status, (size_t)steps * B * sizeof(int), &d_ls));
+    LoopDev L;
+    L.traj = (const double*)d_traj; L.off = (const double*)d_off; L.T = T;
+    for (int i = 0; i < 4; ++i) L.sigma[i] = lo->noise_sigma[i];
+    L.seed = lo->seed; L.t_dist = lo->t_dist; L.amp = lo->amplitude_dist; L.xwidth = lo->xwidth;
+    L.single = s->opts.matlab_single_quirk;
+    const size_t msm = model_smem_bytes(s->nmodels);
+    CK(cudaFuncSetAttribute(k_loop_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+    CK(cudaFuncSetAttribute(k_loop_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+    const unsigned pb = (unsigned)((B + 127) / 128);
+    const unsigned wb = (unsigned)(((size_t)s->N * s->Bp + 255) / 256);
+    for (int i = 1; i <= steps; ++i) {
+        double* lx = d_lx ? (double*)d_lx + (size_t)(i - 1) * B * 4 : nullptr;
+        double* lu = d_lu ? (double*)d_lu + (size_t)(i - 1) * B * 2 : nullptr;
+        int* ls = d_ls ? (int*)d_ls + (size_t)(i - 1) * B : nullptr;
+        k_loop_state<<<pb, 128, msm, s->stream>>>(s->dev, L, i, (double*)d_x, lx);
+        k_loop_window<<<wb, 256, 0, s->stream>>>(s->dev, L, lo->idx0 + i - 1);
+        CK(cudaGetLastError());
+        s->launches += 2;
+        RET(qspush_prepare(s));
+        RET(qspush_solve(s));
+        k_loop_post<<<pb, 128, msm, s->stream>>>(s->dev, (double*)d_x, lu, ls);
+        CK(cudaGetLastError());
+        s->launches++;
+        RET(qspush_shift(s));
+    }
+    if (mem == QSPUSH_MEM_HOST) {
+        CK(cudaMemcpyAsync(x, d_x, B * 4 * 8, cudaMemcpyDeviceToHost, s->stream));
+        if (log_x) CK(cudaMemcpyAsync(log_x, d_lx, (size_t)steps * B * 4 * 8, cudaMemcpyDeviceToHost, s->stream));
+        if (log_u) CK(cudaMemcpyAsync(log_u, d_lu, (size_t)steps * B * 2 * 8, cudaMemcpyDeviceToHost, s->stream));
+        if (log_status) CK(cudaMemcpyAsync(log_status, d_ls, (size_t)steps * B * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+    }
+    return QSPUSH_OK;
+}
+
 int qspush_sync(qspush_solver* s) {
     if (!s) return fail(QSPUSH_ERR_ARG, "NULL solver");
     CK(cudaSetDevice(s->device));

@@ -45,7 +45,56 @@ class helper:
             s -= step
             if abs(step) < 1e-14:
                 break
+        # fminunc starts at s0 = 0 (helper.m:218) and walks to the nearby minimum on the pushed face: report the
+        # representative of the minimiser closest to 0, i.e. in (-b/2, b/2]
+        if s > 0.5 * SP.b:
+            s -= SP.b
         return s
+
+    @staticmethod
+    def closed_loop_device(plant, controller, x0, time_sim, sim_noise=False, disturbance_=False, amplitude_dist=0.0,
+                           t_dist=10 ** 9, seed=0, offset=None):
+        """helper.closed_loop_matlab (helper.m:195-322) for a whole batch WITHOUT host round trips: the loop of reference
+        window -> prepare -> solve -> plant step -> shift runs on the GPU (qspush_closed_loop).  x0: (B,4) numpy array or
+        torch CUDA tensor; the controller's reference (6,T) is shared by the batch, `offset` (B,6) shifts it per problem.
+        Input delays (plant.time_delay, controller.set_delay_comp) are only handled by closed_loop_matlab.
+        Returns (x_s, y_s, theta_s, s_s, u_n, u_t, time_sim_vec, found_sol) with a leading batch axis, in x0's memory space."""
+        if plant.time_delay or controller.delay_buff_comp:
+            raise NotImplementedError("input delays: use closed_loop_matlab")
+        dt = controller.sample_time
+        time_sim_vec = np.arange(0.0, time_sim + 1e-12, dt)
+        T = len(time_sim_vec)
+        solver = controller.ocp_solver.solver
+        y_ref = np.ascontiguousarray(np.asarray(controller.y_ref, dtype=np.float64).T)          # (T_ref, 6)
+        on_dev = helper._is_cuda(x0)
+        if on_dev:
+            import torch
+            x = x0.clone().contiguous()
+            traj = torch.from_numpy(y_ref).to(x.device)
+            off = None if offset is None else offset.contiguous()
+        else:
+            x = np.ascontiguousarray(np.array(x0, dtype=np.float64).reshape(-1, 4))
+            traj = y_ref
+            off = None if offset is None else np.ascontiguousarray(offset, dtype=np.float64)
+        if controller._cold:
+            solver.set_int("cold", np.ones(controller.batch, dtype=np.int32)); controller._cold = False
+        sig = (1e-5, 1e-5, 1e-3, 1e-4) if sim_noise else (0.0, 0.0, 0.0, 0.0)                    # helper.m:241
+        r = solver.closed_loop(traj, x, T, offset=off, idx0=1, noise_sigma=sig, seed=seed,
+                               t_dist=(t_dist if disturbance_ and t_dist <= T else 0), amplitude_dist=amplitude_dist,
+                               xwidth=plant.slider_params["xwidth"])
+        xl, ul, st = r["x_log"], r["u_log"], r["status_log"]
+        tr = (lambda a: a.permute(1, 0, 2)) if on_dev else (lambda a: np.transpose(a, (1, 0, 2)))
+        xl, ul = tr(xl), tr(ul)
+        found = (st == 0).T if not on_dev else (st == 0).t()
+        return xl[..., 0], xl[..., 1], xl[..., 2], xl[..., 3], ul[..., 0], ul[..., 1], time_sim_vec, found
+
+    @staticmethod
+    def _is_cuda(a):
+        try:
+            import torch
+            return isinstance(a, torch.Tensor) and a.is_cuda
+        except ImportError:
+            return False
 
     @staticmethod
     def closed_loop_matlab(plant, controller, x0, time_sim, print_=False, sim_noise=False, debug_cost=False,
