@@ -274,6 +274,23 @@ def run_ours(args):
         lat_b1[tag] = {"p50_ms": ts[len(ts) // 2], "p99_ms": ts[min(len(ts) - 1, int(0.99 * len(ts)))], "solves": len(ts),
                        "sqp_iter": int(s1.get_int("sqp_iter")[0])}
         del s1
+    # Monte-Carlo of whole pushes, device-resident (qspush_closed_loop): the same batch in closed loop for 20 control
+    # periods, nothing crosses PCIe inside the loop (extra information, not the contract's e2e)
+    loop_info = None
+    if world == 1:
+        Tn = 64
+        traj = np.zeros((Tn, 6)); traj[:, 0] = 0.01 * DT * np.arange(Tn)
+        off = np.zeros((B, 6)); off[:, :2] = wl["x0"][:, :2]
+        trd, ofd = torch.from_numpy(traj).to(dev), torch.from_numpy(off).to(dev)
+        for rep in range(2):
+            xd = torch.from_numpy(wl["x0"].copy()).to(dev)
+            solver.set_int("cold", torch.ones(B, dtype=torch.int32, device=dev)); solver.sync()
+            t0 = time.perf_counter()
+            rl = solver.closed_loop(trd, xd, 20, offset=ofd); solver.sync()
+            tl = time.perf_counter() - t0
+        loop_info = {"periods": 20, "instances": B, "ms_per_period": 1e3 * tl / 20, "controller_solves_per_s": B * 20 / tl,
+                     "status_ok_frac": float((rl["status_log"] == 0).float().mean()),
+                     "what": "qspush_closed_loop: reference window, prepare, solve, plant step, shift per period on the device"}
     cores = os.cpu_count() or 1
     cpu_base = None
     if world == 1:                                           # the CPU baseline is timed on rank 0 of the N = 1 run only
@@ -307,6 +324,7 @@ def run_ours(args):
         "latency_ms": {"p50": srt[len(srt) // 2], "p99": srt[min(len(srt) - 1, int(0.99 * len(srt)))], "max": srt[-1],
                        "what": "per-step device time of one batched solve (all instances of the batch finish together)"},
         "latency_b1": lat_b1,
+        "closed_loop_device": loop_info,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
