@@ -148,21 +148,28 @@ __device__ unsigned long long qw_prof[16];
 //     access is a compile-time immediate offset from the record pointer (no integer address arithmetic), and the odd
 //     record stride makes the 64-bit accesses of a half-warp conflict-free;
 //   * tensor memory (TMEM): the read-only linearisation of the stage (A, B, b, h, g: 29 doubles, padded to
-//     QW_TM_STAGE = 32) sits in the lane's own TMEM lane, 64 columns per local stage, written once per problem and
+//     32) sits in the lane's own TMEM lane, written once per problem and
 //     read back with tcgen05.ld.  TMEM is otherwise idle in this kernel; moving these rows out of the records brings
 //     the record from 101 to 73 doubles, i.e. 8 instead of 6 resident problems per SM at N = 40 (shared memory is
 //     what bounds the number of resident warps).
 enum : int {
     R_Z = 0, R_PIK = 6, R_LAM = 10, R_T = 16,                                      // point (22): z, pi_k, lam, t
-    R_RG = 22, R_RB = 28, R_K = 32, R_LI = 40, R_P = 43, R_PB = 53, R_DZA = 57,    // residuals, factor, P_k, P_{k+1} r_b, affine step
-    R_GT = 60, R_PV = 66, R_KFF = 70,                                              // rhs / step (aliased), p_k, k_ff
-    R_ROWS = 73
+    R_RG = 22, R_RB = 28,                                                          // residuals
+    R_K = 32, R_LI = 40, R_DZA = 43, R_PV = 46, R_KFF = 50,                        // factor, affine step, p_k, k_ff: 20 rows that are dead during the element scan
+    R_GT = 52,                                                                     // rhs / step (aliased)
+    R_P = 58, R_PB = 68,                                                           // P_k, P_{k+1} r_b (long horizons: in TMEM instead)
+    R_ROWS = 73, R_ROWS_LONG = 59
 };
+// Long horizons (C >= 3: N >= 64) are the most shared-memory-starved configurations (3 resident problems per SM at
+// N = 100), and with at most 4 warps per CTA each warp owns a full TMEM lane quarter (512 columns): P_k and
+// P_{k+1} r_b move to TMEM as well, the record shrinks to 59 rows (4 problems per SM at N = 100).
+QS_HD constexpr int qw_rows(int C) { return C >= 3 ? R_ROWS_LONG : R_ROWS; }
 // offsets (doubles) inside the TMEM block of one local stage
 // (linearisation 0..31, written once per problem; 32..47 rewritten every IPM iteration in phase (2): the slack
 // reciprocals 1/t_l, 1/t_u and the barrier diagonal D = lam_l/t_l + lam_u/t_u, reused by phases (4)-(8) — 30 FP64
-// divisions per stage and iteration become 6)
-enum : int { QW_TM_AB = 0, QW_TM_BV = 16, QW_TM_HH = 20, QW_TM_G = 24, QW_TM_IT = 32, QW_TM_D = 40, QW_TM_STAGE = 48 };
+// divisions per stage and iteration become 6; 48..63, long horizons only: P_k (10) and P_{k+1} r_b (4))
+enum : int { QW_TM_AB = 0, QW_TM_BV = 16, QW_TM_HH = 20, QW_TM_G = 24, QW_TM_IT = 32, QW_TM_D = 40, QW_TM_P = 48, QW_TM_STAGE = 48, QW_TM_STAGE_LONG = 64 };
+QS_HD constexpr int qw_tm_stage(int C) { return C >= 3 ? QW_TM_STAGE_LONG : QW_TM_STAGE; }
 QS_HD constexpr int qp_warp_chunk(int N) { return (N + 1 + 31) / 32; }
 QS_HD constexpr int qp_warp_lanes(int N, int C) { return (N + 1 + C - 1) / C; }
 // Exchange areas of the warp scans.  Affine maps (M 16, d 4): a dedicated area behind the records, odd stride 21 per
@@ -171,7 +178,7 @@ QS_HD constexpr int qp_warp_lanes(int N, int C) { return (N + 1 + C - 1) / C; }
 constexpr int QW_XA = 21, QW_XE = 37;
 QS_HD constexpr size_t qp_warp_smem_doubles(int N) {
     const int C = qp_warp_chunk(N), L = qp_warp_lanes(N, C);
-    return (size_t)R_ROWS * C * L + (size_t)QW_XA * L + (C >= 2 ? 0 : (size_t)QW_XE * L);
+    return (size_t)qw_rows(C) * C * L + (size_t)QW_XA * L + (C >= 2 ? 0 : (size_t)QW_XE * L);
 }
 
 // ---- small dense helpers --------------------------------------------------------------------------
@@ -367,22 +374,22 @@ QS_HD IneqStep ineq_step(double v, double dva, double dv, double ll, double lu, 
     return s;
 }
 
-#define QW_SM(row, j) sm[((size_t)(j) * Lw_ + lane) * R_ROWS + (row)]
+#define QW_SM(row, j) sm[((size_t)(j) * Lw_ + lane) * qw_rows(C) + (row)]
 
-// A_k (columns 3, 4) and B_k of local stage j from the lane's TMEM block (warp-collective: every lane calls it)
+// A_k (columns 3, 4) and B_k of the local stage whose TMEM block starts at `base` (warp-collective: every lane calls it)
 template <class Ctx>
-QS_HD void qw_ld_lin(const Ctx& w, int j, StageLin& L) {
+QS_HD void qw_ld_lin(const Ctx& w, int base, StageLin& L) {
     double v[16];
-    w.template tm_ld<16>(j * QW_TM_STAGE + QW_TM_AB, v);
+    w.template tm_ld<16>(base + QW_TM_AB, v);
 #pragma unroll
     for (int i = 0; i < 4; ++i) { L.a3[i] = v[i]; L.a4[i] = v[4 + i]; L.b1[i] = v[8 + i]; L.b2[i] = v[12 + i]; }
 }
 // 1/t_l (0..2) and 1/t_u (4..6) of local stage j, as left by phase (2) of the current iteration
 template <class Ctx>
-QS_HD void qw_ld_it(const Ctx& w, int j, double* it8) { w.template tm_ld<8>(j * QW_TM_STAGE + QW_TM_IT, it8); }
+QS_HD void qw_ld_it(const Ctx& w, int base, double* it8) { w.template tm_ld<8>(base + QW_TM_IT, it8); }
 // h_k (3 values) at the linearisation point and beta_k = v_bound'(s_k) (0 unless h_variant 1): 4 doubles
 template <class Ctx>
-QS_HD void qw_ld_h(const Ctx& w, int j, double* h4) { w.template tm_ld<4>(j * QW_TM_STAGE + QW_TM_HH, h4); }
+QS_HD void qw_ld_h(const Ctx& w, int base, double* h4) { w.template tm_ld<4>(base + QW_TM_HH, h4); }
 // value of constraint row c on a stage vector z6 = [u_n, u_t, x, y, theta, s]
 // (the coupling term sits behind a warp-uniform branch: the default constraint set pays nothing for it)
 QS_HD double qw_row(int hv, int c, double beta, const double* z6) {
@@ -413,7 +420,9 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_) 
         for (int j = C - 1; j >= 0; --j) {
             const int k = lane * C + j;
             StageLin L;
-            qw_ld_lin(w, j, L);
+            double Pst[16];
+            qw_ld_lin(w, j * qw_tm_stage(C), L);
+            if constexpr (C >= 3) w.template tm_ld<16>(j * qw_tm_stage(C) + QW_TM_P, Pst);
             if (!act || k > N) continue;
             if (k == N) {                                       // terminal: p_N = rg_N (constant map)
 #pragma unroll
@@ -427,7 +436,7 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_) 
 #pragma unroll
             for (int i = 0; i < 6; ++i) gt[i] = QW_SM(R_GT + i, j);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { Pb[i] = QW_SM(R_PB + i, j); K0[i] = QW_SM(R_K + i, j); K1[i] = QW_SM(R_K + 4 + i, j); }
+            for (int i = 0; i < 4; ++i) { if constexpr (C >= 3) Pb[i] = Pst[10 + i]; else Pb[i] = QW_SM(R_PB + i, j); K0[i] = QW_SM(R_K + i, j); K1[i] = QW_SM(R_K + 4 + i, j); }
 #pragma unroll
             for (int i = 0; i < 3; ++i) Li[i] = QW_SM(R_LI + i, j);
             lin_T_mul_add(L, Pb, gt, m);
@@ -453,7 +462,7 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_) 
         }
     }
     // ---- (b) suffix scan over lanes (exchange through shared memory); afterwards d = p at the first stage of the chunk
-    double* xa = sm + (size_t)R_ROWS * C * Lw_ + (size_t)lane * QW_XA;      // this lane's affine exchange slot
+    double* xa = sm + (size_t)qw_rows(C) * C * Lw_ + (size_t)lane * QW_XA;      // this lane's affine exchange slot
 #pragma unroll 1
     for (int dl = 1; dl < Lw_; dl <<= 1) {
         w.sync();
@@ -483,7 +492,7 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_) 
         for (int j = C - 1; j >= 0; --j) {
             const int k = lane * C + j;
             StageLin L;
-            qw_ld_lin(w, j, L);
+            qw_ld_lin(w, j * qw_tm_stage(C), L);
             if (!act || k > N) continue;
             if (k == N) {
 #pragma unroll
@@ -520,7 +529,7 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_) 
         for (int j = 0; j < C; ++j) {
             const int k = lane * C + j;
             StageLin L;
-            qw_ld_lin(w, j, L);
+            qw_ld_lin(w, j * qw_tm_stage(C), L);
             if (!act || k >= N) continue;
             double K0[4], K1[4], Ab[16], bb[4];
 #pragma unroll
@@ -565,7 +574,7 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_) 
         for (int j = 0; j < C; ++j) {
             const int k = lane * C + j;
             StageLin L;
-            qw_ld_lin(w, j, L);
+            qw_ld_lin(w, j * qw_tm_stage(C), L);
             if (!act || k > N) continue;
             if (k == N) {
                 QW_SM(R_GT + 0, j) = 0.0; QW_SM(R_GT + 1, j) = 0.0;
@@ -605,9 +614,9 @@ QS_HD void qw_init(const Ctx& w, double* __restrict__ sm, const QpConst& Q, cons
     for (int j = 0; j < C; ++j) {
         const int k = lane * C + j;
         const bool on = act && k < N;
-        double v[QW_TM_STAGE];
+        double v[32];
 #pragma unroll
-        for (int i = 0; i < QW_TM_STAGE; ++i) v[i] = 0.0;
+        for (int i = 0; i < 32; ++i) v[i] = 0.0;
         if (act && k <= N) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) QW_SM(R_Z + i, j) = 0.0;
@@ -626,8 +635,8 @@ QS_HD void qw_init(const Ctx& w, double* __restrict__ sm, const QpConst& Q, cons
 #pragma unroll
             for (int i = 0; i < 4; ++i) v[QW_TM_HH + i] = QS_AT(V.hv, k, 4, i);     // h_k (3) and v_bound'(s_k)
         }
-        w.tm_st16(j * QW_TM_STAGE, v);                      // warp-collective: every lane stores (zeros when idle)
-        w.tm_st16(j * QW_TM_STAGE + 16, v + 16);
+        w.tm_st16(j * qw_tm_stage(C), v);                      // warp-collective: every lane stores (zeros when idle)
+        w.tm_st16(j * qw_tm_stage(C) + 16, v + 16);
         if (on) {
             const double* h = v + QW_TM_HH;
             if (k == 0) {
@@ -679,8 +688,8 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
     if (act && lane + 1 < Lw_) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            nx[i] = sm[((size_t)lane + 1) * R_ROWS + R_Z + 2 + i];      // record (j = 0, lane + 1)
-            npi[i] = sm[((size_t)lane + 1) * R_ROWS + R_PIK + i];
+            nx[i] = sm[((size_t)lane + 1) * qw_rows(C) + R_Z + 2 + i];      // record (j = 0, lane + 1)
+            npi[i] = sm[((size_t)lane + 1) * qw_rows(C) + R_PIK + i];
         }
     }
     double l_stat = 0.0, l_eq = 0.0, l_in = 0.0, l_cp = 0.0, l_mu = 0.0;
@@ -691,10 +700,10 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             const int k = lane * C + j;
             StageLin L;
             double gk[8], hk[4], bv[4];
-            qw_ld_lin(w, j, L);
-            w.template tm_ld<8>(j * QW_TM_STAGE + QW_TM_G, gk);
-            w.template tm_ld<4>(j * QW_TM_STAGE + QW_TM_HH, hk);
-            w.template tm_ld<4>(j * QW_TM_STAGE + QW_TM_BV, bv);
+            qw_ld_lin(w, j * qw_tm_stage(C), L);
+            w.template tm_ld<8>(j * qw_tm_stage(C) + QW_TM_G, gk);
+            w.template tm_ld<4>(j * qw_tm_stage(C) + QW_TM_HH, hk);
+            w.template tm_ld<4>(j * qw_tm_stage(C) + QW_TM_BV, bv);
             if (!act || k > N) continue;
             double z6[6], pik[4];
 #pragma unroll
@@ -766,8 +775,8 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             const int k = lane * C + j;
             StageLin L;
             double hk[4];
-            qw_ld_lin(w, j, L);
-            qw_ld_h(w, j, hk);
+            qw_ld_lin(w, j * qw_tm_stage(C), L);
+            qw_ld_h(w, j * qw_tm_stage(C), hk);
             // barrier terms first: slack reciprocals and D go to the TMEM block (warp-collective store), affine rhs to R_GT
             double it8[8], D[4];
 #pragma unroll
@@ -795,8 +804,8 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
 #pragma unroll
                 for (int i = 0; i < 6; ++i) QW_SM(R_GT + i, j) = gt[i];
             }
-            w.template tm_st<8>(j * QW_TM_STAGE + QW_TM_IT, it8);
-            w.template tm_st<4>(j * QW_TM_STAGE + QW_TM_D, D);
+            w.template tm_st<8>(j * qw_tm_stage(C) + QW_TM_IT, it8);
+            w.template tm_st<4>(j * qw_tm_stage(C) + QW_TM_D, D);
             if (!act || k > N) continue;
             if (k == N) {                                   // terminal value function: J = Q_N, A = 0, C = 0
 #pragma unroll
@@ -843,9 +852,9 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
     QW_TICK(2);
     // ================= (3) suffix scan of the chunk aggregates =================
     // exchange slots of this lane: A (16) and C, J (10 + 10)
-    double* xeA = (C >= 2) ? &QW_SM(R_K, 0) : sm + (size_t)R_ROWS * C * Lw_ + (size_t)QW_XA * Lw_ + (size_t)lane * QW_XE;
+    double* xeA = (C >= 2) ? &QW_SM(R_K, 0) : sm + (size_t)qw_rows(C) * C * Lw_ + (size_t)QW_XA * Lw_ + (size_t)lane * QW_XE;
     double* xeCJ = (C >= 2) ? &QW_SM(R_K, (C >= 2 ? 1 : 0)) : xeA + 16;
-    const size_t xstride = (C >= 2) ? (size_t)R_ROWS : (size_t)QW_XE;     // distance between neighbouring lanes' slots
+    const size_t xstride = (C >= 2) ? (size_t)qw_rows(C) : (size_t)QW_XE;     // distance between neighbouring lanes' slots
 #pragma unroll 1
     for (int dl = 1; dl < Lw_; dl <<= 1) {
         w.sync();
@@ -879,25 +888,38 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             const int k = lane * C + j;
             StageLin L;
             double D[4];
-            qw_ld_lin(w, j, L);
-            w.template tm_ld<4>(j * QW_TM_STAGE + QW_TM_D, D);
-            if (!act || k > N) continue;
-            if (k == N) {
+            qw_ld_lin(w, j * qw_tm_stage(C), L);
+            w.template tm_ld<4>(j * qw_tm_stage(C) + QW_TM_D, D);
+            double Pst[16];                                 // P_k (10), P_{k+1} r_b (4): to shared memory, or to TMEM on long horizons
 #pragma unroll
-                for (int i = 0; i < 10; ++i) { P[i] = Q.QN[i]; QW_SM(R_P + i, j) = P[i]; }
-                continue;
+            for (int i = 0; i < 16; ++i) Pst[i] = 0.0;
+            if (act && k <= N) {
+                if (k == N) {
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) P[i] = Q.QN[i];
+                } else {
+                    double rb[4], Pb[4], K0[4], K1[4], Li[3];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) rb[i] = QW_SM(R_RB + i, j);
+                    sym4_mul(P, rb, Pb);
+                    ok = riccati_factor_stage(L, Q.H + (size_t)k * 21, D, P, K0, K1, Li, D[3]) && ok;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { QW_SM(R_K + i, j) = K0[i]; QW_SM(R_K + 4 + i, j) = K1[i]; Pst[10 + i] = Pb[i]; }
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) QW_SM(R_LI + i, j) = Li[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 10; ++i) Pst[i] = P[i];
+                if constexpr (C < 3) {
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) QW_SM(R_P + i, j) = Pst[i];
+                    if (k < N) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) QW_SM(R_PB + i, j) = Pst[10 + i];
+                    }
+                }
             }
-            double rb[4], Pb[4], K0[4], K1[4], Li[3];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) rb[i] = QW_SM(R_RB + i, j);
-            sym4_mul(P, rb, Pb);
-            ok = riccati_factor_stage(L, Q.H + (size_t)k * 21, D, P, K0, K1, Li, D[3]) && ok;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { QW_SM(R_K + i, j) = K0[i]; QW_SM(R_K + 4 + i, j) = K1[i]; QW_SM(R_PB + i, j) = Pb[i]; }
-#pragma unroll
-            for (int i = 0; i < 3; ++i) QW_SM(R_LI + i, j) = Li[i];
-#pragma unroll
-            for (int i = 0; i < 10; ++i) QW_SM(R_P + i, j) = P[i];
+            if constexpr (C >= 3) w.tm_st16(j * qw_tm_stage(C) + QW_TM_P, Pst);     // warp-collective
         }
     }
     if (w.wany(ok ? 0 : 1)) { status = 2; return 1; }
@@ -912,8 +934,8 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             for (int j = 0; j < C; ++j) {
                 const int k = lane * C + j;
                 double hk[4], it8[8];
-                qw_ld_h(w, j, hk);
-                qw_ld_it(w, j, it8);
+                qw_ld_h(w, j * qw_tm_stage(C), hk);
+                qw_ld_it(w, j * qw_tm_stage(C), it8);
                 if (!act || k >= N) continue;
                 double gt[6], z6[6];
 #pragma unroll
@@ -944,8 +966,8 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                 for (int j = 0; j < C; ++j) {
                     const int k = lane * C + j;
                     double hk[4], it8[8];
-                    qw_ld_h(w, j, hk);
-                    qw_ld_it(w, j, it8);
+                    qw_ld_h(w, j * qw_tm_stage(C), hk);
+                    qw_ld_it(w, j * qw_tm_stage(C), it8);
                     if (!act || k >= N) continue;
                     double z6[6], dz6[6];
 #pragma unroll
@@ -981,8 +1003,8 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
         for (int j = 0; j < C; ++j) {
             const int k = lane * C + j;
             double hk[4], it8[8];
-            qw_ld_h(w, j, hk);
-            qw_ld_it(w, j, it8);
+            qw_ld_h(w, j * qw_tm_stage(C), hk);
+            qw_ld_it(w, j * qw_tm_stage(C), it8);
             if (!act || k >= N) continue;
             double z6[6], dz6[6];
 #pragma unroll
@@ -1005,9 +1027,10 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
 #pragma unroll 1
         for (int j = 0; j < C; ++j) {
             const int k = lane * C + j;
-            double hk[4], it8[8];
-            qw_ld_h(w, j, hk);
-            qw_ld_it(w, j, it8);
+            double hk[4], it8[8], Pst[16];
+            qw_ld_h(w, j * qw_tm_stage(C), hk);
+            qw_ld_it(w, j * qw_tm_stage(C), it8);
+            if constexpr (C >= 3) w.template tm_ld<16>(j * qw_tm_stage(C) + QW_TM_P, Pst);
             if (!act || k > N) continue;
             double dz[6];
 #pragma unroll
@@ -1015,7 +1038,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             if (k >= 1) {                                   // dpi_k = P_k dx_k + p_k
                 double Pk[10], dxk[4] = {dz[2], dz[3], dz[4], dz[5]}, dp[4];
 #pragma unroll
-                for (int i = 0; i < 10; ++i) Pk[i] = QW_SM(R_P + i, j);
+                for (int i = 0; i < 10; ++i) { if constexpr (C >= 3) Pk[i] = Pst[i]; else Pk[i] = QW_SM(R_P + i, j); }
                 sym4_mul(Pk, dxk, dp);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) QW_SM(R_PIK + i, j) = fma(alpha, dp[i] + QW_SM(R_PV + i, j), QW_SM(R_PIK + i, j));

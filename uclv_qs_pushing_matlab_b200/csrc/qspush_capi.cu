@@ -558,7 +558,7 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
     const int pwd = (int)((qp_warp_smem_doubles(s->N) + 1) / 2 * 2);
     const size_t smem_cap = 227 * 1024 - 1024;                                       // static __shared__ + reserve
     int W = (int)std::min<size_t>(QW_MAX_WARPS, smem_cap / ((size_t)pwd * sizeof(double)));
-    if (C * QW_TM_STAGE > 128) W = std::min(W, 4);          // more than 256 TMEM columns per warp: one warp per lane quarter
+    if (C * qw_tm_stage(C) > 128) W = std::min(W, 4);          // more than 256 TMEM columns per warp: one warp per lane quarter
     const bool warp = want_warp && C <= 4 && W >= 2;
     if (!warp && s->opts.qp_kernel == 2 && s->opts.problems_per_warp == 0) ppw = (s->B >= 12288) ? 32 : ppw;
     if (!warp) {
