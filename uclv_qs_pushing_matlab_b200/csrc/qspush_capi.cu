@@ -7,6 +7,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <climits>
 #include <vector>
 
 #include "../../include/qspush.h"
@@ -546,10 +547,11 @@ int qspush_prepare(qspush_solver* s) {
 // parallel-in-time; 0 = one problem per thread (any horizon)
 static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, int ppw, int apply) {
     const int C = qp_warp_chunk(s->N);
-    // auto (2): the warp-per-problem kernel wins until the batch is large enough for the one-problem-per-thread
-    // kernel to fill the GPU.  Measured crossovers on B200: N = 40: ~50k problems (2.2M it/s flat
-    // from 8k on vs 0.4M -> 2.3M it/s); N = 10 and N = 100: between 4k and 32k
-    const int warp_below = (C == 2) ? 49152 : 16384;
+    // auto (2): measured on B200 (tools/gpu_kernel_compare.py) the warp-per-problem kernel wins at every
+    // batch size for C >= 2 (N = 40: 2.0M it/s at 4096, 2.46M at 65536 vs 0.39M / 2.25M; N = 100: 0.97M / 1.09M vs
+    // 0.19M / 1.01M); short horizons (C = 1, N <= 31) leave two thirds of a warp idle, there the one-problem-per-thread
+    // kernel takes over once the batch fills the GPU (N = 10: 4.0M vs 2.1M at 4096, 4.7M vs 7.2M at 65536)
+    const int warp_below = (C >= 2) ? INT_MAX : 12288;
     // full SQP (apply == 0): always the warp kernel — its work queue skips the problems that already finished, while
     // the thread kernel keeps mostly idle warps alive (config 5 share, 32 768 x N = 100: 0.87 s vs 2.3 s)
     const bool want_warp = s->opts.qp_kernel == 1 || (s->opts.qp_kernel == 2 && (s->B < warp_below || D.h_variant || !apply));
