@@ -6,12 +6,14 @@
  * (SURVEY.md section 8c).  It is the binding a maintainer of the reference adds; see INTEGRATION.md.
  *
  *   h  = qspush_mex('model_from_ply', ply_path, flip, degree, mu_sg, mu_sp, m, tau_max)
- *   s  = qspush_mex('solver_create', h_model, N, dt, batch, device, mode)        % mode 0 = sqp_rti, 1 = sqp
+ *   s  = qspush_mex('solver_create', h_model, N, dt, batch, device, mode [, h_variant])   % mode 0 = sqp_rti, 1 = sqp;
+ *                                                    % h_variant 1 = h = [u_n; u_t -+ v_bound(s)] (NMPC_controller.m:238)
  *        qspush_mex('set', s, field_id, stage, data)      % data: dim x stages x batch (column-major == C-ABI layout)
  *   v  = qspush_mex('get', s, field_id, stage, nrows, ncols)
  *   v  = qspush_mex('get_int', s, field_id)
  *        qspush_mex('prepare', s) ; qspush_mex('solve', s) ; qspush_mex('shift', s)
  *   t  = qspush_mex('stat', s, which)
+ *   [x, xlog, ulog] = qspush_mex('closed_loop', s, traj(6 x T), x0(4 x batch), steps)   % device-resident helper.closed_loop_matlab
  *        qspush_mex('solver_free', s) ; qspush_mex('model_free', h)
  */
 #include <string.h>
@@ -34,6 +36,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     } else if (!strcmp(cmd, "solver_create")) {
         const qspush_model* m = (const qspush_model*)hnd(prhs[1]);
         qspush_opts o; qspush_opts_default(&o); o.mode = (int)mxGetScalar(prhs[6]);
+        if (nrhs > 7) o.h_variant = (int)mxGetScalar(prhs[7]);
         qspush_solver* s = NULL;
         chk(qspush_solver_create(&m, 1, (int)mxGetScalar(prhs[2]), mxGetScalar(prhs[3]), (int)mxGetScalar(prhs[4]), (int)mxGetScalar(prhs[5]), &o, &s));
         plhs[0] = mkh(s);
@@ -54,6 +57,20 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     else if (!strcmp(cmd, "solve")) chk(qspush_solve((qspush_solver*)hnd(prhs[1])));
     else if (!strcmp(cmd, "shift")) chk(qspush_shift((qspush_solver*)hnd(prhs[1])));
     else if (!strcmp(cmd, "stat")) { double v = 0; chk(qspush_get_stat((qspush_solver*)hnd(prhs[1]), (qspush_stat)(int)mxGetScalar(prhs[2]), &v)); plhs[0] = mxCreateDoubleScalar(v); }
+    else if (!strcmp(cmd, "closed_loop")) {
+        /* traj is 6 x T column-major == [T][6]; x0 is 4 x batch == [batch][4]: the C-ABI layouts */
+        qspush_solver* s = (qspush_solver*)hnd(prhs[1]);
+        const mwSize T = mxGetDimensions(prhs[2])[1], batch = mxGetDimensions(prhs[3])[1];
+        const int steps = (int)mxGetScalar(prhs[4]);
+        qspush_loop_opts lo; memset(&lo, 0, sizeof lo); lo.idx0 = 1;
+        plhs[0] = mxCreateDoubleMatrix(4, batch, mxREAL);
+        memcpy(mxGetPr(plhs[0]), mxGetPr(prhs[3]), sizeof(double) * 4 * batch);
+        mxArray* xl = mxCreateDoubleMatrix(4 * batch, (mwSize)steps, mxREAL);
+        mxArray* ul = mxCreateDoubleMatrix(2 * batch, (mwSize)steps, mxREAL);
+        chk(qspush_closed_loop(s, mxGetPr(prhs[2]), (int)T, NULL, mxGetPr(plhs[0]), steps, &lo, mxGetPr(xl), mxGetPr(ul), NULL, QSPUSH_MEM_HOST));
+        if (nlhs > 1) plhs[1] = xl;
+        if (nlhs > 2) plhs[2] = ul;
+    }
     else if (!strcmp(cmd, "solver_free")) qspush_solver_free((qspush_solver*)hnd(prhs[1]));
     else if (!strcmp(cmd, "model_free")) qspush_model_free((qspush_model*)hnd(prhs[1]));
     else mexErrMsgIdAndTxt("qspush:usage", "unknown command %s", cmd);

@@ -104,3 +104,14 @@ def test_product_never_touches_the_oracle():
     import subprocess
     out = subprocess.run(["ldd", L.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out and "hostsim" not in out
+
+
+def test_mex_gateway_compiles_against_the_header():
+    """matlab/qspush_mex.c (the binding INTEGRATION.md hands to a maintainer of the reference) is type-checked against
+    include/qspush.h with a stub of the MEX API: MATLAB itself does not exist in this container."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror=implicit-function-declaration", "-Werror=incompatible-pointer-types",
+                        "-fsyntax-only", "-I" + os.path.join(root, "tests", "stubs"), "-I" + os.path.join(root, "include"),
+                        os.path.join(root, "matlab", "qspush_mex.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
