@@ -7,6 +7,7 @@
 // the package never loads it.
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -92,9 +93,15 @@ static void emu_run(void (*body)(int, void*), void* arg) {
         e.sp[l] = p;
     }
     g_emu = &e;
+    // lane scheduling order between two collectives: ascending by default, descending with HS_EMU_REVERSE=1.  Code that
+    // is correctly synchronised gives bit-identical results under both (a poor man's racecheck for the shared-memory
+    // exchanges: a missing warp sync shows up as an order dependence)
+    const char* rev_env = std::getenv("HS_EMU_REVERSE");
+    const bool rev = rev_env && rev_env[0] == '1';
     for (;;) {
         bool any = false;
-        for (int l = 0; l < WarpEmu::W; ++l) {
+        for (int li = 0; li < WarpEmu::W; ++li) {
+            const int l = rev ? WarpEmu::W - 1 - li : li;
             if (e.done[l]) continue;
             any = true; e.cur = l;
             qs_ctx_switch(&e.main_sp, e.sp[l]);
