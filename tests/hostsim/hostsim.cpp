@@ -124,17 +124,22 @@ struct WarpCtxHost {
         return e->xbuf[p];
     }
     double shfl(double v, int src) const { return exchange(v)[src & 31]; }
-    template <class F> double butterfly(double v, F f) const {
+    template <int SEG, class F> double butterfly(double v, F f) const {
         const double* b = exchange(v);
         double t[32], u[32];
         for (int i = 0; i < 32; ++i) t[i] = b[i];
-        for (int o = 16; o > 0; o >>= 1) { for (int i = 0; i < 32; ++i) u[i] = f(t[i], t[i ^ o]); for (int i = 0; i < 32; ++i) t[i] = u[i]; }
+        for (int o = SEG / 2; o > 0; o >>= 1) { for (int i = 0; i < 32; ++i) u[i] = f(t[i], t[i ^ o]); for (int i = 0; i < 32; ++i) t[i] = u[i]; }
         return t[lane_];
     }
-    double wmax(double v) const { return butterfly(v, [](double a, double b) { return fmax(a, b); }); }
-    double wmin(double v) const { return butterfly(v, [](double a, double b) { return fmin(a, b); }); }
-    double wsum(double v) const { return butterfly(v, [](double a, double b) { return a + b; }); }
-    int wany(int p) const { const double* b = exchange(p ? 1.0 : 0.0); for (int i = 0; i < 32; ++i) if (b[i] != 0.0) return 1; return 0; }
+    template <int SEG = 32> double wmax(double v) const { return butterfly<SEG>(v, [](double a, double b) { return fmax(a, b); }); }
+    template <int SEG = 32> double wmin(double v) const { return butterfly<SEG>(v, [](double a, double b) { return fmin(a, b); }); }
+    template <int SEG = 32> double wsum(double v) const { return butterfly<SEG>(v, [](double a, double b) { return a + b; }); }
+    template <int SEG = 32> int wany(int p) const {
+        const double* b = exchange(p ? 1.0 : 0.0);
+        const int lo = lane_ & ~(SEG - 1);
+        for (int i = lo; i < lo + SEG; ++i) if (b[i] != 0.0) return 1;
+        return 0;
+    }
     void sync() const { exchange(0.0); }
     bool cta_all(bool pred) const { return pred; }      // one emulated warp per CTA
     // tensor-memory block of the lane (tcgen05.ld / tcgen05.st on the device; warp-collective there, so the emulator
@@ -144,28 +149,35 @@ struct WarpCtxHost {
     void tm_st16(int off, const double* v) const { sync(); for (int i = 0; i < 16; ++i) g_emu->tm[lane_][off + i] = v[i]; }
 };
 
-struct WarpJob { const SolverDev* S; const IpmOpts* io; int b; int apply; double* sm; int C; int handed[32]; };
+struct WarpJob { const SolverDev* S; const IpmOpts* io; int b[2]; int apply; double* sm; int per_problem; int C; int seg16; int handed[32]; };
 static void warp_job_body(int lane, void* arg) {
     WarpJob* j = (WarpJob*)arg;
     WarpCtxHost w{lane};
-    // work queue of the emulated warp: exactly one problem (every lane sees the same sequence b, -1)
-    auto next = [j, lane]() -> int { return j->handed[lane]++ == 0 ? j->b : -1; };
+    // work queue of the emulated warp: exactly one fetch (every lane of a segment sees the same sequence b, -1)
+    auto next = [j, lane](int seg) -> int { return j->handed[lane]++ == 0 ? j->b[seg] : -1; };
     const int hv = j->S->h_variant ? 1 : 0;
+    if (j->seg16) {
+        if (hv) qp_warp_persistent<WarpCtxHost, 1, 1, 16>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next);
+        else qp_warp_persistent<WarpCtxHost, 1, 0, 16>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next);
+        return;
+    }
     switch (j->C * 2 + hv) {
-        case 2: qp_warp_persistent<WarpCtxHost, 1, 0>(w, j->sm, *j->S, *j->io, j->apply, next); break;
-        case 3: qp_warp_persistent<WarpCtxHost, 1, 1>(w, j->sm, *j->S, *j->io, j->apply, next); break;
-        case 4: qp_warp_persistent<WarpCtxHost, 2, 0>(w, j->sm, *j->S, *j->io, j->apply, next); break;
-        case 5: qp_warp_persistent<WarpCtxHost, 2, 1>(w, j->sm, *j->S, *j->io, j->apply, next); break;
-        case 6: qp_warp_persistent<WarpCtxHost, 3, 0>(w, j->sm, *j->S, *j->io, j->apply, next); break;
-        case 7: qp_warp_persistent<WarpCtxHost, 3, 1>(w, j->sm, *j->S, *j->io, j->apply, next); break;
-        case 8: qp_warp_persistent<WarpCtxHost, 4, 0>(w, j->sm, *j->S, *j->io, j->apply, next); break;
-        default: qp_warp_persistent<WarpCtxHost, 4, 1>(w, j->sm, *j->S, *j->io, j->apply, next); break;
+        case 2: qp_warp_persistent<WarpCtxHost, 1, 0, 32>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
+        case 3: qp_warp_persistent<WarpCtxHost, 1, 1, 32>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
+        case 4: qp_warp_persistent<WarpCtxHost, 2, 0, 32>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
+        case 5: qp_warp_persistent<WarpCtxHost, 2, 1, 32>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
+        case 6: qp_warp_persistent<WarpCtxHost, 3, 0, 32>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
+        case 7: qp_warp_persistent<WarpCtxHost, 3, 1, 32>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
+        case 8: qp_warp_persistent<WarpCtxHost, 4, 0, 32>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
+        default: qp_warp_persistent<WarpCtxHost, 4, 1, 32>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
     }
 }
-// mirrors k_qp_warp: one emulated warp per problem
-static void qp_warp_host(const SolverDev& S, const IpmOpts& io, int b, int apply) {
-    std::vector<double> sm(qp_warp_smem_doubles(S.N), 0.0);
-    WarpJob j{&S, &io, b, apply, sm.data(), qp_warp_chunk(S.N), {0}};
+// mirrors k_qp_warp: one emulated warp per problem, or per pair of problems on short horizons (N <= 15; b1 = -1: odd tail)
+static bool qp_warp_pairs(int N) { return qp_warp_chunk(N) == 1 && N + 1 <= 16; }
+static void qp_warp_host(const SolverDev& S, const IpmOpts& io, int b0, int b1, int apply) {
+    const int pwd = (int)((qp_warp_smem_doubles(S.N) + 1) / 2 * 2);
+    std::vector<double> sm((size_t)pwd * 2, 0.0);
+    WarpJob j{&S, &io, {b0, b1}, apply, sm.data(), pwd, qp_warp_chunk(S.N), qp_warp_pairs(S.N) ? 1 : 0, {0}};
     emu_run(warp_job_body, &j);
 }
 
@@ -321,12 +333,19 @@ struct HostRun {
     void out(const std::vector<double>& src, double* dst, int R) const { if (!dst) return; for (int b = 0; b < nb; ++b) for (int r = 0; r < R; ++r) dst[(size_t)b * R + r] = src[(size_t)r * Bp + b]; }
     const double* Mall() const { return blobs.data(); }
     void prepare() { for (int b = 0; b < nb; ++b) prepare_one(S, cp, Mall(), b); }
-    void qp(int b, int apply) { if (use_warp) qp_warp_host(S, io, b, apply); else qp_one(S, io, b, apply); }
+    // QP of every live problem (the warp emulator takes pairs of problems on short horizons, like the kernel's queue)
+    void qp_all(int apply, bool skip_done) {
+        std::vector<int> todo;
+        for (int b = 0; b < nb; ++b) if (!(skip_done && S.done[b])) todo.push_back(b);
+        if (!use_warp) { for (int b : todo) qp_one(S, io, b, apply); return; }
+        if (qp_warp_pairs(N)) { for (size_t i = 0; i < todo.size(); i += 2) qp_warp_host(S, io, todo[i], i + 1 < todo.size() ? todo[i + 1] : -1, apply); }
+        else for (int b : todo) qp_warp_host(S, io, b, -1, apply);
+    }
     void linearise_all() { for (int k = 0; k <= N; ++k) for (int b = 0; b < nb; ++b) if (!S.done[b]) linearise_one(S, Mall(), k, b); }
     void solve() {                                                // qspush_solve
         if (mode == 0 || mode == 2) {
             linearise_all();
-            for (int b = 0; b < nb; ++b) qp(b, mode == 0 ? 1 : 0);
+            qp_all(mode == 0 ? 1 : 0, false);
         } else {
             std::fill(v_done.begin(), v_done.end(), 0); std::fill(v_qpit.begin(), v_qpit.end(), 0);
             for (int it = 0; it <= so.max_iter; ++it) {
@@ -334,7 +353,7 @@ struct HostRun {
                 int nd = 0;
                 for (int b = 0; b < nb; ++b) { if (!S.done[b]) nlp_res_one(S, so, it, b, ChunkSerial(), true); nd += S.done[b]; }
                 if (nd >= nb || it == so.max_iter) break;
-                for (int b = 0; b < nb; ++b) if (!S.done[b]) qp(b, 0);
+                qp_all(0, true);
                 for (int b = 0; b < nb; ++b) if (!S.done[b]) linesearch_one(S, so, Mall(), it, b, ChunkSerial(), true);
             }
             for (int b = 0; b < nb; ++b) cost_one(S, b);

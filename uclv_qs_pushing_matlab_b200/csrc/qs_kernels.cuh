@@ -199,8 +199,8 @@ __global__ void __launch_bounds__(32) k_qp(SolverDev S, IpmOpts o, int ppw, int 
 // the dynamic shared memory; the read-only linearisation lives in tensor memory: the CTA allocates all 512 TMEM
 // columns, warp w owns TMEM lanes 32*(w%4).. (the quarter the hardware lets it address) and columns 256*(w/4)..
 constexpr int QW_MAX_WARPS = 8;
-template <int C, int HV>
-__global__ void __launch_bounds__(32 * QW_MAX_WARPS, 1) k_qp_warp(SolverDev S, IpmOpts o, int apply, int per_warp_doubles) {
+template <int C, int HV, int SEG>
+__global__ void __launch_bounds__(32 * QW_MAX_WARPS, 1) k_qp_warp(SolverDev S, IpmOpts o, int apply, int per_problem_doubles) {
     extern __shared__ __align__(16) double qw_smem[];
     __shared__ unsigned tmem_base;
     const int wid = threadIdx.x >> 5;
@@ -214,16 +214,20 @@ __global__ void __launch_bounds__(32 * QW_MAX_WARPS, 1) k_qp_warp(SolverDev S, I
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tbase = tmem_base;
     WarpCtxDev w{(int)(threadIdx.x & 31), tbase + (((unsigned)(wid & 3) * 32u) << 16) + (unsigned)(wid >> 2) * 256u};
-    auto next = [&]() -> int {
+    // work queue: one atomic per warp fetches 32 / SEG consecutive problems, segment `seg` takes the seg-th of them
+    auto next = [&](int seg) -> int {
+        constexpr int PPW = 32 / SEG;
         int b = -1;
         for (;;) {
-            if (w.lane() == 0) b = atomicAdd(S.ndone + 1, 1);
+            if (w.lane() == 0) b = atomicAdd(S.ndone + 1, PPW);
             b = w.bcast_int(b);
             if (b >= S.B) return -1;
-            if (!(S.done && S.done[b])) return b;                // full SQP: skip problems that already converged
+            const int mine = b + seg;
+            const bool ok = mine < S.B && !(S.done && S.done[mine]);      // full SQP: skip problems that already converged
+            if (w.wany(ok ? 1 : 0)) return ok ? mine : -1;
         }
     };
-    qp_warp_persistent<WarpCtxDev, C, HV>(w, qw_smem + (size_t)wid * per_warp_doubles, S, o, apply, next);
+    qp_warp_persistent<WarpCtxDev, C, HV, SEG>(w, qw_smem + (size_t)wid * (32 / SEG) * per_problem_doubles, per_problem_doubles, S, o, apply, next);
     // every warp left the loop through the same CTA-wide vote: no TMEM access is in flight any more
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

@@ -107,22 +107,27 @@ struct WarpCtxDev {
     }
     __device__ __forceinline__ int lane() const { return lane_; }
     __device__ __forceinline__ double shfl(double v, int src) const { return __shfl_sync(0xffffffffu, v, src & 31); }
-    __device__ __forceinline__ double wmax(double v) const {
+    // reductions over the SEG lanes of this lane's segment (SEG = 32: the warp; 16: two problems per warp, short horizons)
+    template <int SEG = 32> __device__ __forceinline__ double wmax(double v) const {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        for (int o = SEG / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
         return v;
     }
-    __device__ __forceinline__ double wmin(double v) const {
+    template <int SEG = 32> __device__ __forceinline__ double wmin(double v) const {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+        for (int o = SEG / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
         return v;
     }
-    __device__ __forceinline__ double wsum(double v) const {
+    template <int SEG = 32> __device__ __forceinline__ double wsum(double v) const {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        for (int o = SEG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         return v;
     }
-    __device__ __forceinline__ int wany(int p) const { return __any_sync(0xffffffffu, p); }
+    template <int SEG = 32> __device__ __forceinline__ int wany(int p) const {
+        const unsigned m = __ballot_sync(0xffffffffu, p);
+        if constexpr (SEG == 32) return m != 0u;
+        else return (m & (((1u << SEG) - 1u) << (lane_ & ~(SEG - 1)))) != 0u;
+    }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
     // CTA-wide vote: keeps the warps of a CTA (one problem each) in lockstep, one barrier per IPM iteration,
     // so that they share instruction fetches; returns true when every warp of the CTA has finished
@@ -404,10 +409,10 @@ QS_HD void qw_row_add(int hv, int c, double beta, double w, double* g6) {
 
 // One Newton solve with the current factorisation: rhs gt (R_GT rows) and r_b (R_RB) ->
 // step dz (R_GT rows, aliased), costate offsets p_k (R_PV), feed-forward k_ff (R_KFF).
-template <class Ctx, int C>
-QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_) {
-    const int lane = w.lane();
-    const bool act = lane < Lw_;
+template <class Ctx, int C, int SEG>
+QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, bool live) {
+    const int lane = w.lane() & (SEG - 1);
+    const bool act = lane < Lw_ && live;
     // ---- (a) local: d_k, kff0_k and the chunk's composed backward map  p_start = M p_end + d
     double M[16], d[4];
     bool acc_identity = true;
@@ -597,18 +602,19 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_) 
 
 // Per-problem IPM state kept in registers across iterations (everything else lives in shared memory).
 struct QwState {
+    bool fin;                   // this segment's problem is finished (or the segment is idle): its lanes only take part in collectives
     int it, stall, status;
     double rmax_prev, r_stat, r_eq, r_in, r_cp;
     double qN[4];
 };
 
 // ---- load the linearisation of problem V into the warp's shared memory, initial point
-template <class Ctx, int C, int HV>
-QS_HD void qw_init(const Ctx& w, double* __restrict__ sm, const QpConst& Q, const QpView& V, QwState& st) {
+template <class Ctx, int C, int HV, int SEG>
+QS_HD void qw_init(const Ctx& w, double* __restrict__ sm, const QpConst& Q, const QpView& V, QwState& st, bool live) {
     const int N = Q.N;
-    const int lane = w.lane();
+    const int lane = w.lane() & (SEG - 1);
     const int Lw_ = qp_warp_lanes(N, C);
-    const bool act = lane < Lw_;
+    const bool act = lane < Lw_ && live;
     // ---------------- load the linearisation (into the lane's TMEM block), initial point
 #pragma unroll 1
     for (int j = 0; j < C; ++j) {
@@ -660,7 +666,8 @@ QS_HD void qw_init(const Ctx& w, double* __restrict__ sm, const QpConst& Q, cons
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) st.qN[i] = V.qN[i * V.stride];
+    for (int i = 0; i < 4; ++i) st.qN[i] = live ? V.qN[i * V.stride] : 0.0;
+    st.fin = !live;
     st.it = 0; st.stall = 0; st.status = 1; st.rmax_prev = 1e300;
     st.r_stat = st.r_eq = st.r_in = st.r_cp = 0.0;
     w.sync();
@@ -669,12 +676,15 @@ QS_HD void qw_init(const Ctx& w, double* __restrict__ sm, const QpConst& Q, cons
 
 // ---- one IPM iteration: true residuals + stopping tests, factorisation (parallel-in-time), predictor,
 // corrector, step.  Returns 0 to continue, 1 when the problem is finished (st.status set).
-template <class Ctx, int C, int HV>
+// With SEG = 16 a warp carries two problems (lanes 0..15 and 16..31, horizons N <= 15): every reduction is taken over
+// the segment, a segment whose problem has finished keeps executing the warp-collective instructions with all its
+// stores masked (act = false), and the function returns 1 when every segment of the warp is finished.
+template <class Ctx, int C, int HV, int SEG>
 QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, QwState& st) {
     const int N = Q.N;
-    const int lane = w.lane();
+    const int lane = w.lane() & (SEG - 1);
     const int Lw_ = qp_warp_lanes(N, C);
-    const bool act = lane < Lw_;
+    bool act = lane < Lw_ && !st.fin;
     constexpr int hvar = HV;                            // constraint set: compile-time, the default set pays nothing for the coupled rows
     const int m_on = hvar ? 6 * N : 6 * N - 2;
     int& status = st.status; int& it = st.it; int& stall = st.stall;
@@ -754,17 +764,25 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             for (int i = 0; i < 4; ++i) { nx[i] = z6[2 + i]; npi[i] = pik[i]; }
         }
     }
-    r_stat = w.wmax(l_stat); r_eq = w.wmax(l_eq); r_in = w.wmax(l_in); r_cp = w.wmax(l_cp);
-    const double mu_sum = w.wsum(l_mu);
+    const double mu_sum = w.template wsum<SEG>(l_mu);
     const double mu = mu_sum / (double)m_on;
-    if (w.wany(l_nan ? 1 : 0) || !(mu == mu)) { status = 2; return 1; }
-    if (r_stat < Q.tol && r_eq < Q.tol && r_in < Q.tol && r_cp < Q.tol) { status = 0; return 1; }
     {
-        const double rmax = fmax(fmax(r_stat, r_eq), fmax(r_in, r_cp));
-        if (rmax < 0.5 * rmax_prev) { rmax_prev = rmax; stall = 0; } else ++stall;
-        if (stall >= 5 && rmax < QS_QP_TOL_ACCEPT) { status = 0; return 1; }
+        const double q_stat = w.template wmax<SEG>(l_stat), q_eq = w.template wmax<SEG>(l_eq), q_in = w.template wmax<SEG>(l_in), q_cp = w.template wmax<SEG>(l_cp);
+        const bool q_nan = w.template wany<SEG>(l_nan ? 1 : 0) || !(mu == mu);
+        if (!st.fin) {                                       // stopping tests of this segment's problem
+            r_stat = q_stat; r_eq = q_eq; r_in = q_in; r_cp = q_cp;
+            const double rmax = fmax(fmax(r_stat, r_eq), fmax(r_in, r_cp));
+            if (q_nan) { status = 2; st.fin = true; }
+            else if (r_stat < Q.tol && r_eq < Q.tol && r_in < Q.tol && r_cp < Q.tol) { status = 0; st.fin = true; }
+            else {
+                if (rmax < 0.5 * rmax_prev) { rmax_prev = rmax; stall = 0; } else ++stall;
+                if (stall >= 5 && rmax < QS_QP_TOL_ACCEPT) { status = 0; st.fin = true; }
+                else if (it >= Q.max_iter) { status = 1; st.fin = true; }
+            }
+        }
     }
-    if (it >= Q.max_iter) { status = 1; return 1; }
+    if (!w.wany(st.fin ? 0 : 1)) return 1;                  // every segment of the warp is finished
+    act = act && !st.fin;
     QW_TICK(1);
     // ================= (2) barrier terms, affine rhs, stage elements, chunk aggregate =================
     Elem E; elem_identity(E);
@@ -922,7 +940,9 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             if constexpr (C >= 3) w.tm_st16(j * qw_tm_stage(C) + QW_TM_P, Pst);     // warp-collective
         }
     }
-    if (w.wany(ok ? 0 : 1)) { status = 2; return 1; }
+    if (w.template wany<SEG>(ok ? 0 : 1) && !st.fin) { status = 2; st.fin = true; }
+    if (!w.wany(st.fin ? 0 : 1)) return 1;
+    act = act && !st.fin;
     QW_TICK(4);
     // ================= (5)-(7) predictor and corrector share ONE copy of the solve code =================
     double smu = 0.0;
@@ -956,7 +976,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             }
         }
         QW_TICK(5);
-        qp_warp_solve<Ctx, C>(w, sm, N, Lw_);
+        qp_warp_solve<Ctx, C, SEG>(w, sm, N, Lw_, !st.fin);
         QW_TICK(6);
         if (pass == 0) {
             // step to the boundary of the affine step, mu_aff, centering parameter
@@ -988,7 +1008,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                     }
                 }
             }
-            a_aff = w.wmin(fmin(a_aff, a_num / a_den)); S1 = w.wsum(S1); S2 = w.wsum(S2);
+            a_aff = w.template wmin<SEG>(fmin(a_aff, a_num / a_den)); S1 = w.template wsum<SEG>(S1); S2 = w.template wsum<SEG>(S2);
             const double mu_aff = (mu_sum + a_aff * (S1 + a_aff * S2)) / (double)m_on;
             double sigma = (mu > 0.0) ? mu_aff / mu : 0.0;
             sigma = sigma * sigma * sigma;
@@ -1020,9 +1040,11 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             }
         }
     }
-    a_max = w.wmin(fmin(a_max, m_num / m_den));
+    a_max = w.template wmin<SEG>(fmin(a_max, m_num / m_den));
     const double alpha = fmin(1.0, Q.tau * a_max);
-    if (!(alpha == alpha)) { status = 2; return 1; }
+    if (!(alpha == alpha) && !st.fin) { status = 2; st.fin = true; }
+    if (!w.wany(st.fin ? 0 : 1)) return 1;
+    act = act && !st.fin;
     {
 #pragma unroll 1
         for (int j = 0; j < C; ++j) {
@@ -1066,18 +1088,18 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
     }
     w.sync();
     QW_TICK(8);
-    ++it;
+    if (!st.fin) ++it;
     return 0;
     }
 }
 
 // ---- write the point back to the slabs: V.z (du, dx), V.pi (pi[k] = pi_{k+1}), V.lam, V.t
-template <class Ctx, int C>
-QS_HD void qw_writeback(const Ctx& w, double* __restrict__ sm, const QpConst& Q, const QpView& V) {
+template <class Ctx, int C, int SEG>
+QS_HD void qw_writeback(const Ctx& w, double* __restrict__ sm, const QpConst& Q, const QpView& V, bool live) {
     const int N = Q.N;
-    const int lane = w.lane();
+    const int lane = w.lane() & (SEG - 1);
     const int Lw_ = qp_warp_lanes(N, C);
-    const bool act = lane < Lw_;
+    const bool act = lane < Lw_ && live;
     // ---------------- write the point back to the slabs
     if (act) {
 #pragma unroll 1

@@ -244,50 +244,59 @@ QS_HD void qp_one(const SolverDev& S, const IpmOpts& o, int b, int apply) {
 // time and pulls the next one from a work queue when it finishes (`next` returns a warp-uniform problem
 // index or -1), while one CTA-wide vote per IPM iteration keeps the warps in lockstep (shared instruction
 // fetches).  sm = the warp's shared-memory state (qp_warp_smem_doubles(N) doubles).
-template <class Ctx, int C, int HV, class NextFn>
-QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm, const SolverDev& S, const IpmOpts& o, int apply, NextFn next) {
+template <class Ctx, int C, int HV, int SEG, class NextFn>
+QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm_warp, int per_problem_doubles, const SolverDev& S, const IpmOpts& o,
+                              int apply, NextFn next) {
     QpConst Qc;
     Qc.N = S.N; Qc.H = S.H; Qc.QN = S.QN;
 #pragma unroll
     for (int i = 0; i < 3; ++i) { Qc.lh[i] = S.lh[i]; Qc.uh[i] = S.uh[i]; }
     Qc.h_variant = HV;
     Qc.max_iter = o.max_iter; Qc.tol = o.tol; Qc.mu0 = o.mu0; Qc.thr = o.thr; Qc.tau = o.tau;
-    const int lane = w.lane();
+    // SEG = 32: one problem per warp.  SEG = 16 (N <= 15): lanes 0..15 and 16..31 carry one problem each; `b` is the
+    // problem of this lane's segment (-1: none), every per-problem quantity below is per segment.
+    const int seg = w.lane() / SEG;
+    const int lane = w.lane() & (SEG - 1);
+    double* sm = sm_warp + (size_t)seg * per_problem_doubles;
     const int N = S.N;
     QpView V;
     QwState st;
-    // bind problem b to this warp: slab views + linearisation and initial point into shared memory / TMEM.  Done
+    // bind problem b to this segment: slab views + linearisation and initial point into shared memory / TMEM.  Done
     // right after the previous problem finishes, i.e. BEFORE the next lockstep vote: the other warps of the CTA are
     // still inside their IPM iteration then, so nobody waits for the loads of a newly fetched problem.
     auto bind = [&](int b_) {
+        const bool live = b_ >= 0;
+        const int bb = live ? b_ : 0;
         V.stride = (size_t)S.Bp;
-        V.A = S.A + b_; V.B = S.Bm + b_; V.b = S.b + b_; V.g = S.g + b_; V.qN = S.qN + b_; V.dx0 = S.dx0 + b_;
-        V.x = S.x + b_; V.u = S.u + b_; V.hv = S.hv + b_;
-        V.z = S.z + b_; V.zp = S.zp + b_; V.zc = S.zc + b_; V.t = S.t + b_;
-        V.K = S.K + b_; V.Li = S.Li + b_; V.Pb = S.Pb + b_; V.kff = S.kff + b_;
-        V.rg = S.rg + b_; V.rb = S.rb + b_; V.rgs = S.rgs + b_;
-        V.lam = (apply ? S.lam : S.lamq) + b_;
-        V.pi = (apply ? S.pi : S.piq) + b_;
-        qw_init<Ctx, C, HV>(w, sm, Qc, V, st);
+        V.A = S.A + bb; V.B = S.Bm + bb; V.b = S.b + bb; V.g = S.g + bb; V.qN = S.qN + bb; V.dx0 = S.dx0 + bb;
+        V.x = S.x + bb; V.u = S.u + bb; V.hv = S.hv + bb;
+        V.z = S.z + bb; V.zp = S.zp + bb; V.zc = S.zc + bb; V.t = S.t + bb;
+        V.K = S.K + bb; V.Li = S.Li + bb; V.Pb = S.Pb + bb; V.kff = S.kff + bb;
+        V.rg = S.rg + bb; V.rb = S.rb + bb; V.rgs = S.rgs + bb;
+        V.lam = (apply ? S.lam : S.lamq) + bb;
+        V.pi = (apply ? S.pi : S.piq) + bb;
+        qw_init<Ctx, C, HV, SEG>(w, sm, Qc, V, st, live);
     };
-    int b = next();
+    int b = next(seg);
     {
         QW_T0();
-        if (b >= 0) bind(b);
+        if (w.wany(b >= 0 ? 1 : 0)) bind(b);
         QW_TICK(9);
     }
     for (;;) {
         // lockstep point once per IPM iteration (measured: voting every 2nd / 4th iteration is 9 % / 16 % slower,
         // the warps drift and stop sharing instruction fetches); leaves when the queue is drained
         QW_T0();
-        if (w.cta_all(b < 0)) break;
+        const bool idle = !w.wany(b >= 0 ? 1 : 0);         // no segment of this warp has a problem
+        if (w.cta_all(idle)) break;
         QW_TICK(0);
-        if (b < 0) continue;
-        const int fin = qw_iterate<Ctx, C, HV>(w, sm, Qc, st);
+        if (idle) continue;
+        const int fin = qw_iterate<Ctx, C, HV, SEG>(w, sm, Qc, st);
         if (fin == 0) continue;
-        // ---- problem b is finished: write back, K5 epilogue, fetch the next problem
-        qw_writeback<Ctx, C>(w, sm, Qc, V);
-        if (lane == 0) {
+        // ---- the problems of this warp are finished: write back, K5 epilogue, fetch the next ones
+        const bool live = b >= 0;
+        qw_writeback<Ctx, C, SEG>(w, sm, Qc, V, live);
+        if (live && lane == 0) {
             S.qpstat[b] = st.status;
             if (apply) S.qp_iter[b] = st.it; else S.qp_iter[b] += st.it;
         }
@@ -296,21 +305,23 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm, const Solve
             w.sync();
             double cost = 0.0;
             int nan = 0;
+            if (live) {
 #pragma unroll 1
-            for (int j = 0; j < C; ++j) {
-                const int k = lane * C + j;
-                if (k > N) continue;
-                if (k < N) {
+                for (int j = 0; j < C; ++j) {
+                    const int k = lane * C + j;
+                    if (k > N) continue;
+                    if (k < N) {
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) { const double v = QS_EL(S.u, k * 2 + i, b) + QS_EL(S.z, k * 6 + i, b); QS_EL(S.u, k * 2 + i, b) = v; nan |= !(v == v); }
+                        for (int i = 0; i < 2; ++i) { const double v = QS_EL(S.u, k * 2 + i, b) + QS_EL(S.z, k * 6 + i, b); QS_EL(S.u, k * 2 + i, b) = v; nan |= !(v == v); }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) QS_EL(S.x, k * 4 + i, b) += QS_EL(S.z, k * 6 + 2 + i, b);
+                    cost += (k < N) ? stage_cost(S, k, b) : terminal_cost(S, b);
                 }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) QS_EL(S.x, k * 4 + i, b) += QS_EL(S.z, k * 6 + 2 + i, b);
-                cost += (k < N) ? stage_cost(S, k, b) : terminal_cost(S, b);
             }
-            cost = w.wsum(cost);
-            nan = w.wany(nan);
-            if (lane == 0) {
+            cost = w.template wsum<SEG>(cost);
+            nan = w.template wany<SEG>(nan);
+            if (live && lane == 0) {
                 S.cost[b] = cost;
                 QS_EL(S.res, 0, b) = st.r_stat; QS_EL(S.res, 1, b) = st.r_eq; QS_EL(S.res, 2, b) = st.r_in; QS_EL(S.res, 3, b) = st.r_cp;
                 S.sqp_iter[b] = 1;
@@ -318,9 +329,9 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm, const Solve
                 S.status[b] = nan ? 1 : (st.status == 2 ? 4 : 0);
             }
         }
-        b = next();
+        b = next(seg);
         QW_TICK(10);
-        if (b >= 0) bind(b);
+        if (w.wany(b >= 0 ? 1 : 0)) bind(b);
         QW_TICK(9);
     }
 }

@@ -551,7 +551,8 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
     // batch size for C >= 2 (N = 40: 2.0M it/s at 4096, 2.46M at 65536 vs 0.39M / 2.25M; N = 100: 0.97M / 1.09M vs
     // 0.19M / 1.01M); short horizons (C = 1, N <= 31) leave two thirds of a warp idle, there the one-problem-per-thread
     // kernel takes over once the batch fills the GPU (N = 10: 4.0M vs 2.1M at 4096, 4.7M vs 7.2M at 65536)
-    const int warp_below = (C >= 2) ? INT_MAX : 12288;
+    // (N <= 15: two problems per warp, 6.6M it/s at 4096 and 8.3M at 65536 for N = 10 vs 2.0M / 7.1M: warp kernel always)
+    const int warp_below = (C >= 2 || s->N + 1 <= 16) ? INT_MAX : 12288;
     // full SQP (apply == 0): always the warp kernel — its work queue skips the problems that already finished, while
     // the thread kernel keeps mostly idle warps alive (config 5 share, 32 768 x N = 100: 0.87 s vs 2.3 s)
     const bool want_warp = s->opts.qp_kernel == 1 || (s->opts.qp_kernel == 2 && (s->B < warp_below || D.h_variant || !apply));
@@ -559,7 +560,9 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
     // (8 warps of 255 registers) and by TMEM (8 blocks of 32 lanes x 256 columns)
     const int pwd = (int)((qp_warp_smem_doubles(s->N) + 1) / 2 * 2);
     const size_t smem_cap = 227 * 1024 - 1024;                                       // static __shared__ + reserve
-    int W = (int)std::min<size_t>(QW_MAX_WARPS, smem_cap / ((size_t)pwd * sizeof(double)));
+    // short horizons (N <= 15: at most 16 stages): two problems per warp, one per 16-lane segment
+    const int ppw_seg = (C == 1 && s->N + 1 <= 16) ? 2 : 1;
+    int W = (int)std::min<size_t>(QW_MAX_WARPS, smem_cap / ((size_t)pwd * ppw_seg * sizeof(double)));
     if (C * qw_tm_stage(C) > 128) W = std::min(W, 4);          // more than 256 TMEM columns per warp: one warp per lane quarter
     const bool warp = want_warp && C <= 4 && W >= 2;
     if (!warp && s->opts.qp_kernel == 2 && s->opts.problems_per_warp == 0) ppw = (s->B >= 12288) ? 32 : ppw;
@@ -569,25 +572,28 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
         return QSPUSH_OK;
     }
     // at least half of the SM's shared memory, so that two CTAs (both wanting all TMEM columns) never share an SM
-    const size_t smem = std::max((size_t)pwd * W * sizeof(double), (size_t)116 * 1024);   // (sized for W warps, Wl <= W used)
+    const size_t smem = std::max((size_t)pwd * ppw_seg * W * sizeof(double), (size_t)116 * 1024);   // (sized for W warps, Wl <= W used)
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device);
     // small batches: spread the problems over the SMs first (a warp alone on an SM runs its problem fastest)
-    const int Wl = std::max(1, std::min(W, (s->B + nsm - 1) / nsm));
-    const unsigned blocks = (unsigned)std::min((s->B + Wl - 1) / Wl, nsm);             // persistent: one CTA per SM
+    const int slots = (s->B + ppw_seg - 1) / ppw_seg;                                  // warps' worth of work
+    const int Wl = std::max(1, std::min(W, (slots + nsm - 1) / nsm));
+    const unsigned blocks = (unsigned)std::min((slots + Wl - 1) / Wl, nsm);            // persistent: one CTA per SM
     CK(cudaMemsetAsync(D.ndone + 1, 0, sizeof(int), s->stream));                       // work-queue head
-#define QW_LAUNCH(CC, HV)                                                                                          \
-    CK(cudaFuncSetAttribute(k_qp_warp<CC, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    k_qp_warp<CC, HV><<<blocks, 32 * Wl, smem, s->stream>>>(D, io, apply, pwd)
-    switch (C * 2 + (D.h_variant ? 1 : 0)) {
-        case 2: QW_LAUNCH(1, 0); break;
-        case 3: QW_LAUNCH(1, 1); break;
-        case 4: QW_LAUNCH(2, 0); break;
-        case 5: QW_LAUNCH(2, 1); break;
-        case 6: QW_LAUNCH(3, 0); break;
-        case 7: QW_LAUNCH(3, 1); break;
-        case 8: QW_LAUNCH(4, 0); break;
-        default: QW_LAUNCH(4, 1); break;
+#define QW_LAUNCH(CC, HV, SEG)                                                                                     \
+    CK(cudaFuncSetAttribute(k_qp_warp<CC, HV, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    k_qp_warp<CC, HV, SEG><<<blocks, 32 * Wl, smem, s->stream>>>(D, io, apply, pwd)
+    const int hvf = D.h_variant ? 1 : 0;
+    if (ppw_seg == 2) { if (hvf) { QW_LAUNCH(1, 1, 16); } else { QW_LAUNCH(1, 0, 16); } }
+    else switch (C * 2 + hvf) {
+        case 2: QW_LAUNCH(1, 0, 32); break;
+        case 3: QW_LAUNCH(1, 1, 32); break;
+        case 4: QW_LAUNCH(2, 0, 32); break;
+        case 5: QW_LAUNCH(2, 1, 32); break;
+        case 6: QW_LAUNCH(3, 0, 32); break;
+        case 7: QW_LAUNCH(3, 1, 32); break;
+        case 8: QW_LAUNCH(4, 0, 32); break;
+        default: QW_LAUNCH(4, 1, 32); break;
     }
 #undef QW_LAUNCH
     return QSPUSH_OK;
