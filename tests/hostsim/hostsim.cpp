@@ -157,13 +157,19 @@ static void warp_job_body(int lane, void* arg) {
     auto next = [j, lane](int seg) -> int { return j->handed[lane]++ == 0 ? j->b[seg] : -1; };
     const int hv = j->S->h_variant ? 1 : 0;
     if (j->seg16) {
-        if (hv) qp_warp_persistent<WarpCtxHost, 1, 1, 16>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next);
-        else qp_warp_persistent<WarpCtxHost, 1, 0, 16>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next);
+        switch (j->C * 2 + hv) {
+            case 2: qp_warp_persistent<WarpCtxHost, 1, 0, 16>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
+            case 3: qp_warp_persistent<WarpCtxHost, 1, 1, 16>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
+            case 4: qp_warp_persistent<WarpCtxHost, 2, 0, 16>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
+            case 5: qp_warp_persistent<WarpCtxHost, 2, 1, 16>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
+            case 6: qp_warp_persistent<WarpCtxHost, 3, 0, 16>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
+            case 7: qp_warp_persistent<WarpCtxHost, 3, 1, 16>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
+            case 8: qp_warp_persistent<WarpCtxHost, 4, 0, 16>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
+            default: qp_warp_persistent<WarpCtxHost, 4, 1, 16>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
+        }
         return;
     }
     switch (j->C * 2 + hv) {
-        case 2: qp_warp_persistent<WarpCtxHost, 1, 0, 32>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
-        case 3: qp_warp_persistent<WarpCtxHost, 1, 1, 32>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
         case 4: qp_warp_persistent<WarpCtxHost, 2, 0, 32>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
         case 5: qp_warp_persistent<WarpCtxHost, 2, 1, 32>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
         case 6: qp_warp_persistent<WarpCtxHost, 3, 0, 32>(w, j->sm, j->per_problem, *j->S, *j->io, j->apply, next); break;
@@ -173,7 +179,7 @@ static void warp_job_body(int lane, void* arg) {
     }
 }
 // mirrors k_qp_warp: one emulated warp per problem, or per pair of problems on short horizons (N <= 15; b1 = -1: odd tail)
-static bool qp_warp_pairs(int N) { return qp_warp_chunk(N) == 1 && N + 1 <= 16; }
+static bool qp_warp_pairs(int N) { return qp_warp_plan(N).seg == 16; }
 static void qp_warp_host(const SolverDev& S, const IpmOpts& io, int b0, int b1, int apply) {
     const int pwd = (int)((qp_warp_smem_doubles(S.N) + 1) / 2 * 2);
     std::vector<double> sm((size_t)pwd * 2, 0.0);

@@ -64,7 +64,7 @@ def test_set_get_roundtrip_and_errors():
 
 
 @pytest.mark.parametrize("qp_kernel", [1, 0], ids=["warp_scan", "thread"])
-@pytest.mark.parametrize("name,N", [("santal", 40), ("montana", 10), ("balea", 100)])
+@pytest.mark.parametrize("name,N", [("santal", 40), ("montana", 10), ("balea", 100), ("santal", 20), ("montana", 55), ("santal", 60)])
 def test_prepare_qp_rti_vs_oracle(name, N, qp_kernel):
     gm, om = packaged_model_pair(name)
     B = 256

@@ -253,7 +253,7 @@ def test_closed_loop_bodies_vs_oracle():
     assert 0 < np.abs(d0[:, 2]).max() < 6e-3 and np.abs(d0[:, 0]).max() < 6e-5
 
 
-@pytest.mark.parametrize("N,hv", [(40, 0), (10, 0), (100, 0), (40, 1)])
+@pytest.mark.parametrize("N,hv", [(40, 0), (10, 0), (100, 0), (40, 1), (55, 0)])
 def test_warp_kernel_is_independent_of_lane_scheduling(N, hv):
     """Racecheck substitute (compute-sanitizer is not available on the GPU pool): the warp emulator runs the lanes
     between two collectives in ascending or descending order; correctly synchronised shared-memory / TMEM traffic

@@ -175,13 +175,22 @@ QS_HD constexpr int qw_rows(int C) { return C >= 3 ? R_ROWS_LONG : R_ROWS; }
 // divisions per stage and iteration become 6; 48..63, long horizons only: P_k (10) and P_{k+1} r_b (4))
 enum : int { QW_TM_AB = 0, QW_TM_BV = 16, QW_TM_HH = 20, QW_TM_G = 24, QW_TM_IT = 32, QW_TM_D = 40, QW_TM_P = 48, QW_TM_STAGE = 48, QW_TM_STAGE_LONG = 64 };
 QS_HD constexpr int qw_tm_stage(int C) { return C >= 3 ? QW_TM_STAGE_LONG : QW_TM_STAGE; }
-QS_HD constexpr int qp_warp_chunk(int N) { return (N + 1 + 31) / 32; }
+// Mapping of a horizon onto a warp.  seg = 16: two problems per warp, one per 16-lane segment, each lane owning
+// C = ceil((N+1)/16) stages; seg = 32: one problem per warp, C = ceil((N+1)/32).  Measured on B200 (tools/gpu_half_sweep.py):
+// the two-problem mapping wins up to N = 55 (N = 10: +65 %, 20: +31 %, 31: +20 %, 40: +8 %, 47: +15 %, 55: +5 %,
+// 63: -1 %): the same 8 problems are resident per SM either way (shared memory), but one instruction stream serves
+// two problems with 85-100 % instead of 35-65 % of the lanes busy and the scans are one step shorter.
+struct QwPlan { int C, seg; };
+QS_HD constexpr QwPlan qp_warp_plan(int N) {
+    return (N <= 55) ? QwPlan{(N + 1 + 15) / 16, 16} : QwPlan{(N + 1 + 31) / 32, 32};
+}
+QS_HD constexpr int qp_warp_chunk(int N) { return qp_warp_plan(N).C; }
 QS_HD constexpr int qp_warp_lanes(int N, int C) { return (N + 1 + C - 1) / C; }
 // Exchange areas of the warp scans.  Affine maps (M 16, d 4): a dedicated area behind the records, odd stride 21 per
 // lane.  Scan elements (A 16, C 10, J 10): for C >= 2 they travel through rows R_K.. of the j = 0 (A) and j = 1
 // (C, J) records, which are dead during the element scan; for C == 1 through a dedicated area of stride 37.
 constexpr int QW_XA = 21, QW_XE = 37;
-QS_HD constexpr size_t qp_warp_smem_doubles(int N) {
+QS_HD constexpr size_t qp_warp_smem_doubles(int N) {                 // per problem
     const int C = qp_warp_chunk(N), L = qp_warp_lanes(N, C);
     return (size_t)qw_rows(C) * C * L + (size_t)QW_XA * L + (C >= 2 ? 0 : (size_t)QW_XE * L);
 }

@@ -546,13 +546,12 @@ int qspush_prepare(qspush_solver* s) {
 // launch the QP kernel selected by opts.qp_kernel: 1 (default when the horizon fits) = warp per problem,
 // parallel-in-time; 0 = one problem per thread (any horizon)
 static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, int ppw, int apply) {
-    const int C = qp_warp_chunk(s->N);
-    // auto (2): measured on B200 (tools/gpu_kernel_compare.py) the warp-per-problem kernel wins at every
-    // batch size for C >= 2 (N = 40: 2.0M it/s at 4096, 2.46M at 65536 vs 0.39M / 2.25M; N = 100: 0.97M / 1.09M vs
-    // 0.19M / 1.01M); short horizons (C = 1, N <= 31) leave two thirds of a warp idle, there the one-problem-per-thread
-    // kernel takes over once the batch fills the GPU (N = 10: 4.0M vs 2.1M at 4096, 4.7M vs 7.2M at 65536)
-    // (N <= 15: two problems per warp, 6.6M it/s at 4096 and 8.3M at 65536 for N = 10 vs 2.0M / 7.1M: warp kernel always)
-    const int warp_below = (C >= 2 || s->N + 1 <= 16) ? INT_MAX : 12288;
+    const QwPlan plan = qp_warp_plan(s->N);
+    const int C = plan.C;
+    // auto (2): measured on B200 (tools/gpu_kernel_compare.py, tools/gpu_half_sweep.py) the warp kernel
+    // wins at every batch size and horizon it supports (N <= 127): N = 40: 2.2M it/s at 4096, 2.6M at 16384 vs
+    // 0.39M / 1.4M for one problem per thread; N = 100: 0.97M / 1.09M vs 0.19M / 1.01M; N = 10: 6.6M / 8.3M vs 2.0M / 7.1M
+    const int warp_below = INT_MAX;
     // full SQP (apply == 0): always the warp kernel — its work queue skips the problems that already finished, while
     // the thread kernel keeps mostly idle warps alive (config 5 share, 32 768 x N = 100: 0.87 s vs 2.3 s)
     const bool want_warp = s->opts.qp_kernel == 1 || (s->opts.qp_kernel == 2 && (s->B < warp_below || D.h_variant || !apply));
@@ -561,7 +560,7 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
     const int pwd = (int)((qp_warp_smem_doubles(s->N) + 1) / 2 * 2);
     const size_t smem_cap = 227 * 1024 - 1024;                                       // static __shared__ + reserve
     // short horizons (N <= 15: at most 16 stages): two problems per warp, one per 16-lane segment
-    const int ppw_seg = (C == 1 && s->N + 1 <= 16) ? 2 : 1;
+    const int ppw_seg = 32 / plan.seg;                          // problems per warp
     int W = (int)std::min<size_t>(QW_MAX_WARPS, smem_cap / ((size_t)pwd * ppw_seg * sizeof(double)));
     if (C * qw_tm_stage(C) > 128) W = std::min(W, 4);          // more than 256 TMEM columns per warp: one warp per lane quarter
     const bool warp = want_warp && C <= 4 && W >= 2;
@@ -584,16 +583,22 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
     CK(cudaFuncSetAttribute(k_qp_warp<CC, HV, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     k_qp_warp<CC, HV, SEG><<<blocks, 32 * Wl, smem, s->stream>>>(D, io, apply, pwd)
     const int hvf = D.h_variant ? 1 : 0;
-    if (ppw_seg == 2) { if (hvf) { QW_LAUNCH(1, 1, 16); } else { QW_LAUNCH(1, 0, 16); } }
-    else switch (C * 2 + hvf) {
-        case 2: QW_LAUNCH(1, 0, 32); break;
-        case 3: QW_LAUNCH(1, 1, 32); break;
+    switch ((plan.seg == 16 ? 16 : 0) + C * 2 + hvf) {
+        case 16 + 2: QW_LAUNCH(1, 0, 16); break;
+        case 16 + 3: QW_LAUNCH(1, 1, 16); break;
+        case 16 + 4: QW_LAUNCH(2, 0, 16); break;
+        case 16 + 5: QW_LAUNCH(2, 1, 16); break;
+        case 16 + 6: QW_LAUNCH(3, 0, 16); break;
+        case 16 + 7: QW_LAUNCH(3, 1, 16); break;
+        case 16 + 8: QW_LAUNCH(4, 0, 16); break;
+        case 16 + 9: QW_LAUNCH(4, 1, 16); break;
         case 4: QW_LAUNCH(2, 0, 32); break;
         case 5: QW_LAUNCH(2, 1, 32); break;
         case 6: QW_LAUNCH(3, 0, 32); break;
         case 7: QW_LAUNCH(3, 1, 32); break;
         case 8: QW_LAUNCH(4, 0, 32); break;
-        default: QW_LAUNCH(4, 1, 32); break;
+        case 9: QW_LAUNCH(4, 1, 32); break;
+        default: return fail(QSPUSH_ERR_ARG, "no warp QP kernel for this horizon");
     }
 #undef QW_LAUNCH
     return QSPUSH_OK;
