@@ -190,8 +190,8 @@ QS_HD constexpr int qp_warp_lanes(int N, int C) { return (N + 1 + C - 1) / C; }
 // lane.  Scan elements (A 16, C 10, J 10): for C >= 2 they travel through rows R_K.. of the j = 0 (A) and j = 1
 // (C, J) records, which are dead during the element scan; for C == 1 through a dedicated area of stride 37.
 constexpr int QW_XA = 21, QW_XE = 37;
-QS_HD constexpr size_t qp_warp_smem_doubles(int N) {                 // per problem
-    const int C = qp_warp_chunk(N), L = qp_warp_lanes(N, C);
+QS_HD constexpr size_t qp_warp_smem_doubles(int N, int C_plan = 0) {   // per problem; C_plan = 0: chunk of qp_warp_plan(N)
+    const int C = C_plan ? C_plan : qp_warp_chunk(N), L = qp_warp_lanes(N, C);
     return (size_t)qw_rows(C) * C * L + (size_t)QW_XA * L + (C >= 2 ? 0 : (size_t)QW_XE * L);
 }
 

@@ -546,7 +546,12 @@ int qspush_prepare(qspush_solver* s) {
 // launch the QP kernel selected by opts.qp_kernel: 1 (default when the horizon fits) = warp per problem,
 // parallel-in-time; 0 = one problem per thread (any horizon)
 static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, int ppw, int apply) {
-    const QwPlan plan = qp_warp_plan(s->N);
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device);
+    // throughput mapping (two problems per warp up to N = 55) unless the batch is so small that every problem gets an SM
+    // of its own: then one problem per warp with the shortest chunks gives the lowest latency (B = 1, N = 40: 0.54 vs 0.59 ms)
+    QwPlan plan = qp_warp_plan(s->N);
+    if (s->B <= nsm && s->N + 1 > 16) plan = QwPlan{(s->N + 1 + 31) / 32, 32};
     const int C = plan.C;
     // auto (2): measured on B200 (tools/gpu_kernel_compare.py, tools/gpu_half_sweep.py) the warp kernel
     // wins at every batch size and horizon it supports (N <= 127): N = 40: 2.2M it/s at 4096, 2.6M at 16384 vs
@@ -557,7 +562,7 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
     const bool want_warp = s->opts.qp_kernel == 1 || (s->opts.qp_kernel == 2 && (s->B < warp_below || D.h_variant || !apply));
     // resident problems (= warps) per CTA: bounded by shared memory (one CTA per SM), by the register file
     // (8 warps of 255 registers) and by TMEM (8 blocks of 32 lanes x 256 columns)
-    const int pwd = (int)((qp_warp_smem_doubles(s->N) + 1) / 2 * 2);
+    const int pwd = (int)((qp_warp_smem_doubles(s->N, C) + 1) / 2 * 2);
     const size_t smem_cap = 227 * 1024 - 1024;                                       // static __shared__ + reserve
     // short horizons (N <= 15: at most 16 stages): two problems per warp, one per 16-lane segment
     const int ppw_seg = 32 / plan.seg;                          // problems per warp
@@ -572,8 +577,6 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
     }
     // at least half of the SM's shared memory, so that two CTAs (both wanting all TMEM columns) never share an SM
     const size_t smem = std::max((size_t)pwd * ppw_seg * W * sizeof(double), (size_t)116 * 1024);   // (sized for W warps, Wl <= W used)
-    int nsm = 148;
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device);
     // small batches: spread the problems over the SMs first (a warp alone on an SM runs its problem fastest)
     const int slots = (s->B + ppw_seg - 1) / ppw_seg;                                  // warps' worth of work
     const int Wl = std::max(1, std::min(W, (slots + nsm - 1) / nsm));
@@ -592,6 +595,8 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
         case 16 + 7: QW_LAUNCH(3, 1, 16); break;
         case 16 + 8: QW_LAUNCH(4, 0, 16); break;
         case 16 + 9: QW_LAUNCH(4, 1, 16); break;
+        case 2: QW_LAUNCH(1, 0, 32); break;
+        case 3: QW_LAUNCH(1, 1, 32); break;
         case 4: QW_LAUNCH(2, 0, 32); break;
         case 5: QW_LAUNCH(2, 1, 32); break;
         case 6: QW_LAUNCH(3, 0, 32); break;
