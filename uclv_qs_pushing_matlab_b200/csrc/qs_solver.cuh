@@ -37,6 +37,7 @@ struct SolverDev {
     double vbp[4];          // v_alpha, d_v_bound, t_angle0, u_t_ub of v_bound(s) (:229)
     // bookkeeping
     int *status, *sqp_iter, *qp_iter, *cold, *done, *qpstat, *ndone;   // ndone[0]: SQP finished count, ndone[1]: QP work-queue head
+    int *order;             // work-queue order of the warp QP kernel (nullptr: index order), see k_qp_order
     double *cost, *res, *alpha;
     // SQP merit weights
     double *wpi, *wlam, *wx0;

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -43,6 +44,7 @@ struct qspush_solver {
     double *d_Wdt = nullptr, *d_We = nullptr, *d_H = nullptr, *d_QN = nullptr, *d_models = nullptr;
     double* d_stage = nullptr;
     int* d_istage = nullptr;
+    int* d_order = nullptr;       // work-queue order of the warp QP kernel (k_qp_order)
     size_t stage_doubles = 0;
     int* h_ndone = nullptr;        // pinned
     std::vector<double> W, We;     // host copies: N x 36 (y order, column-major), 16
@@ -309,7 +311,7 @@ int qspush_solver_create(const qspush_model* const* models, int nmodels, int N, 
     for (auto& sl : slabs) total += al(sl.rows * Bp);
     const size_t n_const = al((size_t)N * 36) + al(16) + al((size_t)N * 21) + al(10) + al((size_t)nmodels * MODEL_DOUBLES);
     s->stage_doubles = (size_t)(N + 1) * 6 * Bp;                 // largest AoS field (x: (N+1)*4, lam: N*6)
-    const size_t n_int = 8 * Bp + 32;
+    const size_t n_int = 9 * Bp + 32;
     s->arena_bytes = (total + n_const + al(s->stage_doubles)) * 8 + (n_int + Bp) * sizeof(int) + 1024;
     CK(cudaMalloc(&s->arena, s->arena_bytes));
     CK(cudaMemsetAsync(s->arena, 0, s->arena_bytes, s->stream));
@@ -326,6 +328,7 @@ int qspush_solver_create(const qspush_model* const* models, int nmodels, int N, 
     for (int** ip : ints) { *ip = icur; icur += Bp; }
     int* objid = icur; icur += Bp;
     s->d_istage = icur; icur += Bp;
+    s->d_order = icur; icur += Bp;
     D.ndone = icur; icur += 32;
     D.objid = objid;
     D.B = batch; D.Bp = s->Bp; D.N = N; D.nmodels = nmodels; D.dt = dt;
@@ -582,9 +585,16 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
     const int Wl = std::max(1, std::min(W, (slots + nsm - 1) / nsm));
     const unsigned blocks = (unsigned)std::min((slots + Wl - 1) / Wl, nsm);            // persistent: one CTA per SM
     CK(cudaMemsetAsync(D.ndone + 1, 0, sizeof(int), s->stream));                       // work-queue head
+    SolverDev Dq = D;
+    Dq.order = nullptr;
+    if (apply && s->B > nsm * Wl && !std::getenv("QSPUSH_NO_ORDER")) {                 // RTI with more problems than resident slots
+        k_qp_order<<<1, 1024, 0, s->stream>>>(D, s->d_order);
+        Dq.order = s->d_order;
+        s->launches++;
+    }
 #define QW_LAUNCH(CC, HV, SEG)                                                                                     \
     CK(cudaFuncSetAttribute(k_qp_warp<CC, HV, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    k_qp_warp<CC, HV, SEG><<<blocks, 32 * Wl, smem, s->stream>>>(D, io, apply, pwd)
+    k_qp_warp<CC, HV, SEG><<<blocks, 32 * Wl, smem, s->stream>>>(Dq, io, apply, pwd)
     const int hvf = D.h_variant ? 1 : 0;
     switch ((plan.seg == 16 ? 16 : 0) + C * 2 + hvf) {
         case 16 + 2: QW_LAUNCH(1, 0, 16); break;
