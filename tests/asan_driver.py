@@ -16,7 +16,7 @@ from tests.workloads import OBJECT_ORDER, hostsim_model, make_rti_workload  # no
 mhs = [hostsim_model(n) for n in OBJECT_ORDER]
 for N, B, kern, mode in ((40, 7, 1, "rti"), (10, 5, 1, "rti"), (100, 3, 1, "rti"), (40, 33, 0, "rti"), (10, 4, 1, "sqp"),
                          (64, 3, 1, "rti"), (31, 3, 1, "rti"), (95, 2, 1, "rti"), (1, 2, 1, "rti"), (130, 2, 1, "rti"),
-                         (47, 3, 1, "rti"), (55, 3, 1, "rti"), (56, 2, 1, "rti"), (20, 5, 1, "sqp")):
+                         (47, 3, 1, "rti"), (55, 3, 1, "rti"), (63, 2, 1, "rti"), (20, 5, 1, "sqp")):
     wl = make_rti_workload(None, batch=B, N=N, seed=1, n_objects=4)
     r = hs.solve(mhs, N, 0.05, wl["x0"], wl["yref"], wl["yref_e"], np.zeros((B, N + 1, 4)), wl["u_init"], objid=wl["object_id"],
                  mode=mode, prepare=True, shift=True, qp_kernel=kern, max_sqp_iter=3)

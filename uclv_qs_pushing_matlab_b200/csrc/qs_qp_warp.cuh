@@ -177,12 +177,15 @@ enum : int { QW_TM_AB = 0, QW_TM_BV = 16, QW_TM_HH = 20, QW_TM_G = 24, QW_TM_IT 
 QS_HD constexpr int qw_tm_stage(int C) { return C >= 3 ? QW_TM_STAGE_LONG : QW_TM_STAGE; }
 // Mapping of a horizon onto a warp.  seg = 16: two problems per warp, one per 16-lane segment, each lane owning
 // C = ceil((N+1)/16) stages; seg = 32: one problem per warp, C = ceil((N+1)/32).  Measured on B200 (tools/gpu_half_sweep.py):
-// the two-problem mapping wins up to N = 55 (N = 10: +65 %, 20: +31 %, 31: +20 %, 40: +8 %, 47: +15 %, 55: +5 %,
-// 63: -1 %): the same 8 problems are resident per SM either way (shared memory), but one instruction stream serves
+// the two-problem mapping wins for every horizon it fits (N = 10: +65 %, 20: +31 %, 31: +20 %, 40: +8 %, 47: +15 %, 55: +5 %;
+// 56..63: +7..15 % once the work queue pairs problems of equal iteration count, k_qp_order): the same 8 problems are resident per SM either way (shared memory), but one instruction stream serves
 // two problems with 85-100 % instead of 35-65 % of the lanes busy and the scans are one step shorter.
+#ifndef QW_PLAN_MAX
+#define QW_PLAN_MAX 63            // longest horizon that runs two problems per warp (C = ceil((N+1)/16) <= 4)
+#endif
 struct QwPlan { int C, seg; };
 QS_HD constexpr QwPlan qp_warp_plan(int N) {
-    return (N <= 55) ? QwPlan{(N + 1 + 15) / 16, 16} : QwPlan{(N + 1 + 31) / 32, 32};
+    return (N <= QW_PLAN_MAX) ? QwPlan{(N + 1 + 15) / 16, 16} : QwPlan{(N + 1 + 31) / 32, 32};
 }
 QS_HD constexpr int qp_warp_chunk(int N) { return qp_warp_plan(N).C; }
 QS_HD constexpr int qp_warp_lanes(int N, int C) { return (N + 1 + C - 1) / C; }
