@@ -210,14 +210,14 @@ __global__ void __launch_bounds__(1024) k_qp_order(SolverDev S, int* __restrict_
     if (threadIdx.x < QO_BINS) cnt[threadIdx.x] = 0;
     __syncthreads();
     for (int b = threadIdx.x; b < S.B; b += blockDim.x) {
-        const int k = S.qp_iter[b];
+        const int k = S.qp_last[b];
         atomicAdd(&cnt[QO_BINS - 1 - (k < 0 ? 0 : (k > QO_BINS - 1 ? QO_BINS - 1 : k))], 1);
     }
     __syncthreads();
     if (threadIdx.x == 0) { int a = 0; for (int i = 0; i < QO_BINS; ++i) { pos[i] = a; a += cnt[i]; } }
     __syncthreads();
     for (int b = threadIdx.x; b < S.B; b += blockDim.x) {
-        const int k = S.qp_iter[b];
+        const int k = S.qp_last[b];
         order[atomicAdd(&pos[QO_BINS - 1 - (k < 0 ? 0 : (k > QO_BINS - 1 ? QO_BINS - 1 : k))], 1)] = b;
     }
 }

@@ -38,6 +38,7 @@ struct SolverDev {
     // bookkeeping
     int *status, *sqp_iter, *qp_iter, *cold, *done, *qpstat, *ndone;   // ndone[0]: SQP finished count, ndone[1]: QP work-queue head
     int *order;             // work-queue order of the warp QP kernel (nullptr: index order), see k_qp_order
+    int *qp_last;           // IPM iterations of the most recent QP of every problem (the predictor behind `order`)
     double *cost, *res, *alpha;
     // SQP merit weights
     double *wpi, *wlam, *wx0;
@@ -300,6 +301,7 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm_warp, int pe
         if (live && lane == 0) {
             S.qpstat[b] = st.status;
             if (apply) S.qp_iter[b] = st.it; else S.qp_iter[b] += st.it;
+            if (S.qp_last) S.qp_last[b] = st.it;
         }
         if (apply) {
             // K5 (RTI): x += dx, u += du, cost, status — each lane updates its own stages

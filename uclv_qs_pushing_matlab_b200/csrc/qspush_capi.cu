@@ -311,7 +311,7 @@ int qspush_solver_create(const qspush_model* const* models, int nmodels, int N, 
     for (auto& sl : slabs) total += al(sl.rows * Bp);
     const size_t n_const = al((size_t)N * 36) + al(16) + al((size_t)N * 21) + al(10) + al((size_t)nmodels * MODEL_DOUBLES);
     s->stage_doubles = (size_t)(N + 1) * 6 * Bp;                 // largest AoS field (x: (N+1)*4, lam: N*6)
-    const size_t n_int = 9 * Bp + 32;
+    const size_t n_int = 10 * Bp + 32;
     s->arena_bytes = (total + n_const + al(s->stage_doubles)) * 8 + (n_int + Bp) * sizeof(int) + 1024;
     CK(cudaMalloc(&s->arena, s->arena_bytes));
     CK(cudaMemsetAsync(s->arena, 0, s->arena_bytes, s->stream));
@@ -329,6 +329,7 @@ int qspush_solver_create(const qspush_model* const* models, int nmodels, int N, 
     int* objid = icur; icur += Bp;
     s->d_istage = icur; icur += Bp;
     s->d_order = icur; icur += Bp;
+    D.qp_last = icur; icur += Bp;
     D.ndone = icur; icur += 32;
     D.objid = objid;
     D.B = batch; D.Bp = s->Bp; D.N = N; D.nmodels = nmodels; D.dt = dt;
@@ -587,7 +588,7 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
     CK(cudaMemsetAsync(D.ndone + 1, 0, sizeof(int), s->stream));                       // work-queue head
     SolverDev Dq = D;
     Dq.order = nullptr;
-    if (apply && s->B > nsm * Wl && !std::getenv("QSPUSH_NO_ORDER")) {                 // RTI with more problems than resident slots
+    if (s->B > nsm * Wl * ppw_seg && !std::getenv("QSPUSH_NO_ORDER")) {                // more problems than resident slots
         k_qp_order<<<1, 1024, 0, s->stream>>>(D, s->d_order);
         Dq.order = s->d_order;
         s->launches++;
