@@ -307,7 +307,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(h_u0.numel() * 8 + h_status.numel() * 4), "ms_per_step": 1e3 * t_e2e_max / args.steps},
         "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": ("k_qp_warp<2> (Mehrotra IPM, warp per problem, parallel-in-time Riccati scan, state in shared memory + TMEM)" if args.qp_kernel else "k_qp (Riccati/Mehrotra IPM, one problem per thread)"), "achieved": achieved_gbs, "peak": hbm_peak,
+        "roofline": {"bound": "hbm", "kernel": ("k_qp_warp<3,0,16> (Mehrotra IPM, two problems per warp, parallel-in-time Riccati scans, state in shared memory + TMEM, ordered work queue)" if args.qp_kernel else "k_qp (Riccati/Mehrotra IPM, one problem per thread)"), "achieved": achieved_gbs, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src + " (of measured)",
                      "algorithmic_bytes_per_launch": B * ALG_BYTES_PER_ITER, "kernel_ms": qp_avg_ms,
                      "kernel_share_of_step": qp_avg_ms / (sum(step_ms) / len(step_ms)),
@@ -315,7 +315,7 @@ def run_ours(args):
                               "peak_source": "cuBLAS DGEMM 4096^3 measured in this run", "flops_per_iteration": alg_flops_per_iter(k_ipm),
                               "ncu_pipe_fp64_active_pct": pipe_pct,
                               "what": "achieved = algorithmic flops of the serial Riccati IPM (SURVEY 8d); ncu_pipe_fp64_active_pct = "
-                                      "sm__pipe_fp64_cycles_active of the executed parallel-in-time algorithm (profiles/r01_v3_qp_ncu_summary.md)"},
+                                      "sm__pipe_fp64_cycles_active of the executed parallel-in-time algorithm (profiles/r01_v4_qp_ncu_summary.md)"},
                      "note": "the path is FP64-pipe / dependent-chain bound, not HBM bound (SURVEY 8d): the HBM fraction is reported "
                              "because the schema asks for it, the fp64 object is the relevant roofline (see DESIGN.md)"},
         "cpu_baseline": cpu_base,
@@ -339,7 +339,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ppw", type=int, default=0, help="QP kernel packing (problems per warp), 0 = auto")
-    ap.add_argument("--qp-kernel", type=int, default=1, help="1 = warp per problem (parallel-in-time; what auto picks at 4096/GPU), 0 = one problem per thread")
+    ap.add_argument("--qp-kernel", type=int, default=1, help="1 = warp kernel (parallel-in-time, one or two problems per warp; what auto picks), 0 = one problem per thread")
     ap.add_argument("--latency-solves", type=int, default=1000, help="solves per B=1 latency measurement")
     ap.add_argument("--cpu-passes", type=int, default=3, help="passes of the oracle over the batch for cpu_baseline")
     args = ap.parse_args()

@@ -57,7 +57,7 @@ typedef struct {
     double alpha_min, alpha_reduction, eps_sufficient_descent;   /* 0.05, 0.7, 1e-4           */
     int    matlab_single_quirk;     /* reproduce MATLAB `single` rounding of mod(s,b) in prepare */
     int    problems_per_warp;       /* thread-per-problem QP kernel packing: 32, 16, 8, 4 (0 = auto) */
-    int    qp_kernel;               /* 2 = auto by batch size (default); 1 = warp per problem, parallel-in-time Riccati (N <= 127); 0 = one problem per thread */
+    int    qp_kernel;               /* 2 = auto (default: the warp kernel whenever N <= 127); 1 = warp kernel, parallel-in-time Riccati, one or two problems per warp (N <= 127); 0 = one problem per thread */
     int    h_variant;               /* constraint set h of the OCP: 0 = [s; u_n; u_t] (NMPC_controller.m:237, default);
                                        1 = the authors' parked set [u_n; u_t - v_bound(s); u_t + v_bound(s)] (:226-238) with
                                        v_bound from qspush_ctrl; selecting it resets constr_lh / constr_uh to

@@ -194,8 +194,8 @@ __global__ void __launch_bounds__(32) k_qp(SolverDev S, IpmOpts o, int ppw, int 
     qp_one(S, o, b, apply);
 }
 
-// K4 v2: warp per problem, persistent CTAs of up to QW_MAX_WARPS warps (one CTA per SM); finished warps pull the
-// next problem from a global work queue (S.ndone[1]).  The IPM state of each problem lives in its warp's slice of
+// K4 v2: one or two problems per warp (SEG = 32 / 16 lanes each), persistent CTAs of up to QW_MAX_WARPS warps (one CTA
+// per SM); finished warps pull the next problem(s) from a global work queue (S.ndone[1], order S.order).  The IPM state of each problem lives in its warp's slice of
 // the dynamic shared memory; the read-only linearisation lives in tensor memory: the CTA allocates all 512 TMEM
 // columns, warp w owns TMEM lanes 32*(w%4).. (the quarter the hardware lets it address) and columns 256*(w/4)..
 constexpr int QW_MAX_WARPS = 8;

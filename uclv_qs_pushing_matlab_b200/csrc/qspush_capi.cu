@@ -547,7 +547,7 @@ int qspush_prepare(qspush_solver* s) {
     return QSPUSH_OK;
 }
 
-// launch the QP kernel selected by opts.qp_kernel: 1 (default when the horizon fits) = warp per problem,
+// launch the QP kernel selected by opts.qp_kernel: 1 (default when the horizon fits) = warp kernel (one or two problems per warp),
 // parallel-in-time; 0 = one problem per thread (any horizon)
 static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, int ppw, int apply) {
     int nsm = 148;
