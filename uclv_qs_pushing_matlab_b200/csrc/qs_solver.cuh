@@ -165,6 +165,38 @@ QS_HD void linearise_one(const SolverDev& S, const double* __restrict__ Mall, in
     }
 }
 
+// stage cost at given (x_k, u_k): 1/2 (y - y_ref)' dt W (y - y_ref), y = [x; u]
+QS_HD double stage_cost_at(const SolverDev& S, int k, int b, const double x[4], const double u[2]) {
+    double r[6];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = x[i] - QS_EL(S.yref, k * 6 + i, b);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) r[4 + i] = u[i] - QS_EL(S.yref, k * 6 + 4 + i, b);
+    const double* W = S.Wdt + (size_t)k * 36;
+    double q = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double a = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) a = fma(W[i + 6 * j], r[j], a);
+        q = fma(r[i], a, q);
+    }
+    return 0.5 * q;
+}
+QS_HD double terminal_cost_at(const SolverDev& S, int b, const double x[4]) {
+    double r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = x[i] - QS_EL(S.yref_e, i, b);
+    double q = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double a = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a = fma(S.We[i + 4 * j], r[j], a);
+        q = fma(r[i], a, q);
+    }
+    return 0.5 * q;
+}
 QS_HD double stage_cost(const SolverDev& S, int k, int b) {
     double r[6];
 #pragma unroll
@@ -309,17 +341,21 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm_warp, int pe
             double cost = 0.0;
             int nan = 0;
             if (live) {
+                // the step comes from shared memory and the cost is evaluated on the registers that are being stored:
+                // every global load of the epilogue is independent (one latency exposure), nothing is read back
+                const int Lw_ = qp_warp_lanes(N, C);
 #pragma unroll 1
                 for (int j = 0; j < C; ++j) {
                     const int k = lane * C + j;
                     if (k > N) continue;
+                    double xk[4], uk[2] = {0.0, 0.0};
                     if (k < N) {
 #pragma unroll
-                        for (int i = 0; i < 2; ++i) { const double v = QS_EL(S.u, k * 2 + i, b) + QS_EL(S.z, k * 6 + i, b); QS_EL(S.u, k * 2 + i, b) = v; nan |= !(v == v); }
+                        for (int i = 0; i < 2; ++i) { uk[i] = QS_EL(S.u, k * 2 + i, b) + QW_SM(R_Z + i, j); QS_EL(S.u, k * 2 + i, b) = uk[i]; nan |= !(uk[i] == uk[i]); }
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) QS_EL(S.x, k * 4 + i, b) += QS_EL(S.z, k * 6 + 2 + i, b);
-                    cost += (k < N) ? stage_cost(S, k, b) : terminal_cost(S, b);
+                    for (int i = 0; i < 4; ++i) { xk[i] = QS_EL(S.x, k * 4 + i, b) + QW_SM(R_Z + 2 + i, j); QS_EL(S.x, k * 4 + i, b) = xk[i]; }
+                    cost += (k < N) ? stage_cost_at(S, k, b, xk, uk) : terminal_cost_at(S, b, xk);
                 }
             }
             cost = w.template wsum<SEG>(cost);
