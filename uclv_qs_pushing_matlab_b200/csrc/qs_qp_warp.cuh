@@ -183,9 +183,13 @@ QS_HD constexpr int qw_tm_stage(int C) { return C >= 3 ? QW_TM_STAGE_LONG : QW_T
 #ifndef QW_PLAN_MAX
 #define QW_PLAN_MAX 63            // longest horizon that runs two problems per warp (C = ceil((N+1)/16) <= 4)
 #endif
+#ifndef QW_PLAN8_MAX
+#define QW_PLAN8_MAX (-1)         // longest horizon that runs four problems per warp (8-lane segments); -1: never
+#endif
 struct QwPlan { int C, seg; };
 QS_HD constexpr QwPlan qp_warp_plan(int N) {
-    return (N <= QW_PLAN_MAX) ? QwPlan{(N + 1 + 15) / 16, 16} : QwPlan{(N + 1 + 31) / 32, 32};
+    return (N <= QW_PLAN8_MAX) ? QwPlan{(N + 1 + 7) / 8, 8}
+         : (N <= QW_PLAN_MAX) ? QwPlan{(N + 1 + 15) / 16, 16} : QwPlan{(N + 1 + 31) / 32, 32};
 }
 QS_HD constexpr int qp_warp_chunk(int N) { return qp_warp_plan(N).C; }
 QS_HD constexpr int qp_warp_lanes(int N, int C) { return (N + 1 + C - 1) / C; }

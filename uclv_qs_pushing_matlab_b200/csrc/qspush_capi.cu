@@ -597,7 +597,17 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
     CK(cudaFuncSetAttribute(k_qp_warp<CC, HV, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     k_qp_warp<CC, HV, SEG><<<blocks, 32 * Wl, smem, s->stream>>>(Dq, io, apply, pwd)
     const int hvf = D.h_variant ? 1 : 0;
-    switch ((plan.seg == 16 ? 16 : 0) + C * 2 + hvf) {
+    switch ((plan.seg == 16 ? 16 : plan.seg == 8 ? 32 : 0) + C * 2 + hvf) {
+#if QW_PLAN8_MAX >= 0
+        case 32 + 2: QW_LAUNCH(1, 0, 8); break;
+        case 32 + 3: QW_LAUNCH(1, 1, 8); break;
+        case 32 + 4: QW_LAUNCH(2, 0, 8); break;
+        case 32 + 5: QW_LAUNCH(2, 1, 8); break;
+        case 32 + 6: QW_LAUNCH(3, 0, 8); break;
+        case 32 + 7: QW_LAUNCH(3, 1, 8); break;
+        case 32 + 8: QW_LAUNCH(4, 0, 8); break;
+        case 32 + 9: QW_LAUNCH(4, 1, 8); break;
+#endif
         case 16 + 2: QW_LAUNCH(1, 0, 16); break;
         case 16 + 3: QW_LAUNCH(1, 1, 16); break;
         case 16 + 4: QW_LAUNCH(2, 0, 16); break;
