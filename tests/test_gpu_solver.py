@@ -429,3 +429,23 @@ def test_device_resident_closed_loop():
     c.set_reference_trajectory(traj.T)
     out = q.helper.closed_loop_device(p, c, x0s, (steps - 1) * dt, offset=off)
     assert out[0].shape == (B, steps) and np.array_equal(np.stack([out[4], out[5]], -1), np.transpose(r["u_log"], (1, 0, 2))) and out[7].all()
+
+
+@pytest.mark.parametrize("N", [1, 7, 15, 16, 31, 32, 47, 48, 63, 64, 96, 127])
+def test_every_warp_mapping_vs_thread_kernel(N):
+    """The warp QP kernel in every mapping (16- / 32-lane segments, C = 1..4, full and partial last lanes, odd batch:
+    idle partner segment) against the independent one-problem-per-thread kernel, 4 shapes, two solves in a row (the
+    second one runs with the ordered work queue)."""
+    gms = [gpu_model(n) for n in OBJECT_ORDER]
+    B = 37
+    wl = make_rti_workload(None, batch=B, N=N, seed=N, n_objects=4)
+    out = []
+    for kern in (1, 0):
+        s = q.Solver(gms, N, 0.05, B, qp_kernel=kern)
+        _load(s, wl)
+        for rep in range(2):
+            s.set("u", wl["u_init"]); s.prepare(); s.solve()
+        out.append((s.get("u").reshape(B, -1), s.get_int("status"), s.get("res").max(1)))
+    d = np.abs(out[0][0] - out[1][0]).max(1)
+    assert np.array_equal(out[0][1], out[1][1]) and (out[0][1] == 0).all()
+    assert np.median(d) < 1e-9 and d.max() < 2e-4 and (out[0][2] < 1e-6).all()
