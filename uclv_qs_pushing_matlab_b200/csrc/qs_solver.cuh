@@ -183,6 +183,38 @@ QS_HD double stage_cost_at(const SolverDev& S, int k, int b, const double x[4], 
     }
     return 0.5 * q;
 }
+// (same, with the reference already in registers)
+QS_HD double stage_cost_ref(const SolverDev& S, int k, const double x[4], const double u[2], const double yref[6]) {
+    double r[6];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = x[i] - yref[i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) r[4 + i] = u[i] - yref[4 + i];
+    const double* W = S.Wdt + (size_t)k * 36;
+    double q = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double a = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) a = fma(W[i + 6 * j], r[j], a);
+        q = fma(r[i], a, q);
+    }
+    return 0.5 * q;
+}
+QS_HD double terminal_cost_ref(const SolverDev& S, const double x[4], const double yref_e[4]) {
+    double r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = x[i] - yref_e[i];
+    double q = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double a = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a = fma(S.We[i + 4 * j], r[j], a);
+        q = fma(r[i], a, q);
+    }
+    return 0.5 * q;
+}
 QS_HD double terminal_cost_at(const SolverDev& S, int b, const double x[4]) {
     double r[4];
 #pragma unroll
@@ -327,8 +359,29 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm_warp, int pe
         if (idle) continue;
         const int fin = qw_iterate<Ctx, C, HV, SEG>(w, sm, Qc, st);
         if (fin == 0) continue;
-        // ---- the problems of this warp are finished: write back, K5 epilogue, fetch the next ones
+        // ---- the problems of this warp are finished: fetch the next ones FIRST (the queue atomic and the first touch of
+        // the next problem's linearisation then overlap the write-back and the epilogue), write back, K5 epilogue, bind
         const bool live = b >= 0;
+        const int b_next = next(seg);
+        QW_TICK(10);
+        if (b_next >= 0) {
+            const int Lw_ = qp_warp_lanes(N, C);
+            if (lane < Lw_) {
+#pragma unroll 1
+                for (int j = 0; j < C; ++j) {
+                    const int k = lane * C + j;
+                    if (k >= N) continue;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { asm volatile("prefetch.global.L2 [%0];" ::"l"(&QS_EL(S.A, k * 8 + i, b_next))); asm volatile("prefetch.global.L2 [%0];" ::"l"(&QS_EL(S.Bm, k * 8 + i, b_next))); }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(&QS_EL(S.g, k * 6 + i, b_next)));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { asm volatile("prefetch.global.L2 [%0];" ::"l"(&QS_EL(S.b, k * 4 + i, b_next))); asm volatile("prefetch.global.L2 [%0];" ::"l"(&QS_EL(S.hv, k * 4 + i, b_next))); }
+#endif
+                }
+            }
+        }
         qw_writeback<Ctx, C, SEG>(w, sm, Qc, V, live);
         if (live && lane == 0) {
             S.qpstat[b] = st.status;
@@ -344,18 +397,30 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm_warp, int pe
                 // the step comes from shared memory and the cost is evaluated on the registers that are being stored:
                 // every global load of the epilogue is independent (one latency exposure), nothing is read back
                 const int Lw_ = qp_warp_lanes(N, C);
-#pragma unroll 1
+                // all loads of the lane's C stages first (the stores below could alias them as far as the compiler knows)
+                double xo[C][4], uo[C][2], yr[C][6];
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    const int k = lane * C + j;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) xo[j][i] = (k <= N) ? QS_EL(S.x, k * 4 + i, b) : 0.0;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) uo[j][i] = (k < N) ? QS_EL(S.u, k * 2 + i, b) : 0.0;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) yr[j][i] = (k < N) ? QS_EL(S.yref, k * 6 + i, b) : ((k == N && i < 4) ? QS_EL(S.yref_e, i, b) : 0.0);
+                }
+#pragma unroll
                 for (int j = 0; j < C; ++j) {
                     const int k = lane * C + j;
                     if (k > N) continue;
                     double xk[4], uk[2] = {0.0, 0.0};
                     if (k < N) {
 #pragma unroll
-                        for (int i = 0; i < 2; ++i) { uk[i] = QS_EL(S.u, k * 2 + i, b) + QW_SM(R_Z + i, j); QS_EL(S.u, k * 2 + i, b) = uk[i]; nan |= !(uk[i] == uk[i]); }
+                        for (int i = 0; i < 2; ++i) { uk[i] = uo[j][i] + QW_SM(R_Z + i, j); QS_EL(S.u, k * 2 + i, b) = uk[i]; nan |= !(uk[i] == uk[i]); }
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { xk[i] = QS_EL(S.x, k * 4 + i, b) + QW_SM(R_Z + 2 + i, j); QS_EL(S.x, k * 4 + i, b) = xk[i]; }
-                    cost += (k < N) ? stage_cost_at(S, k, b, xk, uk) : terminal_cost_at(S, b, xk);
+                    for (int i = 0; i < 4; ++i) { xk[i] = xo[j][i] + QW_SM(R_Z + 2 + i, j); QS_EL(S.x, k * 4 + i, b) = xk[i]; }
+                    cost += (k < N) ? stage_cost_ref(S, k, xk, uk, yr[j]) : terminal_cost_ref(S, xk, yr[j]);
                 }
             }
             cost = w.template wsum<SEG>(cost);
@@ -368,7 +433,7 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm_warp, int pe
                 S.status[b] = nan ? 1 : (st.status == 2 ? 4 : 0);
             }
         }
-        b = next(seg);
+        b = b_next;
         QW_TICK(10);
         if (w.wany(b >= 0 ? 1 : 0)) bind(b);
         QW_TICK(9);
