@@ -98,12 +98,50 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock / throttle-reason sampler for the timed region.
+
+    NVML in a thread (every 2 ms, initialised before the region starts, so that even a 40 ms region is sampled under load);
+    `nvidia-smi -lms` as the fallback when the NVML binding is missing (its first row arrives only after its own start-up).
+    """
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         self.index, self.rows, self.proc = index, [], None
+        self.nv, self.h, self.samples, self.run, self.thr = None, None, [], False, None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            if uuid is not None:
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID("GPU-" + str(uuid))
+                except Exception:
+                    h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                ids = [v for v in vis.split(",") if v.strip().isdigit()]
+                h = nv.nvmlDeviceGetHandleByIndex(int(ids[index]) if index < len(ids) else index)
+            self.nv, self.h = nv, h
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv, h = self.nv, self.h
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while self.run:
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(reasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nv is not None:
+            self.run = True
+            self.thr = threading.Thread(target=self._poll, daemon=True)
+            self.thr.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -116,6 +154,17 @@ class ClockSampler:
             self.rows.append([c.strip() for c in ln.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            self.run = False
+            self.thr.join(timeout=1.0)
+            sm = [s[0] for s in self.samples]
+            bits = 0
+            for s in self.samples:
+                bits |= s[1]
+            # NVML clocks-event-reason bits: sw_power_cap 0x4, hw_slowdown 0x8, sw_thermal 0x20, hw_thermal 0x40
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(n for b, n in names.items() if bits & b), "samples": len(sm), "source": "nvml, 2 ms period, inside the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -124,7 +173,7 @@ class ClockSampler:
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -184,7 +233,7 @@ def run_ours(args):
     step_host()
 
     # ---- value: K steps, CUDA events on the solver's stream around each step, L2 flushed in between
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(dev), "uuid", None))
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     qp_ms, lin_ms, prep_ms, launches0 = [], [], [], solver.launches
     barrier()
@@ -315,7 +364,7 @@ def run_ours(args):
                               "peak_source": "cuBLAS DGEMM 4096^3 measured in this run", "flops_per_iteration": alg_flops_per_iter(k_ipm),
                               "ncu_pipe_fp64_active_pct": pipe_pct,
                               "what": "achieved = algorithmic flops of the serial Riccati IPM (SURVEY 8d); ncu_pipe_fp64_active_pct = "
-                                      "sm__pipe_fp64_cycles_active of the executed parallel-in-time algorithm (profiles/r01_v4_qp_ncu_summary.md)"},
+                                      "sm__pipe_fp64_cycles_active of the executed parallel-in-time algorithm (profiles/r01_v6_qp_ncu_summary.md)"},
                      "note": "the path is FP64-pipe / dependent-chain bound, not HBM bound (SURVEY 8d): the HBM fraction is reported "
                              "because the schema asks for it, the fp64 object is the relevant roofline (see DESIGN.md)"},
         "cpu_baseline": cpu_base,
@@ -349,4 +398,10 @@ def main():
 
 
 if __name__ == "__main__":
+    # Exactly ONE line on stdout (the JSON line): libraries that chat on fd 1 (NCCL prints its version there under torchrun)
+    # are sent to stderr for the whole run, the JSON line goes to the original stdout.
+    sys.stdout.flush()
+    _json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _json_out
     sys.exit(main())

@@ -371,7 +371,7 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm_warp, int pe
                 for (int j = 0; j < C; ++j) {
                     const int k = lane * C + j;
                     if (k >= N) continue;
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(QW_NO_PREFETCH)
 #pragma unroll
                     for (int i = 0; i < 8; ++i) { asm volatile("prefetch.global.L2 [%0];" ::"l"(&QS_EL(S.A, k * 8 + i, b_next))); asm volatile("prefetch.global.L2 [%0];" ::"l"(&QS_EL(S.Bm, k * 8 + i, b_next))); }
 #pragma unroll
