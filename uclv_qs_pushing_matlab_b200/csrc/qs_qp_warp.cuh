@@ -362,6 +362,22 @@ QS_HD void aff_compose(double M[16], double d[4], const double Mp[16], const dou
     for (int i = 0; i < 4; ++i) d[i] = dn[i];
 }
 
+// M <- M Mp (4x4, row-major)
+QS_HD void mat4_mul(double M[16], const double Mp[16]) {
+    double Mn[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double b = 0.0;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) b = fma(M[4 * i + p], Mp[4 * p + j], b);
+            Mn[4 * i + j] = b;
+        }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) M[i] = Mn[i];
+}
+
 // closed-loop transition Abar = A - B K of a stage (row-major), A = [e1 e2 a3 a4]
 QS_HD void closed_loop(const StageLin& L, const double K0[4], const double K1[4], double Ab[16]) {
 #pragma unroll
@@ -426,9 +442,16 @@ QS_HD void qw_row_add(int hv, int c, double beta, double w, double* g6) {
 // One Newton solve with the current factorisation: rhs gt (R_GT rows) and r_b (R_RB) ->
 // step dz (R_GT rows, aliased), costate offsets p_k (R_PV), feed-forward k_ff (R_KFF).
 template <class Ctx, int C, int SEG>
-QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, bool live) {
+QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, bool live, int pass) {
     const int lane = w.lane() & (SEG - 1);
     const bool act = lane < Lw_ && live;
+    // The matrix parts of the two affine recursions depend on the factorisation only, not on the right-hand side: with TMEM room
+    // for one more 4x4 per lane (C <= 3) the chunk's composed backward matrix M = Abar_k0' ... Abar_k1' (stages k < N) is built by
+    // the predictor pass (pass 0) only and kept there; the corrector reloads it, and the forward chunk matrix of either pass is
+    // its transpose.  The vector parts are rolled through the stages directly (Abar' p = A'p - K'(B'p), forward_stage).  The
+    // terminal stage leaves M alone: a chunk matrix that reaches the terminal stage is never applied to a vector by the scan.
+    constexpr bool KEEP = (C <= 3);
+    constexpr int TM_M = C * qw_tm_stage(C);
     // ---- (a) local: d_k, kff0_k and the chunk's composed backward map  p_start = M p_end + d
     double M[16], d[4];
     bool acc_identity = true;
@@ -446,11 +469,13 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
             if constexpr (C >= 3) w.template tm_ld<16>(j * qw_tm_stage(C) + QW_TM_P, Pst);
             if (!act || k > N) continue;
             if (k == N) {                                       // terminal: p_N = rg_N (constant map)
+                if constexpr (!KEEP) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) M[i] = 0.0;
+                    for (int i = 0; i < 16; ++i) M[i] = 0.0;
+                    acc_identity = false;
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { d[i] = QW_SM(R_RG + 2 + i, j); QW_SM(R_PV + i, j) = d[i]; }
-                acc_identity = false;
                 continue;
             }
             double gt[6], Pb[4], K0[4], K1[4], Li[3], m[6];
@@ -467,20 +492,50 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
             double dk[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) { dk[i] = m[2 + i] - fma(K0[i], m[0], K1[i] * m[1]); QW_SM(R_PV + i, j) = dk[i]; }
-            double Ab[16], At[16];
-            closed_loop(L, K0, K1, Ab);
+            if constexpr (KEEP) {
+                // vector part of acc <- f_k o acc:  d <- Abar_k' d + d_k
+                {
+                    const double m0 = dot4(L.b1, d), m1 = dot4(L.b2, d);
+                    double dn[4];
+                    dn[0] = dk[0] + d[0] - fma(K0[0], m0, K1[0] * m1);
+                    dn[1] = dk[1] + d[1] - fma(K0[1], m0, K1[1] * m1);
+                    dn[2] = dk[2] + dot4(L.a3, d) - fma(K0[2], m0, K1[2] * m1);
+                    dn[3] = dk[3] + dot4(L.a4, d) - fma(K0[3], m0, K1[3] * m1);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 4; ++i) d[i] = dn[i];
+                }
+                if (pass == 0) {                                // matrix part: M <- Abar_k' M
+                    double Ab[16], At[16];
+                    closed_loop(L, K0, K1, Ab);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) At[4 * i + q] = Ab[4 * q + i];
-            // acc <- f_k o acc
-            if (!acc_identity) aff_compose(At, dk, M, d);
-            acc_identity = false;
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) M[i] = At[i];
+                        for (int q = 0; q < 4; ++q) At[4 * i + q] = Ab[4 * q + i];
+                    if (!acc_identity) mat4_mul(At, M);
+                    acc_identity = false;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) d[i] = dk[i];
+                    for (int i = 0; i < 16; ++i) M[i] = At[i];
+                }
+            } else {
+                double Ab[16], At[16];
+                closed_loop(L, K0, K1, Ab);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) At[4 * i + q] = Ab[4 * q + i];
+                // acc <- f_k o acc
+                if (!acc_identity) aff_compose(At, dk, M, d);
+                acc_identity = false;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) M[i] = At[i];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d[i] = dk[i];
+            }
         }
+    }
+    if constexpr (KEEP) {                                       // warp-collective TMEM accesses: every lane, outside divergent code
+        if (pass == 0) w.tm_st16(TM_M, M);
+        else w.template tm_ld<16>(TM_M, M);
     }
     // ---- (b) suffix scan over lanes (exchange through shared memory); afterwards d = p at the first stage of the chunk
     double* xa = sm + (size_t)qw_rows(C) * C * Lw_ + (size_t)lane * QW_XA;      // this lane's affine exchange slot
@@ -542,10 +597,30 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
     // ---- (d) forward: chunk's composed map dx_end = M dx_start + d, prefix scan, local rollout
     acc_identity = true;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) M[i] = (i % 5 == 0) ? 1.0 : 0.0;
-#pragma unroll
     for (int i = 0; i < 4; ++i) d[i] = 0.0;
-    {
+    if constexpr (KEEP) {
+        // forward chunk matrix Abar_k1 ... Abar_k0 = (backward chunk matrix)'
+        double Mb[16];
+        w.template tm_ld<16>(TM_M, Mb);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) M[4 * i + q] = Mb[4 * q + i];
+#pragma unroll 1
+        for (int j = 0; j < C; ++j) {
+            const int k = lane * C + j;
+            StageLin L;
+            qw_ld_lin(w, j * qw_tm_stage(C), L);
+            if (!act || k >= N) continue;
+            double K0[4], K1[4], bk[4], kff[2], u[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { K0[i] = QW_SM(R_K + i, j); K1[i] = QW_SM(R_K + 4 + i, j); bk[i] = QW_SM(R_RB + i, j); }
+            kff[0] = QW_SM(R_KFF, j); kff[1] = QW_SM(R_KFF + 1, j);
+            forward_stage(L, bk, K0, K1, kff, d, u);            // d <- Abar_k d + (r_b - B k_ff)
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) M[i] = (i % 5 == 0) ? 1.0 : 0.0;
 #pragma unroll 1
         for (int j = 0; j < C; ++j) {
             const int k = lane * C + j;
@@ -992,7 +1067,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             }
         }
         QW_TICK(5);
-        qp_warp_solve<Ctx, C, SEG>(w, sm, N, Lw_, !st.fin);
+        qp_warp_solve<Ctx, C, SEG>(w, sm, N, Lw_, !st.fin, pass);
         QW_TICK(6);
         if (pass == 0) {
             // step to the boundary of the affine step, mu_aff, centering parameter
