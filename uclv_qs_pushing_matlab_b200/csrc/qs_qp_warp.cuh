@@ -247,6 +247,9 @@ QS_HD void elem_identity(Elem& e) {
 }
 
 // e1 <- e1 (x) e2 : e1 covers the earlier interval (i -> j), (A2, C2, J2) the later one (j -> k).
+// JONLY: only J of the result is formed (last step of the suffix scan: A and C of the aggregate are never read again;
+// A2 and C2 are not referenced)
+template <bool JONLY = false>
 QS_HD void elem_combine(Elem& e1, const double A2[16], const double C2[10], const double J2[10]) {
     double L2[10], i2[4];
     chol4_psd(J2, L2, i2);
@@ -290,10 +293,22 @@ QS_HD void elem_combine(Elem& e1, const double A2[16], const double C2[10], cons
         for (int i = 0; i < 4; ++i) {
             double a = g[i], b = t[i];
 #pragma unroll
-            for (int p = 0; p < i; ++p) { a = fma(-Lw[LT(i, p)], Z[4 * p + c], a); b = fma(-Lw[LT(i, p)], Y[4 * p + c], b); }
+            for (int p = 0; p < i; ++p) { a = fma(-Lw[LT(i, p)], Z[4 * p + c], a); if constexpr (!JONLY) b = fma(-Lw[LT(i, p)], Y[4 * p + c], b); }
             Z[4 * i + c] = a * iw[i];
             Y[4 * i + c] = b * iw[i];
         }
+    }
+    if constexpr (JONLY) {                                     // J = Z'Z + J1 (same operation order as below)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                double b = e1.J[LT(i, j)];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) b = fma(Z[4 * p + i], Z[4 * p + j], b);
+                e1.J[LT(i, j)] = b;
+            }
+        return;
     }
     // FA = A1 - Y'Z ; FC = C1 - Y'Y (sym) ; J = Z'Z + J1
     double FA[16], FC[10];
@@ -358,6 +373,20 @@ QS_HD void aff_compose(double M[16], double d[4], const double Mp[16], const dou
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) M[i] = Mn[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[i] = dn[i];
+}
+
+// vector part of aff_compose only: d <- M dp + d (same operation order)
+QS_HD void aff_apply(const double M[16], double d[4], const double dp[4]) {
+    double dn[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double a = d[i];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) a = fma(M[4 * i + p], dp[p], a);
+        dn[i] = a;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) d[i] = dn[i];
 }
@@ -541,17 +570,23 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
     double* xa = sm + (size_t)qw_rows(C) * C * Lw_ + (size_t)lane * QW_XA;      // this lane's affine exchange slot
 #pragma unroll 1
     for (int dl = 1; dl < Lw_; dl <<= 1) {
+        const bool last = (dl << 1) >= Lw_;                    // after the last step only d is read
         w.sync();
-        xch_put(w, xa, act, M, 16); xch_put(w, xa + 16, act, d, 4);
+        if (!last) xch_put(w, xa, act, M, 16);
+        xch_put(w, xa + 16, act, d, 4);
         w.sync();
         if (act && lane + dl < Lw_) {
             double Mp[16], dp[4];
             const double* xp = xa + (size_t)dl * QW_XA;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) Mp[i] = xp[i];
-#pragma unroll
             for (int i = 0; i < 4; ++i) dp[i] = xp[16 + i];
-            aff_compose(M, d, Mp, dp);
+            if (last) {
+                aff_apply(M, d, dp);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) Mp[i] = xp[i];
+                aff_compose(M, d, Mp, dp);
+            }
         }
     }
     w.sync();
@@ -644,17 +679,23 @@ QS_HD void qp_warp_solve(const Ctx& w, double* __restrict__ sm, int N, int Lw_, 
     }
 #pragma unroll 1
     for (int dl = 1; dl < Lw_; dl <<= 1) {
+        const bool last = (dl << 1) >= Lw_;                    // after the last step only d is read
         w.sync();
-        xch_put(w, xa, act, M, 16); xch_put(w, xa + 16, act, d, 4);
+        if (!last) xch_put(w, xa, act, M, 16);
+        xch_put(w, xa + 16, act, d, 4);
         w.sync();
         if (act && lane - dl >= 0) {
             double Mp[16], dp[4];
             const double* xp = xa - (size_t)dl * QW_XA;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) Mp[i] = xp[i];
-#pragma unroll
             for (int i = 0; i < 4; ++i) dp[i] = xp[16 + i];
-            aff_compose(M, d, Mp, dp);
+            if (last) {
+                aff_apply(M, d, dp);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) Mp[i] = xp[i];
+                aff_compose(M, d, Mp, dp);
+            }
         }
     }
     w.sync();
@@ -966,18 +1007,26 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
     const size_t xstride = (C >= 2) ? (size_t)qw_rows(C) : (size_t)QW_XE;     // distance between neighbouring lanes' slots
 #pragma unroll 1
     for (int dl = 1; dl < Lw_; dl <<= 1) {
+        const bool last = (dl << 1) >= Lw_;                    // after the last step only J is read (P at the chunk boundaries)
         w.sync();
-        xch_put(w, xeA, act, E.A, 16); xch_put(w, xeCJ, act, E.C, 10); xch_put(w, xeCJ + 10, act, E.J, 10);
+        if (!last) { xch_put(w, xeA, act, E.A, 16); xch_put(w, xeCJ, act, E.C, 10); }
+        xch_put(w, xeCJ + 10, act, E.J, 10);
         w.sync();
         if (act && lane + dl < Lw_) {
             double A2[16], C2[10], J2[10];
             const double* pA = xeA + (size_t)dl * xstride;
             const double* pCJ = xeCJ + (size_t)dl * xstride;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) A2[i] = pA[i];
+            for (int i = 0; i < 10; ++i) J2[i] = pCJ[10 + i];
+            if (last) {
+                elem_combine<true>(E, A2, C2, J2);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 10; ++i) { C2[i] = pCJ[i]; J2[i] = pCJ[10 + i]; }
-            elem_combine(E, A2, C2, J2);
+                for (int i = 0; i < 16; ++i) A2[i] = pA[i];
+#pragma unroll
+                for (int i = 0; i < 10; ++i) C2[i] = pCJ[i];
+                elem_combine<false>(E, A2, C2, J2);
+            }
         }
     }
     w.sync();
