@@ -138,10 +138,10 @@ def test_dynamics_and_jacobian_vs_sympy():
     m = orc.Model.create(S, P, 3, mu, c, single_quirk=False)
     rng = np.random.default_rng(3)
     knots = np.unique(S)
-    for span in (2, 11, 20, 29):
+    for span in (2, 20):                                     # (each span costs ~30 s of symbolic differentiation)
         lo, hi = knots[span], knots[span + 1]
         funs, cone = _sympy_dynamics(S, P, m.c1, lo, m.b, mu, c)
-        for _ in range(4):
+        for _ in range(3):
             sv = rng.uniform(lo + 1e-5, hi - 1e-5); thv = rng.uniform(-3, 3); unv = rng.uniform(2e-3, 0.03)
             gl, gr = [float(v) for v in cone(thv, sv, unv, 0.0)]
             for mode, r in (("st", gr + (gl - gr) * rng.uniform(0.1, 0.9)), ("sl", gl + rng.uniform(0.1, 1.0)), ("sr", gr - rng.uniform(0.1, 1.0))):
