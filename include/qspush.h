@@ -188,6 +188,15 @@ typedef struct {
 } qspush_loop_opts;
 int qspush_closed_loop(qspush_solver* s, const double* traj, int T, const double* offset, double* x, int steps,
                        const qspush_loop_opts* lo, double* log_x, double* log_u, int* log_status, qspush_mem mem);
+/* NMPC_controller.set_reference_trajectory (NMPC_controller.m:425-431) for the batch: the reference columns stay on
+ * the device; traj [T][6] = [x_ref(4); u_ref(2)] shared by all problems, offset [batch][6] added per problem (NULL:
+ * none); both in `mem`, copied (the caller may free them).  Replaces a previously set trajectory. */
+int qspush_set_reference_trajectory(qspush_solver* s, const double* traj, int T, const double* offset, qspush_mem mem);
+/* get_y_ref + the per-stage cost_y_ref / cost_y_ref_e calls of NMPC_controller.solve (NMPC_controller.m:307-313,
+ * 343-348) for control period idx (1-based): stage k gets column min(idx + k, T), the terminal reference the x part
+ * of the last window column.  Asynchronous on the solver's stream; with it a control period moves only x0 (in) and
+ * u0 / status (out) between host and device. */
+int qspush_set_reference_window(qspush_solver* s, int idx);
 /* wait for everything queued on the solver's stream */
 int qspush_sync(qspush_solver* s);
 /* the solver's cudaStream_t (as void*) so callers can order their own work / events on it */

@@ -56,6 +56,10 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     } else if (!strcmp(cmd, "prepare")) chk(qspush_prepare((qspush_solver*)hnd(prhs[1])));
     else if (!strcmp(cmd, "solve")) chk(qspush_solve((qspush_solver*)hnd(prhs[1])));
     else if (!strcmp(cmd, "shift")) chk(qspush_shift((qspush_solver*)hnd(prhs[1])));
+    else if (!strcmp(cmd, "set_reference")) {
+        /* y_ref is 6 x T column-major == [T][6] (controller.y_ref, NMPC_controller.m:425-431); kept on the device */
+        chk(qspush_set_reference_trajectory((qspush_solver*)hnd(prhs[1]), mxGetPr(prhs[2]), (int)mxGetDimensions(prhs[2])[1], NULL, QSPUSH_MEM_HOST));
+    } else if (!strcmp(cmd, "reference_window")) chk(qspush_set_reference_window((qspush_solver*)hnd(prhs[1]), (int)mxGetScalar(prhs[2])));
     else if (!strcmp(cmd, "stat")) { double v = 0; chk(qspush_get_stat((qspush_solver*)hnd(prhs[1]), (qspush_stat)(int)mxGetScalar(prhs[2]), &v)); plhs[0] = mxCreateDoubleScalar(v); }
     else if (!strcmp(cmd, "closed_loop")) {
         /* traj is 6 x T column-major == [T][6]; x0 is 4 x batch == [batch][4]: the C-ABI layouts */

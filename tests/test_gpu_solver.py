@@ -63,6 +63,47 @@ def test_set_get_roundtrip_and_errors():
     assert torch.equal(out, t)                                    # device-pointer path, no host copies
 
 
+def test_reference_trajectory_window_on_device():
+    """qspush_set_reference_trajectory / qspush_set_reference_window = NMPC_controller.set_reference_trajectory (:425-431) and the
+    get_y_ref window + per-stage cost_y_ref calls of NMPC_controller.solve (:307-313, 343-348), kept on the device."""
+    import torch
+    gm = gpu_model("santal")
+    B, N, T = 37, 20, 30
+    s = q.Solver([gm], N, 0.05, B)
+    with pytest.raises(q.QspushError):
+        s.set_reference_window(1)                                  # no trajectory yet
+    rng = np.random.default_rng(1)
+    traj, off = rng.standard_normal((T, 6)), rng.standard_normal((B, 6))
+
+    def expect(idx, offset):
+        cols = np.minimum(idx + np.arange(N), T) - 1               # stage k: column min(idx + k, T) (1-based), clamped at the end
+        y = traj[cols][None, :, :] + (offset[:, None, :] if offset is not None else 0.0)
+        return np.broadcast_to(y, (B, N, 6)), np.broadcast_to(y[:, N - 1, :4], (B, 4))
+
+    s.set_reference_trajectory(traj, off)
+    for idx in (1, 5, T - 3, T + 10):
+        s.set_reference_window(idx)
+        y, ye = expect(idx, off)
+        assert np.array_equal(s.get("yref"), y) and np.array_equal(s.get("yref_e"), ye)
+    with pytest.raises(q.QspushError):
+        s.set_reference_window(0)                                  # 1-based
+    s.set_reference_trajectory(torch.from_numpy(traj).cuda())      # device pointer, no offset: replaces the previous one
+    s.set_reference_window(2)
+    y, ye = expect(2, None)
+    assert np.array_equal(s.get("yref"), y) and np.array_equal(s.get("yref_e"), ye)
+    with pytest.raises(q.QspushError):
+        s.set_reference_trajectory(np.zeros((4, 5)))
+    # a control period through the window is the field-by-field control period
+    wl = make_rti_workload(None, batch=B, N=N, seed=7)
+    tr = np.zeros((N, 6)); tr[:, 0] = 0.01 * (np.arange(N) * 0.05)
+    of = np.zeros((B, 6)); of[:, :2] = wl["x0"][:, :2]
+    s.set_reference_trajectory(tr, of)
+    _load(s, wl); s.prepare(); s.solve(); u_a = s.get("u")
+    s.set("x0", wl["x0"]); s.set_reference_window(1); s.set("u", wl["u_init"]); s.set_int("cold", np.zeros(B, dtype=np.int32))
+    s.prepare(); s.solve()
+    assert np.array_equal(s.get("yref"), wl["yref"]) and np.array_equal(s.get("u"), u_a)
+
+
 @pytest.mark.parametrize("qp_kernel", [1, 0], ids=["warp_scan", "thread"])
 @pytest.mark.parametrize("name,N", [("santal", 40), ("montana", 10), ("balea", 100), ("santal", 20), ("montana", 55), ("santal", 60)])
 def test_prepare_qp_rti_vs_oracle(name, N, qp_kernel):

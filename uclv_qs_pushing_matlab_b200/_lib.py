@@ -84,6 +84,8 @@ SIGNATURES = {
     "qspush_solve": (C.c_int, [vp]),
     "qspush_shift": (C.c_int, [vp]),
     "qspush_plant_step": (C.c_int, [vp, vp, vp, C.c_int]),
+    "qspush_set_reference_trajectory": (C.c_int, [vp, vp, C.c_int, vp, C.c_int]),
+    "qspush_set_reference_window": (C.c_int, [vp, C.c_int]),
     "qspush_closed_loop": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, C.POINTER(LoopOpts), vp, vp, vp, C.c_int]),
     "qspush_sync": (C.c_int, [vp]),
     "qspush_stream": (vp, [vp]),

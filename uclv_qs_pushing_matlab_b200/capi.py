@@ -291,6 +291,26 @@ class Solver:
         L.check(L.lib().qspush_closed_loop(self._h, pt, int(T), po, px, int(steps), C.byref(lo), plx, plu, pls, mem))
         return dict(x=x, x_log=lx, u_log=lu, status_log=ls)
 
+    def set_reference_trajectory(self, traj, offset=None):
+        """NMPC_controller.set_reference_trajectory (NMPC_controller.m:425-431) for the batch: traj (T,6) columns
+        [x_ref; u_ref], offset (batch,6) optional per-problem shift; kept on the device (qspush_set_reference_trajectory)."""
+        pt, mem, kt = _buf(traj)
+        po = None
+        if offset is not None:
+            po, mem_o, ko = _buf(offset)
+            if mem_o != mem:
+                raise L.QspushError("traj and offset must live in the same memory space")
+            if tuple(ko.shape) != (self.batch, 6):
+                raise L.QspushError("offset must be (batch, 6)")
+        if len(kt.shape) != 2 or kt.shape[1] != 6:
+            raise L.QspushError("traj must be (T, 6)")
+        L.check(L.lib().qspush_set_reference_trajectory(self._h, pt, int(kt.shape[0]), po, mem))
+
+    def set_reference_window(self, idx):
+        """Reference window of control period idx (1-based) into cost_y_ref / cost_y_ref_e of every stage
+        (NMPC_controller.m:307-313, 343-348), on the device (qspush_set_reference_window)."""
+        L.check(L.lib().qspush_set_reference_window(self._h, int(idx)))
+
     def sync(self):
         L.check(L.lib().qspush_sync(self._h))
 

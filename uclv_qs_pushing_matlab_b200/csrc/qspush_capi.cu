@@ -45,6 +45,9 @@ struct qspush_solver {
     double* d_stage = nullptr;
     int* d_istage = nullptr;
     int* d_order = nullptr;       // work-queue order of the warp QP kernel (k_qp_order)
+    double* d_ref_traj = nullptr; // reference trajectory kept on the device (qspush_set_reference_trajectory): [T][6], [B][6]
+    double* d_ref_off = nullptr;
+    int ref_T = 0;
     size_t stage_doubles = 0;
     int* h_ndone = nullptr;        // pinned
     std::vector<double> W, We;     // host copies: N x 36 (y order, column-major), 16
@@ -366,6 +369,8 @@ void qspush_solver_free(qspush_solver* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     if (s->arena) cudaFree(s->arena);
+    if (s->d_ref_traj) cudaFree(s->d_ref_traj);
+    if (s->d_ref_off) cudaFree(s->d_ref_off);
     if (s->h_ndone) cudaFreeHost(s->h_ndone);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -775,6 +780,40 @@ int qspush_closed_loop(qspush_solver* s, const double* traj, int T, const double
         if (log_status) CK(cudaMemcpyAsync(log_status, d_ls, (size_t)steps * B * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
     }
+    return QSPUSH_OK;
+}
+
+int qspush_set_reference_trajectory(qspush_solver* s, const double* traj, int T, const double* offset, qspush_mem mem) {
+    if (!s || !traj) return fail(QSPUSH_ERR_ARG, "NULL argument");
+    if (T < 1) return fail(QSPUSH_ERR_ARG, "reference trajectory: need T >= 1");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));                       // a window kernel may still read the old columns
+    if (s->d_ref_traj) { cudaFree(s->d_ref_traj); s->d_ref_traj = nullptr; }
+    if (s->d_ref_off) { cudaFree(s->d_ref_off); s->d_ref_off = nullptr; }
+    s->ref_T = 0;
+    const cudaMemcpyKind kind = mem == QSPUSH_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CK(cudaMalloc(&s->d_ref_traj, (size_t)T * 6 * sizeof(double)));
+    CK(cudaMemcpyAsync(s->d_ref_traj, traj, (size_t)T * 6 * sizeof(double), kind, s->stream));
+    if (offset) {
+        CK(cudaMalloc(&s->d_ref_off, (size_t)s->B * 6 * sizeof(double)));
+        CK(cudaMemcpyAsync(s->d_ref_off, offset, (size_t)s->B * 6 * sizeof(double), kind, s->stream));
+    }
+    CK(cudaStreamSynchronize(s->stream));                       // the caller may reuse its buffers
+    s->ref_T = T;
+    return QSPUSH_OK;
+}
+
+int qspush_set_reference_window(qspush_solver* s, int idx) {
+    if (!s) return fail(QSPUSH_ERR_ARG, "NULL solver");
+    if (!s->d_ref_traj || s->ref_T < 1) return fail(QSPUSH_ERR_ARG, "no reference trajectory set (qspush_set_reference_trajectory)");
+    if (idx < 1) return fail(QSPUSH_ERR_ARG, "reference window: idx is 1-based");
+    CK(cudaSetDevice(s->device));
+    LoopDev L{};
+    L.traj = s->d_ref_traj; L.off = s->d_ref_off; L.T = s->ref_T;
+    const unsigned wb = (unsigned)(((size_t)s->N * s->Bp + 255) / 256);
+    k_loop_window<<<wb, 256, 0, s->stream>>>(s->dev, L, idx);
+    CK(cudaGetLastError());
+    s->launches++;
     return QSPUSH_OK;
 }
 
