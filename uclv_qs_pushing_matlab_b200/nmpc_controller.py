@@ -168,6 +168,7 @@ class NMPC_controller:
     def create_ocp_solver(self):
         self.ocp_solver = acados_ocp(self.create_ocp_model(), self.create_ocp_opts(), batch=self.batch, device=self.device)
         s = self.ocp_solver.solver
+        self._ref_key = None                                                   # the new solver holds no reference trajectory yet
         s.set_ctrl(v_alpha=self.v_alpha, d_v_bound=self.d_v_bound, t_angle0=self.t_angle0, u_t_ub=self.u_t_ub, u_n_lb=self.u_n_lb)
 
     # :307-313  (1-based index like the reference)
@@ -200,15 +201,19 @@ class NMPC_controller:
         x0 = np.asarray(x0, dtype=np.float64)
         self.ocp_solver.set("constr_x0", x0)                                   # :334 (the wrap of :332 happens in k_prepare)
         # reference window (:343-348)
-        cols = [min(index_time + k, self.y_ref.shape[-1]) - 1 for k in range(N)]
-        win = self.y_ref[..., cols]                                            # (6,N) or (B,6,N)
-        if win.ndim == 2:
-            yref = np.broadcast_to(win.T[None], (B, N, 6))
+        if self.y_ref.ndim == 2:
+            # one trajectory shared by the batch: it lives on the device like obj.y_ref lives in the controller, and the window
+            # of this period is cut there (qspush_set_reference_trajectory / _window); re-sent only when the array changed
+            key = hash(self.y_ref.tobytes())
+            if getattr(self, "_ref_key", None) != key:
+                s.set_reference_trajectory(np.ascontiguousarray(self.y_ref.T))
+                self._ref_key = key
+            s.set_reference_window(int(index_time))
         else:
-            yref = np.transpose(win, (0, 2, 1))
-        yref = np.ascontiguousarray(yref)
-        s.set("yref", yref)
-        s.set("yref_e", np.ascontiguousarray(yref[:, N - 1, :4]))
+            cols = [min(index_time + k, self.y_ref.shape[-1]) - 1 for k in range(N)]
+            yref = np.ascontiguousarray(np.transpose(self.y_ref[..., cols], (0, 2, 1)))   # (B,6,N) -> (B,N,6)
+            s.set("yref", yref)
+            s.set("yref_e", np.ascontiguousarray(yref[:, N - 1, :4]))
         if self._cold:                                                         # :351-355
             s.set_int("cold", np.ones(B, dtype=np.int32))
             self._cold = False
