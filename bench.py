@@ -422,7 +422,7 @@ def run_ours(args):
                               "peak_source": "cuBLAS DGEMM 4096^3 measured in this run", "flops_per_iteration": alg_flops_per_iter(k_ipm),
                               "ncu_pipe_fp64_active_pct": pipe_pct,
                               "what": "achieved = algorithmic flops of the serial Riccati IPM (SURVEY 8d); ncu_pipe_fp64_active_pct = "
-                                      "sm__pipe_fp64_cycles_active of the executed parallel-in-time algorithm (profiles/r01_v7_qp_ncu_summary.md)"},
+                                      "sm__pipe_fp64_cycles_active of the executed parallel-in-time algorithm (profiles/r01_v9_qp_ncu_summary.md)"},
                      "note": "the path is FP64-pipe / dependent-chain bound, not HBM bound (SURVEY 8d): the HBM fraction is reported "
                              "because the schema asks for it, the fp64 object is the relevant roofline (see DESIGN.md)"},
         "cpu_baseline": cpu_base,
