@@ -49,10 +49,10 @@ typedef struct {
     int    max_sqp_iter;            /* nlp_solver_max_iter = 30                               */
     double tol_stat, tol_eq, tol_ineq, tol_comp;   /* nlp_solver_tol_* = 1e-6                 */
     int    qp_max_iter;             /* qp_solver_iter_max = 50                                */
-    double qp_tol;                  /* IPM residual / complementarity tolerance               */
+    double qp_tol;                  /* IPM tolerance on stationarity / dynamics / inequality residuals (1e-11) */
     double qp_mu0;                  /* IPM initial barrier parameter                          */
     double qp_thr;                  /* IPM lower clamp on the initial slacks                  */
-    double qp_tau;                  /* IPM fraction to the boundary                           */
+    double qp_tau;                  /* IPM fixed fraction to the boundary (only used when qp_gamma_f = 0) */
     int    globalization;           /* 1 = merit backtracking, 0 = fixed full step            */
     double alpha_min, alpha_reduction, eps_sufficient_descent;   /* 0.05, 0.7, 1e-4           */
     int    matlab_single_quirk;     /* reproduce MATLAB `single` rounding of mod(s,b) in prepare */
@@ -63,6 +63,13 @@ typedef struct {
                                        v_bound from qspush_ctrl; selecting it resets constr_lh / constr_uh to
                                        [u_n_lb, -2 u_t_ub, 0] / [u_n_ub(0.03), 0, 2 u_t_ub] (:247-248).  Needs the warp QP kernel
                                        (N <= 127): qspush_solve fails with QSPUSH_ERR_ARG otherwise                          */
+    /* IPM end game (appended in r02; the fields above keep their offsets).  Complementarity is driven far below the other
+     * residuals: multipliers of this QP are as small as 1e-9 (input weight 5e-5), so lam*t <= 1e-12 would leave du 1e-5 away
+     * from the QP solution; at 1e-18 the returned point is within 1e-9 of it whatever path the IPM took. */
+    double qp_tol_comp;             /* tolerance on max lam * t (1e-18)                                        */
+    double qp_t_min;                /* slack floor (1e-12): pairs with t <= 4 t_min count as converged, centering target lam * t_min */
+    double qp_gamma_f;              /* step to the boundary: blocking pair keeps gamma_f * predicted mu reduction (0.05; 0 = fixed qp_tau) */
+    int    qp_stall;                /* iterations without halving the normalised residual before a point below 1e-6 is accepted (10) */
 } qspush_opts;
 
 /* controller-side constants of NMPC_controller (NMPC_controller.m:23-26, 98-100) */

@@ -66,6 +66,7 @@ def lib():
         L.orc_constraints_batch.argtypes = [C.c_void_p, C.c_int] + [_dp] * 4
         L.orc_linearise_batch.argtypes = [C.c_void_p, C.c_int] + [_dp] * 10
         L.orc_qp_batch.argtypes = [C.c_void_p, C.c_int] + [_dp] * 5 + [C.c_int] + [_dp] * 5 + [_ip, _ip, _dp]
+        L.orc_qp_data_batch.argtypes = [C.c_void_p, C.c_int] + [_dp] * 5 + [_dp] * 11 + [_ip, _ip]
         L.orc_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_int] + [_dp] * 7 + [C.c_int, _ip, _dp]
         L.orc_prepare_batch.argtypes = [C.c_void_p, C.c_int, _dp, _ip] + [_dp] * 4 + [C.c_int]
         L.orc_shift_batch.argtypes = [C.c_void_p, C.c_int] + [_dp] * 4
@@ -173,8 +174,9 @@ class Model:
 
 DEFAULT_OPTS = dict(
     max_sqp_iter=30, tol_stat=1e-6, tol_eq=1e-6, tol_ineq=1e-6, tol_comp=1e-6,
-    qp_max_iter=50, qp_tol=1e-12, qp_mu0=0.1, qp_thr=1e-3, qp_tau=0.9995,
+    qp_max_iter=50, qp_tol=1e-11, qp_mu0=0.1, qp_thr=1e-3, qp_tau=0.9995,
     alpha_min=0.05, alpha_reduction=0.7, eps_sufficient_descent=1e-4, globalization=1, local_spline=1,
+    qp_tol_comp=1e-18, qp_t_min=1e-12, qp_gamma_f=0.05, qp_stall=10,
 )
 _OPT_ORDER = list(DEFAULT_OPTS.keys())
 
@@ -250,6 +252,19 @@ class Ocp:
         lib().orc_qp_batch(self.h, nb, _d(x0bar), _d(yref), _d(yref_e), _d(x), _d(u), int(nthreads),
                            _d(du), _d(dx), _d(pi), _d(lam), _d(t), _i(iters), _i(status), _d(res))
         return dict(du=du, dx=dx, pi=pi, lam=lam, t=t, iters=iters, status=status, res=res)
+
+    def qp_data(self, x0bar, yref, yref_e, x, u):
+        """The QP of the linearisation at (x, u) as dense per-stage data (input of the extended-precision arbiter)."""
+        x0bar, yref, yref_e, x, u = map(_c, (x0bar, yref, yref_e, x, u))
+        nb, N = x.shape[0], self.N
+        d = dict(H=np.zeros((nb, N, 6, 6)), g=np.zeros((nb, N, 6)), A=np.zeros((nb, N, 4, 4)), B=np.zeros((nb, N, 4, 2)),
+                 b=np.zeros((nb, N, 4)), QN=np.zeros((4, 4)), qN=np.zeros((nb, 4)), dx0=np.zeros((nb, 4)),
+                 dl=np.zeros((nb, N, 3)), du=np.zeros((nb, N, 3)), beta=np.zeros((nb, N, 3)),
+                 on=np.zeros((nb, N, 3), dtype=np.int32), ci=np.zeros((nb, N, 3), dtype=np.int32))
+        lib().orc_qp_data_batch(self.h, nb, _d(x0bar), _d(yref), _d(yref_e), _d(x), _d(u),
+                                *[_d(d[k]) for k in ("H", "g", "A", "B", "b", "QN", "qN", "dx0", "dl", "du", "beta")],
+                                _i(d["on"]), _i(d["ci"]))
+        return d
 
     def solve(self, mode, x0bar, yref, yref_e, x, u, pi=None, lam=None, nthreads=1):
         """mode 'rti' or 'sqp'.  Returns updated copies and stats."""

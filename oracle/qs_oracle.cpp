@@ -235,19 +235,29 @@ static double v_bound_sym(const Model& m, const Ocp& ocp, double s, bool local, 
 
 // MATLAB mod(s, b) for b > 0: result in [0, b).  With the single quirk the result is single
 // (mod(double, single) -> single), bspline_shape.m:147,155,193; NMPC_controller.m:320,332.
-static double matlab_mod(const Model& m, double s) {
-    if (m.single_quirk) {
-        float sf = (float)s, bf = (float)m.b;
-        float r = sf - std::floor(sf / bf) * bf;
-        // MATLAB guards the rounding of the quotient; keep the result inside [0, b)
-        if (r < 0.f) r += bf;
-        if (r >= bf) r -= bf;
-        return (double)r;
+// The builtin's algorithm [MATLAB-RECALL: the form MATLAB Coder emits for mod on floating-point operands]:
+//   r = fmod(x, y); r is forced to 0 when x / y is an integer within eps * |x / y|; otherwise r += y when the signs differ.
+// The result is NOT always below y: for a tiny negative x the sum r + y rounds to y itself (in single precision already
+// for |x| < 1.5e-8 with b = 0.28) — x0(4) = mod(x0(4), b) - b (x0(4) < 0) then gives 0, not -b.
+template <class F>
+static F matlab_mod_t(F x, F y, F eps) {
+    if (y == (F)0) return x;
+    if (!(x == x) || !(y == y) || std::isinf(x)) return std::numeric_limits<F>::quiet_NaN();
+    if (x == (F)0) return (F)0 / y;
+    if (std::isinf(y)) return ((y < (F)0) != (x < (F)0)) ? y : x;
+    F r = std::fmod(x, y);
+    bool req0 = (r == (F)0);
+    if (!req0 && y > std::floor(y)) {
+        const F q = std::fabs(x / y);
+        req0 = !(std::fabs(q - std::floor(q + (F)0.5)) > eps * q);
     }
-    double r = s - std::floor(s / m.b) * m.b;
-    if (r < 0.0) r += m.b;
-    if (r >= m.b) r -= m.b;
+    if (req0) r = y * (F)0;
+    else if ((x < (F)0) != (y < (F)0)) r += y;
     return r;
+}
+static double matlab_mod(const Model& m, double s) {
+    if (m.single_quirk) return (double)matlab_mod_t<float>((float)s, (float)m.b, 1.1920929e-7f);
+    return matlab_mod_t<double>(s, m.b, 2.220446049250313e-16);
 }
 
 // =========================================================================================
@@ -536,13 +546,10 @@ static void qp_solve_ipm(const QP& qp, const OcpOpts& o, QPSol& sol) {
             lam[(size_t)k * 6 + c] = o.qp_mu0 / tl; lam[(size_t)k * 6 + 3 + c] = o.qp_mu0 / tu;
         }
     std::vector<double> rg(nz + 4), rb((size_t)N * 4), rd(nc), rm(nc), Hb(nz), Hx((size_t)N), rgt(nz + 4);
-    std::vector<double> dz, dxN, dpi, dlam(nc), dt_(nc), dz2, dxN2, dpi2;
+    std::vector<double> dz, dxN, dpi, dlam(nc), dt_(nc), dz2, dxN2, dpi2, wgt(nc, 0.0);
     RiccatiFactor F;
-    sol.status = 1;
-    int it = 0, stall = 0;
-    double rmax_prev = 1e300;
-    for (;; ++it) {
-        // ---- residuals
+    // true residuals of the current point: rg (stationarity), rb (dynamics), rd (inequality rows minus slacks)
+    auto residuals = [&]() {
         for (int k = 0; k < N; ++k) {
             const StageQP& s = qp.st[k];
             const double* zk = &z[(size_t)k * 6];
@@ -581,18 +588,26 @@ static void qp_solve_ipm(const QP& qp, const OcpOpts& o, QPSol& sol) {
         }
         // x_0 is not a variable: its stationarity row is not a residual
         for (int j = 0; j < 4; ++j) rg[2 + j] = 0.0;
+    };
+    sol.status = 1;
+    const double tol_cp = o.qp_tol_comp, t_min = o.qp_t_min;
+    int it = 0, stall = 0;
+    double rmax_prev = 1e300;
+    for (;; ++it) {
+        residuals();
         double mu = 0.0, r_stat = 0.0, r_eq = 0.0, r_in = 0.0, r_cp = 0.0;
-        for (size_t i = 0; i < nc; ++i) if (on[i]) { mu += lam[i] * t[i]; r_cp = std::max(r_cp, lam[i] * t[i]); r_in = std::max(r_in, std::fabs(rd[i])); }
+        for (size_t i = 0; i < nc; ++i) if (on[i]) { wgt[i] = (t[i] > 4.0 * t_min) ? 1.0 : 0.0; mu += wgt[i] * lam[i] * t[i]; r_cp = std::max(r_cp, wgt[i] * lam[i] * t[i]); r_in = std::max(r_in, std::fabs(rd[i])); }
         mu = m_on ? mu / m_on : 0.0;
         for (size_t i = 0; i < nz + 4; ++i) r_stat = std::max(r_stat, std::fabs(rg[i]));
         for (size_t i = 0; i < rb.size(); ++i) r_eq = std::max(r_eq, std::fabs(rb[i]));
         sol.res[0] = r_stat; sol.res[1] = r_eq; sol.res[2] = r_in; sol.res[3] = r_cp;
         if (!(r_stat == r_stat) || !(r_eq == r_eq) || !(mu == mu)) { sol.status = 2; break; }
-        if (r_stat < o.qp_tol && r_eq < o.qp_tol && r_in < o.qp_tol && r_cp < o.qp_tol) { sol.status = 0; break; }
+        if (r_stat < o.qp_tol && r_eq < o.qp_tol && r_in < o.qp_tol && r_cp < tol_cp) { sol.status = 0; break; }
         {   // stall exit (weakly active pairs): residuals stopped moving below the reference's QP tolerance 1e-6
             const double rmax = std::max(std::max(r_stat, r_eq), std::max(r_in, r_cp));
-            if (rmax < 0.5 * rmax_prev) { rmax_prev = rmax; stall = 0; } else ++stall;   // rmax_prev = best so far
-            if (stall >= 5 && rmax < 1e-6) { sol.status = 0; break; }
+            const double rrel = std::max(std::max(r_stat, std::max(r_eq, r_in)) / o.qp_tol, r_cp / tol_cp);   // > 1: not converged
+            if (rrel < 0.5 * rmax_prev) { rmax_prev = rrel; stall = 0; } else ++stall;   // rmax_prev = best so far
+            if (stall >= o.qp_stall && rmax < 1e-6) { sol.status = 0; break; }
         }
         if (it >= o.qp_max_iter) { sol.status = 1; break; }
         // ---- factorise with barrier diagonal
@@ -637,14 +652,22 @@ static void qp_solve_ipm(const QP& qp, const OcpOpts& o, QPSol& sol) {
         solve_with(rm, dz, dxN, dpi);
         double a_aff = max_step();
         double mu_aff = 0.0;
-        for (size_t i = 0; i < nc; ++i) if (on[i]) mu_aff += (lam[i] + a_aff * dlam[i]) * (t[i] + a_aff * dt_[i]);
+        for (size_t i = 0; i < nc; ++i) if (on[i]) mu_aff += wgt[i] * (lam[i] + a_aff * dlam[i]) * (t[i] + a_aff * dt_[i]);
         mu_aff = m_on ? mu_aff / m_on : 0.0;
         double sigma = (mu > 0.0) ? (mu_aff / mu) : 0.0; sigma = sigma * sigma * sigma;
         // ---- corrector
-        const double smu = std::max(sigma * mu, 0.1 * o.qp_tol);   // centering target floor (keeps lam/t bounded at the end)
-        for (size_t i = 0; i < nc; ++i) rm[i] = on[i] ? (lam[i] * t[i] + dlam[i] * dt_[i] - smu) : 0.0;
+        const double smu = std::max(sigma * mu, 0.1 * tol_cp);   // centering target floor (keeps lam/t bounded at the end)
+        for (size_t i = 0; i < nc; ++i) rm[i] = on[i] ? (lam[i] * t[i] + dlam[i] * dt_[i] - std::max(smu, lam[i] * t_min)) : 0.0;
         solve_with(rm, dz, dxN, dpi);
-        double alpha = std::min(1.0, o.qp_tau * max_step());
+        // Step to the boundary (Mehrotra's heuristic in scalar form): the blocking pair keeps the fraction
+        // gamma_f * (predicted reduction of mu) of its value, clamped to [1e-8, 0.5], instead of a fixed 1 - tau.  A blocked step
+        // (a_max < 1) then leaves its blocking pair near the new central path instead of 1e-3 below it — the fixed rule made
+        // inputs whose only curvature is the 5e-5 weight jump from bound to bound every iteration —, while an unblocked end-game
+        // step may shrink a product by sigma (superlinear convergence; with 1 - tau = 5e-4 every iteration gains 3 digits at most).
+        const double a_max_ = max_step();
+        const double red = 1.0 - std::min(a_max_, 1.0) * (1.0 - smu / std::max(mu, 1e-300));
+        const double tau_k = (o.qp_gamma_f > 0.0) ? 1.0 - std::min(std::max(o.qp_gamma_f * red, 1e-8), 0.5) : o.qp_tau;   // gamma_f = 0: fixed fraction qp_tau
+        double alpha = std::min(1.0, tau_k * a_max_);
         if (m_on == 0) alpha = 1.0;
         // ---- update
         for (int k = 0; k < N; ++k) {
@@ -913,7 +936,7 @@ static double v_bound(const Model& m, const CtrlParams& cp, double s, bool local
     sm = matlab_mod(m, sm);                                // getAngleCurvatures applies mod again, bspline_shape.m:147
     double t_angle = std::fabs(angle_dot(m, sm, local));   // :321
     if (t_angle_out) *t_angle_out = t_angle;
-    return std::min(cp.v_alpha / (std::fabs(t_angle - cp.t_angle0) + 0.0001) + cp.d_v_bound, cp.u_t_ub);  // :322
+    return std::fmin(cp.v_alpha / (std::fabs(t_angle - cp.t_angle0) + 0.0001) + cp.d_v_bound, cp.u_t_ub);  // :322 (MATLAB min ignores NaN, like fmin)
 }
 
 static double sgn(double v) { return (v > 0.0) - (v < 0.0); }
@@ -1122,13 +1145,15 @@ void orc_ocp_set_bounds(void* o_, const double* lh, const double* uh) {
     for (int i = 0; i < 3; ++i) { o->ocp.lh[i] = lh[i]; o->ocp.uh[i] = uh[i]; }
 }
 // opts: [max_sqp_iter, tol_stat, tol_eq, tol_ineq, tol_comp, qp_max_iter, qp_tol, qp_mu0, qp_thr, qp_tau,
-//        alpha_min, alpha_reduction, eps_sufficient_descent, globalization, local_spline]
+//        alpha_min, alpha_reduction, eps_sufficient_descent, globalization, local_spline,
+//        qp_tol_comp, qp_t_min, qp_gamma_f, qp_stall]
 void orc_ocp_set_opts(void* o_, const double* v) {
     OrcOcp* o = (OrcOcp*)o_; OcpOpts& p = o->ocp.opts;
     p.max_sqp_iter = (int)v[0]; p.tol_stat = v[1]; p.tol_eq = v[2]; p.tol_ineq = v[3]; p.tol_comp = v[4];
     p.qp_max_iter = (int)v[5]; p.qp_tol = v[6]; p.qp_mu0 = v[7]; p.qp_thr = v[8]; p.qp_tau = v[9];
     p.alpha_min = v[10]; p.alpha_reduction = v[11]; p.eps_sufficient_descent = v[12]; p.globalization = (int)v[13];
     o->local = v[14] != 0.0;
+    p.qp_tol_comp = v[15]; p.qp_t_min = v[16]; p.qp_gamma_f = v[17]; p.qp_stall = (int)v[18];
 }
 // h_variant 1: h = [u_n; u_t - v_bound(s); u_t + v_bound(s)]; the caller sets the matching lh / uh
 // ([u_n_lb, 2 u_t_lb, 0] / [u_n_ub, 0, 2 u_t_ub], NMPC_controller.m:247-248) with orc_ocp_set_bounds.
@@ -1211,6 +1236,31 @@ void orc_qp_batch(void* o_, int nb, const double* x0bar, const double* yref, con
         iters[b] = qs.iters; status[b] = qs.status;
         if (res) for (int i = 0; i < 4; ++i) res[4 * b + i] = qs.res[i];
     });
+}
+
+// The QP itself (for the extended-precision arbiter, oracle/qs_arbiter.cpp): H [nb][N][36] row-major in z = [u;x] order,
+// g [nb][N][6], A [nb][N][16], B [nb][N][8], b [nb][N][4], QN [16], qN [nb][4], dx0 [nb][4], dl / du / beta [nb][N][3],
+// on / ci [nb][N][3].
+void orc_qp_data_batch(void* o_, int nb, const double* x0bar, const double* yref, const double* yref_e,
+                       const double* x, const double* u, double* H, double* g, double* A, double* B, double* bres,
+                       double* QN, double* qN, double* dx0, double* dl, double* du, double* beta, int* on, int* ci) {
+    OrcOcp* o = (OrcOcp*)o_; const int N = o->ocp.N;
+    for (int b = 0; b < nb; ++b) {
+        Traj tr; load_traj(o, b, x, u, nullptr, nullptr, tr);
+        RefData rd{x0bar + 4 * b, yref + (size_t)b * N * 6, yref_e + 4 * b};
+        QP qp; linearise(o->ocp, rd, tr, o->local, qp);
+        for (int k = 0; k < N; ++k) {
+            const size_t s = (size_t)b * N + k; const StageQP& st = qp.st[k];
+            for (int i = 0; i < 6; ++i) { for (int j = 0; j < 6; ++j) H[s * 36 + 6 * i + j] = st.H[i][j]; g[s * 6 + i] = st.g[i]; }
+            for (int i = 0; i < 4; ++i) {
+                for (int j = 0; j < 4; ++j) A[s * 16 + 4 * i + j] = st.A[i][j];
+                for (int j = 0; j < 2; ++j) B[s * 8 + 2 * i + j] = st.B[i][j];
+                bres[s * 4 + i] = st.b[i];
+            }
+            for (int c = 0; c < 3; ++c) { dl[s * 3 + c] = st.dl[c]; du[s * 3 + c] = st.du[c]; beta[s * 3 + c] = st.beta[c]; on[s * 3 + c] = st.on[c]; ci[s * 3 + c] = st.ci[c]; }
+        }
+        for (int i = 0; i < 4; ++i) { for (int j = 0; j < 4; ++j) QN[4 * i + j] = qp.QN[i][j]; qN[4 * b + i] = qp.qN[i]; dx0[4 * b + i] = qp.dx0[i]; }
+    }
 }
 
 // mode 0 = RTI (one iteration, full step), 1 = full SQP.  x,u,pi,lam are in/out.

@@ -129,12 +129,20 @@ struct OcpOpts {
     int    max_sqp_iter = 30;          // NMPC_controller.m:276
     double tol_stat = 1e-6, tol_eq = 1e-6, tol_ineq = 1e-6, tol_comp = 1e-6;  // :276
     int    qp_max_iter = 50;           // acados default qp_solver_iter_max
-    double qp_tol = 1e-12;              // QP residual tolerance (all four)
+    double qp_tol = 1e-11;             // QP residual tolerance on stationarity, dynamics and inequality residuals
     double qp_mu0 = 0.1;               // initial barrier parameter
     double qp_thr = 1e-3;              // lower clamp on initial slacks
-    double qp_tau = 0.9995;            // fraction to the boundary
+    double qp_tau = 0.9995;            // fixed fraction to the boundary (used when qp_gamma_f = 0)
     double alpha_min = 0.05, alpha_reduction = 0.7, eps_sufficient_descent = 1e-4;  // acados defaults
     int    globalization = 1;          // 1 = merit backtracking (NMPC_controller.m:272), 0 = full step
+    // Complementarity is driven much further than the other residuals: the multipliers of this QP are as small as 1e-9
+    // (the input weight is 5e-5), so lam * t <= 1e-12 leaves the slack of such a row — and with it du — 1e-5 away from
+    // the QP solution; at 1e-18 every row is within 1e-9 and the returned point no longer depends on the path of the IPM
+    // (tests/test_qp_exact.py compares it with the extended-precision arbiter, oracle/qs_arbiter.cpp).
+    double qp_tol_comp = 1e-18;        // tolerance on max lam * t
+    double qp_t_min = 1e-12;           // slack floor: pairs with t <= 4 t_min count as converged, their centering target is lam * t_min (bounds lam / t)
+    double qp_gamma_f = 0.05;          // step to the boundary: blocking pair keeps gamma_f * (predicted mu reduction) of its value
+    int    qp_stall = 10;              // iterations without halving the normalised residual before a point below 1e-6 is accepted
 };
 
 struct Ocp {

@@ -15,6 +15,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
+from oracle import arbiter as arb  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 from tests.workloads import OBJECT_ORDER, make_rti_workload, make_samples_config2, oracle_model  # noqa: E402
 
@@ -38,9 +39,15 @@ def main():
     pr = ocp.prepare(wl["x0"], np.zeros(B, dtype=np.int32), np.zeros((B, N + 1, 4)), wl["u_init"])
     qp = ocp.qp(pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"])
     rti = ocp.solve("rti", pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"])
+    # the EXACT solution of the same QPs (oracle/qs_arbiter.cpp, __float128 active-set method + KKT certificate)
+    d = ocp.qp_data(pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"])
+    ex = arb.solve_exact(d, arb.working_set_from_ipm(qp["lam"], qp["t"], d["on"]))
+    assert (ex["status"] == 0).all() and ex["kkt"].max() < 1e-18
     np.savez_compressed(os.path.join(HERE, "rti_santal_N40.npz"), x0=wl["x0"], yref=wl["yref"], yref_e=wl["yref_e"], u_init=wl["u_init"],
                         x0_wrapped=pr["x0"], x_prep=pr["x"], u_prep=pr["u"], du=qp["du"], dx=qp["dx"], qp_pi=qp["pi"], qp_lam=qp["lam"],
-                        qp_iters=qp["iters"], x=rti["x"], u=rti["u"], pi=rti["pi"], lam=rti["lam"], cost=rti["cost"])
+                        qp_iters=qp["iters"], x=rti["x"], u=rti["u"], pi=rti["pi"], lam=rti["lam"], cost=rti["cost"],
+                        du_exact=ex["du"], dx_exact=ex["dx"], pi_exact=ex["pi"], lam_exact=ex["lam"], kkt_exact=ex["kkt"])
+    print("rti fixture: oracle vs exact du %.2e dx %.2e" % (np.abs(qp["du"] - ex["du"]).max(), np.abs(qp["dx"] - ex["dx"]).max()))
     # full SQP to convergence on a short horizon (config 1 shape: N = 10)
     B, N = 16, 10
     wl = make_rti_workload(None, batch=B, N=N, seed=4, mixed_modes=True)

@@ -273,7 +273,7 @@ void hs_eval_vbound(void* m_, int cnt, const double* s, const double* ctrl5, int
 }
 
 // Whole solver pipeline in kernel order on host slabs.
-//   opts_d: [qp_tol, qp_mu0, qp_thr, qp_tau, tol_stat, tol_eq, tol_ineq, tol_comp, alpha_min, alpha_red, eps_sd]
+//   opts_d: [qp_tol, qp_mu0, qp_thr, qp_tau, tol_stat, tol_eq, tol_ineq, tol_comp, alpha_min, alpha_red, eps_sd, qp_tol_comp, qp_t_min, qp_gamma_f, qp_stall]
 //   opts_i: [mode(0 rti,1 sqp,2 qp-only), qp_max_iter, max_sqp_iter, globalization, single_quirk, do_prepare, do_shift, qp_kernel(0 thread,1 warp), h_variant]
 //   ctrl5 : [v_alpha, d_v_bound, t_angle0, u_t_ub, u_n_lb]
 // AoS in/out: x0 [nb][4] (in/out: wrapped by prepare), yref [nb][N][6], yref_e [nb][4], x [nb][N+1][4], u [nb][N][2],
@@ -327,7 +327,7 @@ struct HostRun {
         S.h_variant = opts_i[8];                                     // like apply_variant() in qspush_capi.cu
         for (int i = 0; i < 4; ++i) S.vbp[i] = ctrl5[i];
         mode = opts_i[0];
-        io = IpmOpts{opts_i[1], opts_d[0], opts_d[1], opts_d[2], opts_d[3]};
+        io = IpmOpts{opts_i[1], opts_d[0], opts_d[1], opts_d[2], opts_d[3], opts_d[11], opts_d[12], opts_d[13], (int)opts_d[14]};
         so = SqpOpts{opts_i[2], {opts_d[4], opts_d[5], opts_d[6], opts_d[7]}, opts_i[3], opts_d[8], opts_d[9], opts_d[10]};
         cp = CtrlDev{ctrl5[0], ctrl5[1], ctrl5[2], ctrl5[3], ctrl5[4], opts_i[4]};
         single = opts_i[4];

@@ -29,6 +29,19 @@ def _oracle_prepared(om, wl, N, **opts):
     return ocp, ocp.prepare(wl["x0"], np.zeros(B, dtype=np.int32), np.zeros((B, N + 1, 4)), wl["u_init"])
 
 
+def _exact_step(ocp, pr, wl, idx=None):
+    """Exact solution of the QP the oracle linearises at the prepared point (extended-precision arbiter, oracle/qs_arbiter.cpp):
+    returns the exact RTI iterate u + du, x + dx of the selected problems."""
+    from oracle import arbiter as arb
+    sl = slice(None) if idx is None else idx
+    args = (pr["x0"][sl], wl["yref"][sl], wl["yref_e"][sl], pr["x"][sl], pr["u"][sl])
+    qo = ocp.qp(*args, nthreads=8)
+    d = ocp.qp_data(*args)
+    ex = arb.solve_exact(d, arb.working_set_from_ipm(qo["lam"], qo["t"], d["on"]), nthreads=16)
+    assert (ex["status"] == 0).all() and ex["kkt"].max() < 1e-18
+    return pr["u"][sl] + ex["du"], pr["x"][sl] + ex["dx"]
+
+
 def test_set_get_roundtrip_and_errors():
     gm = gpu_model("santal")
     B, N = 37, 7                                                  # ragged: batch not a multiple of 32
@@ -120,17 +133,21 @@ def test_prepare_qp_rti_vs_oracle(name, N, qp_kernel):
     u, x, pi, lam = s.get("u"), s.get("x"), s.get("pi"), s.get("lam")
     it = s.get_int("qp_iter")
     assert (s.get_int("status") == 0).all() and (s.get_int("sqp_iter") == 1).all()
-    assert np.abs(it - ro["qp_iter"]).max() <= 4 and (it == ro["qp_iter"]).mean() > 0.8   # FMA contraction moves threshold crossings
-    same = it == ro["qp_iter"]
+    assert np.abs(it - ro["qp_iter"]).max() <= 2 and (it == ro["qp_iter"]).mean() > 0.9   # FMA contraction may move a threshold crossing
+    # north_star: per-iteration QP solution and u0 within 1e-6 — asserted on EVERY problem, two decades tighter, (i) against the
+    # oracle and (ii) against the exact QP solution; the oracle's own distance to the exact solution is reported beside it
     u0err = np.abs(u[:, 0] - ro["u"][:, 0]).max(1)
-    assert u0err[same].max() < 1e-6 and (u0err < 1e-6).mean() >= 0.95 and u0err.max() < (2e-5 if N <= 40 else 2e-4)     # north_star: u0 within 1e-6
-    assert np.abs(u[same] - ro["u"][same]).max() < 1e-6 and np.abs(x[same] - ro["x"][same]).max() < 1e-6
-    floor = 2e-5 if N <= 40 else 2e-4                            # FP64 conditioning floor of this QP grows with the horizon, DESIGN.md 2.1
-    assert np.abs(u - ro["u"]).max() < floor and np.abs(x - ro["x"]).max() < floor
-    assert rel_err(pi[same], ro["pi"][same]) < 1e-5 and np.abs(lam[same] - ro["lam"][same]).max() < 1e-5 * max(1.0, np.abs(ro["lam"]).max())
-    assert rel_err(s.get("cost"), ro["cost"]) < 1e-8
-    rmax = s.get("res").max(1)                                    # true KKT residuals of every returned QP point
-    assert (rmax < 1e-11).mean() >= 0.99 and rmax.max() < 1e-6    # stall exits (weakly active pair) stay below the reference's own 1e-6
+    assert u0err.max() < 1e-8, u0err.max()
+    assert np.abs(u - ro["u"]).max() < 1e-8 and np.abs(x - ro["x"]).max() < 1e-8
+    ne = B if N <= 60 else 64                                     # the __float128 arbiter costs O(N^3) per problem
+    u_ex, x_ex = _exact_step(ocp, pr, wl, slice(0, ne))
+    gpu_vs_exact = np.abs(u[:ne] - u_ex).max(axis=(1, 2)); orc_vs_exact = np.abs(ro["u"][:ne] - u_ex).max(axis=(1, 2))
+    assert gpu_vs_exact.max() < 1e-8 and orc_vs_exact.max() < 1e-8, (gpu_vs_exact.max(), orc_vs_exact.max())
+    assert np.abs(x[:ne] - x_ex).max() < 1e-8
+    assert rel_err(pi, ro["pi"]) < 1e-7 and np.abs(lam - ro["lam"]).max() < 1e-6 * max(1.0, np.abs(ro["lam"]).max())
+    assert rel_err(s.get("cost"), ro["cost"]) < 1e-9
+    res = s.get("res")                                            # true KKT residuals of every returned QP point: no stall exits
+    assert res[:, :3].max() < 1e-11 and res[:, 3].max() < 1e-18
     assert s.stat("time_tot") > 0 and s.stat("time_qp_sol") > 0 and s.launches > 0
 
 
@@ -142,8 +159,11 @@ def test_rti_vs_golden_fixture():
     _load(s, {k: g[k] for k in ("x0", "yref", "yref_e", "u_init")}); s.prepare()
     assert np.array_equal(s.get("x0"), g["x0_wrapped"]) and rel_err(s.get("x"), g["x_prep"]) < REL
     s.solve()
-    assert np.abs(s.get("u") - g["u"]).max() < 1e-6 and np.abs(s.get("x") - g["x"]).max() < 1e-6
-    assert rel_err(s.get("cost"), g["cost"]) < 1e-8
+    assert np.abs(s.get("u") - g["u"]).max() < 1e-8 and np.abs(s.get("x") - g["x"]).max() < 1e-8
+    # committed EXACT solution of the same QPs (__float128 arbiter, frozen by tests/golden/make_golden.py)
+    assert g["kkt_exact"].max() < 1e-18
+    assert np.abs(s.get("u") - (g["u_prep"] + g["du_exact"])).max() < 1e-8 and np.abs(s.get("x") - (g["x_prep"] + g["dx_exact"])).max() < 1e-8
+    assert rel_err(s.get("cost"), g["cost"]) < 1e-9
 
 
 def test_multi_object_batch_shift_and_warm_start():
@@ -162,10 +182,10 @@ def test_multi_object_batch_shift_and_warm_start():
         ocp, pr = _oracle_prepared(oms[o], sub, N)
         ro = ocp.solve("rti", pr["x0"], sub["yref"], sub["yref_e"], pr["x"], pr["u"], nthreads=4)
         sh = ocp.shift(ro["x"], ro["u"], ro["pi"], ro["lam"])
-        assert np.abs(u[idx] - sh["u"]).max() < 1e-5 and np.abs(x[idx] - sh["x"]).max() < 1e-5 and (np.abs(u[idx] - sh["u"]).max(axis=(1, 2)) < 1e-6).mean() > 0.9
+        assert np.abs(u[idx] - sh["u"]).max() < 1e-8 and np.abs(x[idx] - sh["x"]).max() < 1e-8
         pr2 = ocp.prepare(pr["x0"], np.zeros(len(idx), dtype=np.int32), sh["x"], sh["u"], sh["pi"], sh["lam"])
         r2 = ocp.solve("rti", pr2["x0"], sub["yref"], sub["yref_e"], pr2["x"], pr2["u"], pr2["pi"], pr2["lam"], nthreads=4)
-        assert (np.abs(u2[idx] - r2["u"]).max(axis=(1, 2)) < 1e-5).mean() > 0.9
+        assert np.abs(u2[idx] - r2["u"]).max() < 1e-7            # second RTI iteration: the 1e-9 difference of the first one re-enters through the linearisation
 
 
 def test_cold_start_and_plant_step():
@@ -218,13 +238,11 @@ def test_config3_full_size_properties():
     _load(s2, wl); s2.prepare(); s2.solve()
     _load(s, wl); s.prepare(); s.solve()
     d12 = np.abs(s.get("u") - s2.get("u")).max(axis=(1, 2))
-    # measured on B200: 99.93 % within 1e-6 (99.7 % within 1e-8); max 4e-5 on 3 problems whose stopping test fires 2 iterations apart
-    assert (d12 < 1e-6).mean() >= 0.99 and d12.max() < 2e-4 and (s2.get_int("status") == 0).all()
+    assert d12.max() < 1e-8 and (s2.get_int("status") == 0).all()   # the two kernels agree on all 4096 problems (r01: 99.9 %, max 4e-5)
     st, it, res, u, x = s.get_int("status"), s.get_int("qp_iter"), s.get("res"), s.get("u"), s.get("x")
     assert (st == 0).all() and it.max() <= 30 and 8 < it.mean() < 16
-    # KKT certificate of all 4096 QPs: 1e-12 target; the rare stall exits (weakly active pair) stay below the reference's 1e-6
-    rmax = res.max(1)
-    assert (rmax < 1e-11).mean() >= 0.999 and rmax.max() < 1e-6
+    # KKT certificate of all 4096 QPs at the full tolerance: no stall exit, no iteration limit
+    assert res[:, :3].max() < 1e-11 and res[:, 3].max() < 1e-18
     assert u[:, :, 0].min() > -1e-9 and u[:, :, 0].max() < 0.03 + 1e-9 and np.abs(u[:, :, 1]).max() < 0.05 + 1e-9
     assert x[:, 1:N, 3].min() > -0.06 - 1e-9 and x[:, 1:N, 3].max() < 0.011 + 1e-9     # h is constrained at k = 1..N-1 (nothing at k = N)
     assert np.array_equal(x[:, 0], s.get("x0"))                     # x_0 + dx_0 = x0bar exactly
@@ -233,7 +251,9 @@ def test_config3_full_size_properties():
     ocp, pr = _oracle_prepared(om, sub, N)
     ro = ocp.solve("rti", pr["x0"], sub["yref"], sub["yref_e"], pr["x"], pr["u"], nthreads=8)
     e = np.abs(u[idx][:, 0] - ro["u"][:, 0]).max(1)
-    assert (e < 1e-6).mean() >= 0.95 and e.max() < 2e-5
+    assert e.max() < 1e-8, e.max()                                 # u0 vs oracle, every problem of the subset
+    u_ex, x_ex = _exact_step(ocp, pr, sub)
+    assert np.abs(u[idx] - u_ex).max() < 1e-8 and np.abs(ro["u"] - u_ex).max() < 1e-8 and np.abs(x[idx] - x_ex).max() < 1e-8   # vs the exact QP solution
 
 
 def _bucketed(wl):
@@ -253,8 +273,7 @@ def test_config4_gpu_share_properties():
     _load(s, wl); s.prepare(); s.solve()
     st, it, res, u, x = s.get_int("status"), s.get_int("qp_iter"), s.get("res"), s.get("u"), s.get("x")
     assert (st == 0).all() and it.max() <= 30
-    rmax = res.max(1)
-    assert (rmax < 1e-11).mean() >= 0.995 and rmax.max() < 1e-6
+    assert res[:, :3].max() < 1e-11 and res[:, 3].max() < 1e-18
     assert u[:, :, 0].min() > -1e-9 and u[:, :, 0].max() < 0.03 + 1e-9 and np.abs(u[:, :, 1]).max() < 0.05 + 1e-9
     assert x[:, 1:N, 3].min() > -0.06 - 1e-9 and x[:, 1:N, 3].max() < 0.011 + 1e-9
     assert np.array_equal(x[:, 0], s.get("x0"))
@@ -264,7 +283,9 @@ def test_config4_gpu_share_properties():
         ocp, pr = _oracle_prepared(oms[o], sub, N)
         ro = ocp.solve("rti", pr["x0"], sub["yref"], sub["yref_e"], pr["x"], pr["u"], nthreads=8)
         e = np.abs(u[idx][:, 0] - ro["u"][:, 0]).max(1)
-        assert (e < 1e-6).mean() >= 0.9 and e.max() < 5e-5, (names[o], e.max())
+        assert e.max() < 1e-8, (names[o], e.max())                 # u0 vs oracle on every problem of the subset
+        u_ex, x_ex = _exact_step(ocp, pr, sub)
+        assert np.abs(u[idx] - u_ex).max() < 1e-8 and np.abs(ro["u"] - u_ex).max() < 1e-8, names[o]   # vs the exact QP solution
         assert np.array_equal(st[idx], ro["status"])
 
 
@@ -341,14 +362,14 @@ def test_long_horizon_falls_back_to_thread_kernel_and_auto_selection():
     s = q.Solver([gm], N, 0.05, B, qp_kernel=1)
     _load(s, wl); s.prepare(); s.solve()
     e = np.abs(s.get("u") - ro["u"]).max(axis=(1, 2))
-    assert (s.get_int("status") == 0).all() and (e < 1e-6).mean() >= 0.8 and e.max() < 1e-4
+    assert (s.get_int("status") == 0).all() and e.max() < 1e-8
     B, N = 64, 40
     wl = make_rti_workload(None, batch=B, N=N, seed=6)
     us = []
     for kern in (2, 1, 0):
         s = q.Solver([gm], N, 0.05, B, qp_kernel=kern)
         _load(s, wl); s.prepare(); s.solve(); us.append(s.get("u"))
-    assert np.array_equal(us[0], us[1]) and np.abs(us[0] - us[2]).max() < 1e-5
+    assert np.array_equal(us[0], us[1]) and np.abs(us[0] - us[2]).max() < 1e-8
 
 
 def test_closed_loop_disturbance_noise_and_delay():
@@ -420,10 +441,8 @@ def test_velocity_constraint_variant_vs_oracle():
         assert np.allclose(s.get("lh"), VARIANT_LH) and np.allclose(s.get("uh"), VARIANT_UH)     # defaults of :247-248
         _load(s, wl); s.prepare(); s.solve()
         it = s.get_int("qp_iter")
-        assert (s.get_int("status") == 0).all() and np.abs(it - ro["qp_iter"]).max() <= 4
-        same = it == ro["qp_iter"]
-        assert same.mean() > 0.7 and np.abs(s.get("u")[same] - ro["u"][same]).max() < 1e-6
-        assert np.abs(s.get("u") - ro["u"]).max() < (2e-5 if N <= 40 else 2e-4)
+        assert (s.get_int("status") == 0).all() and np.abs(it - ro["qp_iter"]).max() <= 2
+        assert np.abs(s.get("u") - ro["u"]).max() < 1e-8           # every problem (r01: 1e-6 where the iteration counts agreed, 2e-5 / 2e-4 otherwise)
         lam = s.get("lam")
         assert (np.abs(lam[:, 1:, [1, 2, 4, 5]]).max(axis=(1, 2)) > 1e-3).sum() >= B // 4     # the v_bound rows are active
         assert rel_err(s.get("cost"), ro["cost"]) < 1e-8 and s.get("res").max() < 1e-6
@@ -549,4 +568,4 @@ def test_every_warp_mapping_vs_thread_kernel(N):
         out.append((s.get("u").reshape(B, -1), s.get_int("status"), s.get("res").max(1)))
     d = np.abs(out[0][0] - out[1][0]).max(1)
     assert np.array_equal(out[0][1], out[1][1]) and (out[0][1] == 0).all()
-    assert np.median(d) < 1e-9 and d.max() < 2e-4 and (out[0][2] < 1e-6).all()
+    assert d.max() < 1e-8 and (out[0][2] < 1e-11).all()            # every mapping, every problem (r01: median 1e-9, max 2e-4)

@@ -197,6 +197,9 @@ def test_erk4_sens_is_derivative_of_rk4_map():
     assert np.array_equal(A[0][:, :2], np.eye(4)[:, :2])          # df/dx = df/dy = 0
 
 
+T_FLOOR = 4e-12          # 4 * qp_t_min of the oracle's IPM
+
+
 def _dense_kkt_check(lin, sol, W, We, dt, lh, uh, x, u, x0bar, yref_e_unused=None):
     """Independent dense-algebra KKT certificate of one QP solution (convex QP: KKT <=> optimal)."""
     N = lin["A"].shape[0]
@@ -216,7 +219,8 @@ def _dense_kkt_check(lin, sol, W, We, dt, lh, uh, x, u, x0bar, yref_e_unused=Non
                 continue
             g[idx[c]] += lam[k, 3 + c] - lam[k, c]
             v = z[idx[c]]; sl, su = v - (lh[c] - h[c]), (uh[c] - h[c]) - v
-            r_in = max(r_in, -min(sl, 0), -min(su, 0)); r_cp = max(r_cp, abs(lam[k, c] * sl), abs(lam[k, 3 + c] * su))
+            # complementarity: a slack at its floor (qp_t_min = 1e-12, "t <= 4 t_min" = converged active pair) counts as zero
+            r_in = max(r_in, -min(sl, 0), -min(su, 0)); r_cp = max(r_cp, lam[k, c] * max(sl - T_FLOOR, 0), lam[k, 3 + c] * max(su - T_FLOOR, 0))
             assert lam[k, c] >= 0 and lam[k, 3 + c] >= 0
         r_stat = max(r_stat, np.abs(g[:2]).max(), np.abs(g[2:]).max() if k > 0 else 0.0)
         r_eq = max(r_eq, np.abs(lin["A"][k] @ dx[k] + lin["B"][k] @ du[k] + lin["b"][k] - dx[k + 1]).max())
@@ -239,27 +243,32 @@ def test_qp_solution_kkt_certificate():
         lb = {k: v[b] for k, v in lin.items()}
         sb = {k: q[k][b] for k in ("du", "dx", "pi", "lam")}
         r = _dense_kkt_check(lb, sb, W, We, dt, [-0.06, 0.0, -0.05], [0.011, 0.03, 0.05], pr["x"][b], pr["u"][b], pr["x0"][b])
-        assert max(r) < 5e-12, (b, r)
+        assert max(r[:3]) < 1.5e-11 and r[3] < 1e-17, (b, r)
 
 
 def test_qp_solution_sensitivity_to_tolerance_is_documented_behaviour():
-    """DESIGN.md "conditioning": the QP of this OCP (input weight 5e-5 vs terminal weight 2e5) amplifies KKT
-    residuals by ~1e7.  At the reference's own QP tolerance (1e-6) du is ~1e-2 away from the exact solution;
-    at 1e-12 two different IPM paths still differ by ~1e-5 (median ~1e-7) although the optimal cost agrees to
-    1e-13.  Parity between implementations is therefore stated for the SAME algorithm and parameters."""
+    """the QP of this OCP (input weight 5e-5 vs terminal weight 2e5, multipliers down to 1e-9) is sensitive to
+    where the IPM stops.  At the reference's own QP tolerance (1e-6 on all four residuals, NMPC_controller.m:276) du is ~1e-2
+    away from the solution; with complementarity at 1e-12 (the round-1 rule) two IPM paths still differ by ~1e-5 although
+    the optimal cost agrees to 1e-13; with the end game of this round (complementarity 1e-18) the paths agree to 1e-8 —
+    tests/test_qp_exact.py compares the point with the exact solution."""
     om = oracle_model("santal")
     B, N = 64, 40
     wl = make_rti_workload(None, batch=B, N=N, seed=2)
     pr = orc.Ocp(om, N, 0.05).prepare(wl["x0"], np.zeros(B, dtype=np.int32), np.zeros((B, N + 1, 4)), wl["u_init"])
-    sol = {}
-    for tol, mu0 in ((1e-6, 1.0), (1e-12, 1.0), (1e-12, 1e-2)):
-        sol[(tol, mu0)] = orc.Ocp(om, N, 0.05, qp_tol=tol, qp_mu0=mu0).qp(pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"], nthreads=4)
-    loose = np.abs(sol[(1e-6, 1.0)]["du"] - sol[(1e-12, 1.0)]["du"]).max()
-    d = np.abs(sol[(1e-12, 1e-2)]["du"] - sol[(1e-12, 1.0)]["du"]).reshape(B, -1).max(1)   # two iterate paths, same limit
-    assert loose > 1e-3, loose
-    assert d.max() < 1e-4 and np.median(d) < 1e-6, (d.max(), np.median(d))
-    dx = np.abs(sol[(1e-12, 1e-2)]["dx"] - sol[(1e-12, 1.0)]["dx"]).max()
-    assert dx < 1e-5, dx
+    args = (pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"])
+    r01 = dict(qp_t_min=0.0, qp_gamma_f=0.0, qp_stall=5)
+    ref = orc.Ocp(om, N, 0.05).qp(*args, nthreads=4)
+    loose = orc.Ocp(om, N, 0.05, qp_tol=1e-6, qp_tol_comp=1e-6, **r01).qp(*args, nthreads=4)
+    assert np.abs(loose["du"] - ref["du"]).max() > 1e-3
+    a = orc.Ocp(om, N, 0.05, qp_tol=1e-12, qp_tol_comp=1e-12, qp_mu0=1.0, **r01).qp(*args, nthreads=4)
+    b = orc.Ocp(om, N, 0.05, qp_tol=1e-12, qp_tol_comp=1e-12, qp_mu0=1e-2, **r01).qp(*args, nthreads=4)
+    d = np.abs(a["du"] - b["du"]).reshape(B, -1).max(1)            # round-1 rule: two iterate paths, same limit
+    assert 1e-6 < d.max() < 1e-4 and np.median(d) < 1e-6, (d.max(), np.median(d))
+    a = orc.Ocp(om, N, 0.05, qp_mu0=1.0).qp(*args, nthreads=4)
+    b = orc.Ocp(om, N, 0.05, qp_mu0=1e-2).qp(*args, nthreads=4)
+    assert np.abs(a["du"] - b["du"]).max() < 1e-8 and np.abs(a["dx"] - b["dx"]).max() < 1e-8
+    assert np.abs(a["du"] - ref["du"]).max() < 1e-8
 
 
 def test_golden_fixtures_match_oracle():
@@ -313,9 +322,9 @@ def test_velocity_constraint_variant_derivative_and_kkt_certificate():
                 a = np.zeros(6); a[0 if c == 0 else 1] = 1.0; a[5] = beta[b, k, c]
                 g += a * (lam[k, 3 + c] - lam[k, c]); v = a @ z
                 sl, su = v - (VARIANT_LH[c] - h[b, k, c]), (VARIANT_UH[c] - h[b, k, c]) - v
-                worst = max(worst, -min(sl, 0), -min(su, 0), abs(lam[k, c] * sl), abs(lam[k, 3 + c] * su))
+                worst = max(worst, -min(sl, 0), -min(su, 0), lam[k, c] * max(sl - T_FLOOR, 0), lam[k, 3 + c] * max(su - T_FLOOR, 0))
                 active += int(c > 0 and max(lam[k, c], lam[k, 3 + c]) > 1e-3 and k > 0 and abs(beta[b, k, c]) > 1.0)
             worst = max(worst, np.abs(g[:2]).max(), np.abs(g[2:]).max() if k > 0 else 0.0)
             worst = max(worst, np.abs(lin["A"][b, k] @ dx[k] + lin["B"][b, k] @ du[k] + lin["b"][b, k] - dx[k + 1]).max())
         worst = max(worst, np.abs(We @ dx[N] + lin["qN"][b] - pi[N - 1]).max())
-    assert worst < 5e-12 and active >= 10, (worst, active)
+    assert worst < 1.5e-11 and active >= 10, (worst, active)

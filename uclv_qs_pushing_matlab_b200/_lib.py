@@ -33,6 +33,7 @@ class Opts(C.Structure):
         ("alpha_min", C.c_double), ("alpha_reduction", C.c_double), ("eps_sufficient_descent", C.c_double),
         ("matlab_single_quirk", C.c_int), ("problems_per_warp", C.c_int), ("qp_kernel", C.c_int),
         ("h_variant", C.c_int),
+        ("qp_tol_comp", C.c_double), ("qp_t_min", C.c_double), ("qp_gamma_f", C.c_double), ("qp_stall", C.c_int),
     ]
 
 

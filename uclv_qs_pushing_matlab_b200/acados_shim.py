@@ -74,7 +74,7 @@ class acados_ocp:
                 kw["h_variant"] = 1                              # NMPC_controller.m:238 (the authors' parked constraint set)
             elif expr_h != ("s", "u_n", "u_t"):
                 raise L.QspushError(f"constr_expr_h {expr_h!r} is not one of the two constraint sets of the reference")
-        for k in ("qp_tol", "qp_mu0", "qp_thr", "qp_tau", "problems_per_warp", "matlab_single_quirk", "qp_kernel"):
+        for k in ("qp_tol", "qp_mu0", "qp_thr", "qp_tau", "qp_tol_comp", "qp_t_min", "qp_gamma_f", "qp_stall", "problems_per_warp", "matlab_single_quirk", "qp_kernel"):
             if opts.get(k) is not None:
                 kw[k] = opts.get(k)
         self.solver = Solver([p._model for p in plants], self.N, self.dt, self.batch, device=device, **kw)

@@ -90,11 +90,14 @@ class bspline_shape:
         return cur
 
     def _mod(self, s):
-        # MATLAB mod(double, single) -> single (b is a `single` because pcread returns single)
-        sf, bf = s.astype(np.float32), np.float32(self.b)
-        r = sf - np.floor(sf / bf) * bf
-        r = np.where(r < 0, r + bf, r)
-        r = np.where(r >= bf, r - bf, r)
+        # MATLAB mod(double, single) -> single (b is a `single` because pcread returns single); the builtin's algorithm:
+        # r = fmod(x, y), 0 when x / y is an integer within eps |x / y|, else r += y when the signs differ (may round to y)
+        x, y = s.astype(np.float32), np.float32(self.b)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            r = np.fmod(x, y)
+            q = np.abs(x / y)
+            req0 = (r == 0) | ~(np.abs(q - np.floor(q + np.float32(0.5))) > np.float32(1.1920929e-7) * q)
+            r = np.where(req0, np.float32(0.0), np.where((x < 0) != (y < 0), r + y, r)).astype(np.float32)
         return r.astype(np.float64)
 
     # bspline_shape.m:181-185

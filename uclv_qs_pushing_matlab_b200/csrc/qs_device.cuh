@@ -89,17 +89,31 @@ QS_HD void curve_dd(const double* __restrict__ M, double sg, double& ex, double&
 
 // MATLAB mod(s,b), b>0, result in [0,b)  (bspline_shape.m:147,155,193; NMPC_controller.m:320,332).
 // With `single` the operation happens in float32, as MATLAB does when b is a `single`.
+// The builtin's algorithm (the form MATLAB Coder emits for mod on floating-point operands): r = fmod(x, y), forced to 0 when
+// x / y is an integer within eps |x / y|, otherwise r += y when the signs differ.  The result can EQUAL y: for a tiny negative
+// x the sum rounds to y (in single precision for |x| < 1.5e-8 at b = 0.28), and x0(4) = mod(x0(4), b) - b (x0(4) < 0) is 0.
 QS_HD double matlab_mod(double s, double b, bool single) {
     if (single) {
-        const float sf = (float)s, bf = (float)b;
-        float r = sf - floorf(sf / bf) * bf;
-        if (r < 0.f) r += bf;
-        if (r >= bf) r -= bf;
+        const float x = (float)s, y = (float)b;
+        if (y == 0.f) return (double)x;
+        if (!(x == x) || !(y == y) || fabsf(x) == (float)INFINITY) return (double)NAN;
+        if (x == 0.f) return (double)(0.f / y);
+        float r = fmodf(x, y);
+        bool req0 = (r == 0.f);
+        if (!req0 && y > floorf(y)) { const float q = fabsf(x / y); req0 = !(fabsf(q - floorf(q + 0.5f)) > 1.1920929e-7f * q); }
+        if (req0) r = y * 0.f;
+        else if ((x < 0.f) != (y < 0.f)) r += y;
         return (double)r;
     }
-    double r = s - floor(s / b) * b;
-    if (r < 0.0) r += b;
-    if (r >= b) r -= b;
+    const double x = s, y = b;
+    if (y == 0.0) return x;
+    if (!(x == x) || !(y == y) || fabs(x) == (double)INFINITY) return (double)NAN;
+    if (x == 0.0) return 0.0 / y;
+    double r = fmod(x, y);
+    bool req0 = (r == 0.0);
+    if (!req0 && y > floor(y)) { const double q = fabs(x / y); req0 = !(fabs(q - floor(q + 0.5)) > 2.220446049250313e-16 * q); }
+    if (req0) r = y * 0.0;
+    else if ((x < 0.0) != (y < 0.0)) r += y;
     return r;
 }
 

@@ -429,14 +429,14 @@ QS_HD void ratio_min(double v, double dv, double& num, double& den) {
 
 // Newton step of one two-sided bound pair (lower: t = v - dl, upper: t = du - v), Mehrotra corrector included.
 struct IneqStep { double dtl, dtu, dll, dlu; };
-QS_HD IneqStep ineq_step(double v, double dva, double dv, double ll, double lu, double tl, double tu, double itl, double itu, double dl, double du, double smu) {
+QS_HD IneqStep ineq_step(double v, double dva, double dv, double ll, double lu, double tl, double tu, double itl, double itu, double dl, double du, double smu, double t_min) {
     const double rdl = v - dl - tl, rdu = du - v - tu;
     const double dtal = dva + rdl, dtau = -dva + rdu;
     const double cl = (-ll - ll * dtal * itl) * dtal, cu = (-lu - lu * dtau * itu) * dtau;
     IneqStep s;
     s.dtl = dv + rdl; s.dtu = -dv + rdu;
-    s.dll = -(ll * tl - smu + cl + ll * s.dtl) * itl;
-    s.dlu = -(lu * tu - smu + cu + lu * s.dtu) * itu;
+    s.dll = -(ll * tl - fmax(smu, ll * t_min) + cl + ll * s.dtl) * itl;      // centering target of a pair: max(sigma mu, lam t_min)
+    s.dlu = -(lu * tu - fmax(smu, lu * t_min) + cu + lu * s.dtu) * itu;
     return s;
 }
 
@@ -819,6 +819,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
     bool act = lane < Lw_ && !st.fin;
     constexpr int hvar = HV;                            // constraint set: compile-time, the default set pays nothing for the coupled rows
     const int m_on = hvar ? 6 * N : 6 * N - 2;
+    const double t4 = 4.0 * Q.t_min;
     int& status = st.status; int& it = st.it; int& stall = st.stall;
     double& rmax_prev = st.rmax_prev; double& r_stat = st.r_stat; double& r_eq = st.r_eq; double& r_in = st.r_in; double& r_cp = st.r_cp;
     const double* qN = st.qN;
@@ -878,8 +879,9 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                     qw_row_add(hvar, c, hk[3], lu - ll, rg);
                     const double rdl = v - (Q.lh[c] - h) - tl, rdu = (Q.uh[c] - h) - v - tu;
                     l_in = fmax(l_in, fmax(fabs(rdl), fabs(rdu)));
-                    l_cp = fmax(l_cp, fmax(ll * tl, lu * tu));
-                    l_mu += ll * tl + lu * tu;
+                    const double pl = tl > t4 ? ll * tl : 0.0, pu = tu > t4 ? lu * tu : 0.0;   // converged active pairs (slack at its floor) leave mu
+                    l_cp = fmax(l_cp, fmax(pl, pu));
+                    l_mu += pl + pu;
                 }
                 if (k == 0) { rg[2] = 0.0; rg[3] = 0.0; rg[4] = 0.0; rg[5] = 0.0; }
 #pragma unroll
@@ -903,13 +905,10 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
         const bool q_nan = w.template wany<SEG>(l_nan ? 1 : 0) || !(mu == mu);
         if (!st.fin) {                                       // stopping tests of this segment's problem
             r_stat = q_stat; r_eq = q_eq; r_in = q_in; r_cp = q_cp;
-            const double rmax = fmax(fmax(r_stat, r_eq), fmax(r_in, r_cp));
             if (q_nan) { status = 2; st.fin = true; }
-            else if (r_stat < Q.tol && r_eq < Q.tol && r_in < Q.tol && r_cp < Q.tol) { status = 0; st.fin = true; }
             else {
-                if (rmax < 0.5 * rmax_prev) { rmax_prev = rmax; stall = 0; } else ++stall;
-                if (stall >= 5 && rmax < QS_QP_TOL_ACCEPT) { status = 0; st.fin = true; }
-                else if (it >= Q.max_iter) { status = 1; st.fin = true; }
+                const int fin_ = qp_stop_test(Q, r_stat, r_eq, r_in, r_cp, it, rmax_prev, stall);
+                if (fin_ >= 0) { status = fin_; st.fin = true; }
             }
         }
     }
@@ -1109,7 +1108,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                     const double dtl = dva + rdl, dtu = -dva + rdu;
                     const double itl = it8[c], itu = it8[4 + c];
                     const double cl = (-ll - ll * dtl * itl) * dtl, cu = (-lu - lu * dtu * itu) * dtu;
-                    qw_row_add(hvar, c, hk[3], (ll * tl - smu + cl + ll * rdl) * itl - (lu * tu - smu + cu + lu * rdu) * itu, gt);
+                    qw_row_add(hvar, c, hk[3], (ll * tl - fmax(smu, ll * Q.t_min) + cl + ll * rdl) * itl - (lu * tu - fmax(smu, lu * Q.t_min) + cu + lu * rdu) * itu, gt);
                 }
 #pragma unroll
                 for (int i = 0; i < 6; ++i) QW_SM(R_GT + i, j) = gt[i];
@@ -1143,8 +1142,9 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                         const double dll = -ll - ll * dtl * it8[c], dlu = -lu - lu * dtu * it8[4 + c];
                         ratio_min(tl, dtl, a_num, a_den); ratio_min(tu, dtu, a_num, a_den);
                         ratio_min(ll, dll, a_num, a_den); ratio_min(lu, dlu, a_num, a_den);
-                        S1 += ll * dtl + tl * dll + lu * dtu + tu * dlu;
-                        S2 += dll * dtl + dlu * dtu;
+                        const double wl = tl > t4 ? 1.0 : 0.0, wu = tu > t4 ? 1.0 : 0.0;
+                        S1 += wl * (ll * dtl + tl * dll) + wu * (lu * dtu + tu * dlu);
+                        S2 += wl * (dll * dtl) + wu * (dlu * dtu);
                     }
                 }
             }
@@ -1152,7 +1152,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             const double mu_aff = (mu_sum + a_aff * (S1 + a_aff * S2)) / (double)m_on;
             double sigma = (mu > 0.0) ? mu_aff / mu : 0.0;
             sigma = sigma * sigma * sigma;
-            smu = fmax(sigma * mu, 0.1 * Q.tol);
+            smu = fmax(sigma * mu, 0.1 * Q.tol_cp);
         }
     }
     QW_TICK(7);
@@ -1174,14 +1174,14 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                 if (!h_on(hvar, k, c)) continue;
                 IneqStep s_ = ineq_step(qw_row(hvar, c, hk[3], z6), QW_SM(R_DZA + c, j), qw_row(hvar, c, hk[3], dz6),
                                         QW_SM(R_LAM + c, j), QW_SM(R_LAM + 3 + c, j), QW_SM(R_T + c, j), QW_SM(R_T + 3 + c, j),
-                                        it8[c], it8[4 + c], Q.lh[c] - hk[c], Q.uh[c] - hk[c], smu);
+                                        it8[c], it8[4 + c], Q.lh[c] - hk[c], Q.uh[c] - hk[c], smu, Q.t_min);
                 ratio_min(QW_SM(R_T + c, j), s_.dtl, m_num, m_den); ratio_min(QW_SM(R_T + 3 + c, j), s_.dtu, m_num, m_den);
                 ratio_min(QW_SM(R_LAM + c, j), s_.dll, m_num, m_den); ratio_min(QW_SM(R_LAM + 3 + c, j), s_.dlu, m_num, m_den);
             }
         }
     }
     a_max = w.template wmin<SEG>(fmin(a_max, m_num / m_den));
-    const double alpha = fmin(1.0, Q.tau * a_max);
+    const double alpha = qp_step_length(Q, a_max, smu, mu);
     if (!(alpha == alpha) && !st.fin) { status = 2; st.fin = true; }
     if (!w.wany(st.fin ? 0 : 1)) return 1;
     act = act && !st.fin;
@@ -1215,7 +1215,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                     if (!h_on(hvar, k, c)) continue;
                     IneqStep s_ = ineq_step(qw_row(hvar, c, hk[3], z6), QW_SM(R_DZA + c, j), qw_row(hvar, c, hk[3], dz),
                                             QW_SM(R_LAM + c, j), QW_SM(R_LAM + 3 + c, j), QW_SM(R_T + c, j), QW_SM(R_T + 3 + c, j),
-                                            it8[c], it8[4 + c], Q.lh[c] - hk[c], Q.uh[c] - hk[c], smu);
+                                            it8[c], it8[4 + c], Q.lh[c] - hk[c], Q.uh[c] - hk[c], smu, Q.t_min);
                     QW_SM(R_T + c, j) = fma(alpha, s_.dtl, QW_SM(R_T + c, j));
                     QW_SM(R_T + 3 + c, j) = fma(alpha, s_.dtu, QW_SM(R_T + 3 + c, j));
                     QW_SM(R_LAM + c, j) = fma(alpha, s_.dll, QW_SM(R_LAM + c, j));

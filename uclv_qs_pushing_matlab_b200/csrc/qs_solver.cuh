@@ -44,7 +44,7 @@ struct SolverDev {
     double *wpi, *wlam, *wx0;
 };
 
-struct IpmOpts { int max_iter; double tol, mu0, thr, tau; };
+struct IpmOpts { int max_iter; double tol, mu0, thr, tau, tol_cp, t_min, gamma_f; int stall; };
 struct SqpOpts { int max_iter; double tol[4]; int globalization; double alpha_min, alpha_red, eps_sd; };
 struct CtrlDev { double v_alpha, d_v_bound, t_angle0, u_t_ub, u_n_lb; int single; };
 
@@ -269,6 +269,7 @@ QS_HD void qp_one(const SolverDev& S, const IpmOpts& o, int b, int apply) {
     for (int i = 0; i < 3; ++i) { C.lh[i] = S.lh[i]; C.uh[i] = S.uh[i]; }
     C.h_variant = 0;                           // the thread-per-problem kernel implements h = [s; u_n; u_t] only
     C.max_iter = o.max_iter; C.tol = o.tol; C.mu0 = o.mu0; C.thr = o.thr; C.tau = o.tau;
+    C.tol_cp = o.tol_cp; C.t_min = o.t_min; C.gamma_f = o.gamma_f; C.stall = o.stall;
     QpView V;
     V.stride = (size_t)S.Bp;
     V.hv = S.hv + b;
@@ -319,6 +320,7 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm_warp, int pe
     for (int i = 0; i < 3; ++i) { Qc.lh[i] = S.lh[i]; Qc.uh[i] = S.uh[i]; }
     Qc.h_variant = HV;
     Qc.max_iter = o.max_iter; Qc.tol = o.tol; Qc.mu0 = o.mu0; Qc.thr = o.thr; Qc.tau = o.tau;
+    Qc.tol_cp = o.tol_cp; Qc.t_min = o.t_min; Qc.gamma_f = o.gamma_f; Qc.stall = o.stall;
     // SEG = 32: one problem per warp.  SEG = 16 (N <= 15): lanes 0..15 and 16..31 carry one problem each; `b` is the
     // problem of this lane's segment (-1: none), every per-problem quantity below is per segment.
     const int seg = w.lane() / SEG;

@@ -252,7 +252,8 @@ void qspush_opts_default(qspush_opts* o) {
     o->max_sqp_iter = 30;                                      // NMPC_controller.m:276
     o->tol_stat = o->tol_eq = o->tol_ineq = o->tol_comp = 1e-6;
     o->qp_max_iter = 50;
-    o->qp_tol = 1e-12; o->qp_mu0 = 0.1; o->qp_thr = 1e-3; o->qp_tau = 0.9995;   // tuned on config 3: K_ipm 12.3 -> 11.0
+    o->qp_tol = 1e-11; o->qp_mu0 = 0.1; o->qp_thr = 1e-3; o->qp_tau = 0.9995;   // mu0 tuned on config 3: K_ipm 12.3 -> 11.0
+    o->qp_tol_comp = 1e-18; o->qp_t_min = 1e-12; o->qp_gamma_f = 0.05; o->qp_stall = 10;   // end game: DESIGN.md 2.1
     o->globalization = 1;                                      // merit_backtracking, :272
     o->alpha_min = 0.05; o->alpha_reduction = 0.7; o->eps_sufficient_descent = 1e-4;
     o->matlab_single_quirk = 1;
@@ -649,7 +650,7 @@ int qspush_solve(qspush_solver* s) {
     CK(cudaSetDevice(s->device));
     RET(flush_cost(s));
     const qspush_opts& o = s->opts;
-    IpmOpts io{o.qp_max_iter, o.qp_tol, o.qp_mu0, o.qp_thr, o.qp_tau};
+    IpmOpts io{o.qp_max_iter, o.qp_tol, o.qp_mu0, o.qp_thr, o.qp_tau, o.qp_tol_comp, o.qp_t_min, o.qp_gamma_f, o.qp_stall};
     const int ppw = pick_ppw(s);
     const size_t smem = model_smem_bytes(s->nmodels);
     const size_t nlin = (size_t)(s->N + 1) * s->Bp;
