@@ -204,6 +204,25 @@ int qspush_set_reference_trajectory(qspush_solver* s, const double* traj, int T,
  * of the last window column.  Asynchronous on the solver's stream; with it a control period moves only x0 (in) and
  * u0 / status (out) between host and device. */
 int qspush_set_reference_window(qspush_solver* s, int idx);
+/* One control period at the controller boundary = NMPC_controller.solve(x0, index_time) for the whole batch
+ * (NMPC_controller.m:329-423) as ONE CUDA graph launch (RTI mode):
+ *     constr_x0 <- x0, reference window of period idx (when a trajectory is set, else the references as last set),
+ *     x0 wrap / cold start / v_bound clip / Euler rollout (:332, 351-380), linearisation, QP, full step (:389),
+ *     u0 = get('u', 0) (:403) and status, optionally the shift of the warm start (:397-399).
+ * Kernels per period: k_prepare, k_linearise, k_qp_warp, k_step_out (+ k_shift) — against 9 launches and as many host
+ * round trips through qspush_set / _set_reference_window / _prepare / _solve / _get.  Same arithmetic, bit-identical u0.
+ *   x0 [batch][4] in, u0 [batch][2] and status [batch] out, all in `mem`; with host memory the call returns after the
+ *   results have arrived (one synchronisation), with device memory it is asynchronous on the solver's stream.
+ * flags: QSPUSH_STEP_SHIFT          shift the warm start after the solve (what the controller does every period)
+ *        QSPUSH_STEP_RESTORE_GUESS  before the period, restore the initial guess saved by qspush_snapshot_guess
+ *                                   (benchmarks: every period solves the same problems)                              */
+enum { QSPUSH_STEP_SHIFT = 1, QSPUSH_STEP_RESTORE_GUESS = 2 };
+int qspush_step(qspush_solver* s, const double* x0, int idx, unsigned flags, double* u0, int* status, qspush_mem mem);
+/* save the current input trajectory (QSPUSH_U) on the device for QSPUSH_STEP_RESTORE_GUESS */
+int qspush_snapshot_guess(qspush_solver* s);
+/* Measured FP64 roofline denominator of this device: DFMA issue-rate microbenchmark (16 independent chains per thread, all
+ * SMs, no memory traffic), best of 5 event-timed launches, in TFLOP/s (2 flop per DFMA).  SURVEY.md 7 step 3. */
+int qspush_measure_fp64_peak(int device, double* tflops);
 /* wait for everything queued on the solver's stream */
 int qspush_sync(qspush_solver* s);
 /* the solver's cudaStream_t (as void*) so callers can order their own work / events on it */

@@ -31,13 +31,31 @@ def build(force: bool = False) -> str:
 
 
 _lib = None
+_build = "parity"
+
+
+def select_build(which: str) -> None:
+    """'parity' (default): libqs_oracle.so, -O2 without FMA contraction — the arithmetic the golden fixtures were frozen with.
+    'fast': libqs_oracle_fast.so, the same source at -O3 -march=x86-64-v3 — the timed CPU baseline of bench.py.
+    Must be called before the library is first used."""
+    global _build
+    if _lib is not None and which != _build:
+        raise RuntimeError("oracle library already loaded")
+    if which not in ("parity", "fast"):
+        raise ValueError(which)
+    _build = which
 
 
 def lib():
     global _lib
     if _lib is None:
         build()
-        L = C.CDLL(_LIB_PATH)
+        path = _LIB_PATH
+        if _build == "fast":
+            path = os.path.join(_HERE, "libqs_oracle_fast.so")
+            if not os.path.exists(path) or os.path.getmtime(os.path.join(_HERE, "qs_oracle.cpp")) > os.path.getmtime(path):
+                subprocess.check_call(["make", "-C", _HERE, "-s", "libqs_oracle_fast.so"])
+        L = C.CDLL(path)
         L.orc_model_create.restype = C.c_void_p
         L.orc_model_create.argtypes = [_dp, C.c_int, _dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
         L.orc_model_from_ply.restype = C.c_void_p

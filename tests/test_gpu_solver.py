@@ -569,3 +569,65 @@ def test_every_warp_mapping_vs_thread_kernel(N):
     d = np.abs(out[0][0] - out[1][0]).max(1)
     assert np.array_equal(out[0][1], out[1][1]) and (out[0][1] == 0).all()
     assert d.max() < 1e-8 and (out[0][2] < 1e-11).all()            # every mapping, every problem (r01: median 1e-9, max 2e-4)
+
+
+def test_step_graph_is_the_field_by_field_control_period():
+    """qspush_step (one CUDA graph: k_prepare, k_linearise, k_qp_warp, k_step_out [+ k_shift]) = the control period built
+    from qspush_set / _set_reference_window / _prepare / _solve / _get / _shift: bit-identical u0, status, warm start; host and
+    device buffers; the shift flag; the restored guess; graphs survive an option change (re-captured)."""
+    import torch
+    gm = gpu_model("santal")
+    B, N, T = 300, 40, 64                                         # more problems than resident slots on a small box? (ordered queue path at 4096 in bench)
+    wl = make_rti_workload(None, batch=B, N=N, seed=12)
+    traj = np.zeros((T, 6)); traj[:, 0] = 0.01 * 0.05 * np.arange(T)
+    off = np.zeros((B, 6)); off[:, :2] = wl["x0"][:, :2]
+    zeros = np.zeros(B, dtype=np.int32)
+
+    def reference(periods, shift):
+        s = q.Solver([gm], N, 0.05, B)
+        s.set_reference_trajectory(traj, off)
+        s.set("u", wl["u_init"]); s.set_int("cold", zeros)
+        x0 = wl["x0"].copy(); out = []
+        for i in range(1, periods + 1):
+            s.set("x0", x0); s.set_reference_window(i); s.prepare(); s.solve()
+            u0 = s.get("u", stage=0); st = s.get_int("status")
+            if shift:
+                s.shift()
+            out.append((u0, st, s.get("u"), s.get("x")))
+            x0 = s.plant_step(x0.copy(), u0)
+        return out
+
+    ref = reference(3, True)
+    s = q.Solver([gm], N, 0.05, B)
+    s.set_reference_trajectory(traj, off)
+    s.set("u", wl["u_init"]); s.set_int("cold", zeros)
+    x0 = wl["x0"].copy()
+    l0 = s.launches
+    for i in range(1, 4):
+        u0, st = s.step(x0, i, shift=True)
+        assert np.array_equal(u0, ref[i - 1][0]) and np.array_equal(st, ref[i - 1][1]) and (st == 0).all()
+        assert np.array_equal(s.get("u"), ref[i - 1][2]) and np.array_equal(s.get("x"), ref[i - 1][3])
+        x0 = s.plant_step(x0.copy(), u0)
+    # device buffers, no shift, restored guess: every period solves the same problems
+    ref1 = reference(1, False)
+    s = q.Solver([gm], N, 0.05, B)
+    s.set_reference_trajectory(traj, off)
+    s.set("u", wl["u_init"]); s.set_int("cold", zeros); s.snapshot_guess()
+    dx0 = torch.from_numpy(wl["x0"]).cuda()
+    du0 = torch.empty(B, 2, dtype=torch.float64, device="cuda"); dst = torch.empty(B, dtype=torch.int32, device="cuda")
+    l0 = s.launches
+    for rep in range(3):
+        s.step(dx0, 1, du0, dst, restore_guess=True); s.sync()
+        assert np.array_equal(du0.cpu().numpy(), ref1[0][0]) and (dst.cpu().numpy() == 0).all()
+    assert (s.launches - l0) / 3 <= 4                            # k_prepare, k_linearise, k_qp_warp, k_step_out
+    assert s.stat("time_qp_sol") > 0 and s.stat("time_prep") > 0  # phase events are part of the graph
+    s.set_opts(qp_max_iter=49)                                    # drops the graph; the next period re-captures
+    s.step(dx0, 1, du0, dst, restore_guess=True); s.sync()
+    assert np.array_equal(du0.cpu().numpy(), ref1[0][0])
+    with pytest.raises(q.QspushError):
+        s.step(dx0, 0, du0, dst)                                  # idx is 1-based
+    with pytest.raises(q.QspushError):
+        s.step(wl["x0"], 1, du0, dst)                             # mixed memory spaces
+    sq = q.Solver([gm], N, 0.05, B, mode=1)
+    with pytest.raises(q.QspushError):
+        sq.step(wl["x0"], 1)                                      # RTI only

@@ -14,7 +14,7 @@ a CUDA device every compute call raises QspushError.
 """
 from . import _lib
 from ._lib import QspushError
-from .capi import Model, Solver, default_ctrl, default_opts
+from .capi import Model, Solver, default_ctrl, default_opts, measure_fp64_peak
 
 _lib.lib()  # fail loudly at import time if libqspush.so is missing or does not export the C-ABI
 
@@ -27,6 +27,6 @@ from .helper import helper  # noqa: E402
 from .trajectory_generator import TrajectoryGenerator  # noqa: E402
 from . import sharding  # noqa: E402
 
-__all__ = ["QspushError", "Model", "Solver", "default_opts", "default_ctrl", "OBJECT_TABLE", "object_selection",
+__all__ = ["QspushError", "Model", "Solver", "default_opts", "default_ctrl", "measure_fp64_peak", "OBJECT_TABLE", "object_selection",
            "bspline_shape", "PusherSliderModel", "acados_ocp", "NMPC_controller", "helper", "TrajectoryGenerator",
            "sharding"]

@@ -56,6 +56,7 @@ STATUS, SQP_ITER, QP_ITER, OBJECT_ID, COLD = 32, 33, 34, 35, 36
 MEM_HOST, MEM_DEVICE = 0, 1
 MODE_RTI, MODE_SQP = 0, 1
 TIME_TOT, TIME_LIN, TIME_QP, TIME_PREP = 0, 1, 2, 3
+STEP_SHIFT, STEP_RESTORE_GUESS = 1, 2
 
 # every symbol include/qspush.h declares: name -> (restype, argtypes)
 SIGNATURES = {
@@ -88,6 +89,9 @@ SIGNATURES = {
     "qspush_set_reference_trajectory": (C.c_int, [vp, vp, C.c_int, vp, C.c_int]),
     "qspush_set_reference_window": (C.c_int, [vp, C.c_int]),
     "qspush_closed_loop": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, C.POINTER(LoopOpts), vp, vp, vp, C.c_int]),
+    "qspush_step": (C.c_int, [vp, vp, C.c_int, C.c_uint, vp, vp, C.c_int]),
+    "qspush_snapshot_guess": (C.c_int, [vp]),
+    "qspush_measure_fp64_peak": (C.c_int, [C.c_int, dp]),
     "qspush_sync": (C.c_int, [vp]),
     "qspush_stream": (vp, [vp]),
     "qspush_get_stat": (C.c_int, [vp, C.c_int, dp]),

@@ -121,6 +121,13 @@ class Model:
         return vb, ta
 
 
+def measure_fp64_peak(device=0) -> float:
+    """FP64 DFMA issue rate of the device in TFLOP/s (qspush_measure_fp64_peak)."""
+    v = C.c_double()
+    L.check(L.lib().qspush_measure_fp64_peak(int(device), C.byref(v)))
+    return v.value
+
+
 def default_opts(**kw) -> L.Opts:
     o = L.Opts()
     L.lib().qspush_opts_default(C.byref(o))
@@ -310,6 +317,28 @@ class Solver:
         """Reference window of control period idx (1-based) into cost_y_ref / cost_y_ref_e of every stage
         (NMPC_controller.m:307-313, 343-348), on the device (qspush_set_reference_window)."""
         L.check(L.lib().qspush_set_reference_window(self._h, int(idx)))
+
+    def step(self, x0, idx=1, u0=None, status=None, shift=False, restore_guess=False):
+        """One control period at the controller boundary = NMPC_controller.solve(x0, index_time) for the batch as one CUDA
+        graph launch (qspush_step): x0 (batch,4) in, u0 (batch,2) and status (batch) out, all host (numpy / pinned torch)
+        or all torch CUDA tensors.  Returns (u0, status)."""
+        px, mem, kx = _buf(x0)
+        on_dev = mem == L.MEM_DEVICE
+        if u0 is None:
+            u0 = torch.empty(self.batch, 2, dtype=torch.float64, device=x0.device) if on_dev else np.zeros((self.batch, 2))
+        if status is None:
+            status = torch.empty(self.batch, dtype=torch.int32, device=x0.device) if on_dev else np.zeros(self.batch, dtype=np.int32)
+        pu, mem_u, ku = _buf(u0, writable=True)
+        ps, mem_s, ks = _buf(status, dtype=np.int32, writable=True)
+        if mem_u != mem or mem_s != mem:
+            raise L.QspushError("x0, u0 and status must live in the same memory space")
+        flags = (L.STEP_SHIFT if shift else 0) | (L.STEP_RESTORE_GUESS if restore_guess else 0)
+        L.check(L.lib().qspush_step(self._h, px, int(idx), flags, pu, ps, mem))
+        return u0, status
+
+    def snapshot_guess(self):
+        """Save the current input trajectory on the device for step(restore_guess=True)."""
+        L.check(L.lib().qspush_snapshot_guess(self._h))
 
     def sync(self):
         L.check(L.lib().qspush_sync(self._h))

@@ -167,13 +167,6 @@ __global__ void k_eval_vbound(const double* __restrict__ gmodel, int cnt, const 
 // ------------------------------------------------------------------------------------------------
 // solver kernels: thin launch wrappers around the per-thread bodies in qs_solver.cuh
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_prepare(SolverDev S, CtrlDev cp) {
-    const double* Mall = stage_models(S.models, S.nmodels);
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= S.B) return;
-    prepare_one(S, cp, Mall, b);
-}
-
 // one thread per (problem, stage); consecutive threads walk problems -> coalesced slab accesses
 __global__ void __launch_bounds__(128, 3) k_linearise(SolverDev S) {
     const double* Mall = stage_models(S.models, S.nmodels);
@@ -345,6 +338,72 @@ __global__ void __launch_bounds__(128) k_loop_post(SolverDev S, double* xs, doub
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= S.B) return;
     loop_post_one(S, Mall, xs, log_u, log_status, b);
+}
+
+
+// ---- FP64 roofline denominator, measured (MEASURED_PEAKS.json has no FP64 entry): 16 independent
+// DFMA chains per thread, 4 x 256-thread CTAs per SM resident, no memory traffic.  qspush_measure_fp64_peak times it.
+__global__ void __launch_bounds__(256) k_fp64_peak(double* __restrict__ out, int iters, double a, double b) {
+    double v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (double)(threadIdx.x + i) * 1e-3;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fma(v[i], a, b);
+    }
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += v[i];
+    if (t == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = t;     // never true: keeps the chains alive
+}
+
+// ---- controller-level step (qspush_step): the whole NMPC_controller.solve pre-processing in ONE launch and the whole
+// post-processing in one.  k_prepare (step form): constr_x0 from the caller's [B][4] array, reference window of period *idx
+// (NMPC_controller.m:307-313, 343-348; skipped when no trajectory is set), then prepare_one (x0 wrap, cold start, v_bound
+// clip, Euler rollout).  k_step_out: u0 = get('u', 0) and status to [B][2] / [B] arrays; the last CTA also sorts the
+// work queue of the NEXT solve by this solve's IPM iteration counts (what k_qp_order does as a launch of its own).
+// K6.  ONE kernel for both entry points (two instantiations of prepare_one were contracted differently by the compiler and
+// disagreed in the last bit): qspush_prepare passes x0 = nullptr / L.traj = nullptr and the kernel works on the slabs as set;
+// qspush_step passes the caller's [B][4] state and the device-resident reference trajectory.
+__global__ void __launch_bounds__(128) k_prepare(SolverDev S, CtrlDev cp, LoopDev L, const int* __restrict__ idx, const double* __restrict__ x0) {
+    const double* Mall = stage_models(S.models, S.nmodels);
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= S.B) return;
+    if (x0) {
+        const double2 a = reinterpret_cast<const double2*>(x0)[2 * b], c = reinterpret_cast<const double2*>(x0)[2 * b + 1];
+        QS_EL(S.x0, 0, b) = a.x; QS_EL(S.x0, 1, b) = a.y; QS_EL(S.x0, 2, b) = c.x; QS_EL(S.x0, 3, b) = c.y;
+    }
+    if (L.traj) {
+        const int i0 = *idx;
+        for (int k = 0; k < S.N; ++k) loop_window_one(S, L, i0, k, b);
+    }
+    prepare_one(S, cp, Mall, b);
+}
+__global__ void __launch_bounds__(1024) k_step_out(SolverDev S, double* __restrict__ u0, int* __restrict__ status, int* __restrict__ order) {
+    if (blockIdx.x + 1 == gridDim.x) {                          // last CTA: counting sort, descending previous iteration count
+        __shared__ int cnt[QO_BINS], pos[QO_BINS];
+        if (threadIdx.x < QO_BINS) cnt[threadIdx.x] = 0;
+        __syncthreads();
+        for (int b = threadIdx.x; b < S.B; b += blockDim.x) {
+            const int k = S.qp_last[b];
+            atomicAdd(&cnt[QO_BINS - 1 - (k < 0 ? 0 : (k > QO_BINS - 1 ? QO_BINS - 1 : k))], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int a = 0; for (int i = 0; i < QO_BINS; ++i) { pos[i] = a; a += cnt[i]; } }
+        __syncthreads();
+        for (int b = threadIdx.x; b < S.B; b += blockDim.x) {
+            const int k = S.qp_last[b];
+            order[atomicAdd(&pos[QO_BINS - 1 - (k < 0 ? 0 : (k > QO_BINS - 1 ? QO_BINS - 1 : k))], 1)] = b;
+        }
+        return;
+    }
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= S.B) return;
+    reinterpret_cast<double2*>(u0)[b] = make_double2(QS_EL(S.u, 0, b), QS_EL(S.u, 1, b));
+    status[b] = S.status[b];
 }
 
 }  // namespace qs

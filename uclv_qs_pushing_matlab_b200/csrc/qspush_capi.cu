@@ -56,7 +56,22 @@ struct qspush_solver {
     double t_tot = 0, t_lin = 0, t_qp = 0, t_prep = 0;
     long long launches = 0;
     bool smem_attr_set = false;
+    // qspush_step: one CUDA graph per flag combination (captured on first use, dropped when options / cost / bounds change)
+    cudaGraphExec_t step_exec[4] = {nullptr, nullptr, nullptr, nullptr};
+    double* d_guess = nullptr;     // qspush_snapshot_guess: copy of the u slab
+    int* d_idx = nullptr;          // reference index of the current period (read by k_step_prepare)
+    int step_launches = 0;         // kernels inside one step graph
+    bool capturing = false;        // the step graph is being captured
+    bool order_valid = false;      // d_order holds a permutation (written by k_step_out / k_qp_order)
 };
+// phase events: plain records outside a capture; inside the capture of the step graph they must be EXTERNAL event-record
+// nodes (a plain cudaEventRecord on a capturing stream only creates a capture-internal dependency, not a timed event)
+static cudaError_t rec_event(qspush_solver* s, int i) {
+    return s->capturing ? cudaEventRecordWithFlags(s->ev[i], s->stream, cudaEventRecordExternal) : cudaEventRecord(s->ev[i], s->stream);
+}
+static void drop_step_graphs(qspush_solver* s) {
+    for (auto& g : s->step_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+}
 
 extern "C" {
 
@@ -373,6 +388,9 @@ void qspush_solver_free(qspush_solver* s) {
     if (s->d_ref_traj) cudaFree(s->d_ref_traj);
     if (s->d_ref_off) cudaFree(s->d_ref_off);
     if (s->h_ndone) cudaFreeHost(s->h_ndone);
+    drop_step_graphs(s);
+    if (s->d_guess) cudaFree(s->d_guess);
+    if (s->d_idx) cudaFree(s->d_idx);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -381,12 +399,13 @@ int qspush_solver_set_opts(qspush_solver* s, const qspush_opts* o) {
     if (!s || !o) return fail(QSPUSH_ERR_ARG, "NULL argument");
     const bool changed = (o->h_variant != 0) != (s->opts.h_variant != 0);
     s->opts = *o;
+    drop_step_graphs(s);
     if (changed) reset_bounds(s);
     return QSPUSH_OK;
 }
 int qspush_solver_set_ctrl(qspush_solver* s, const qspush_ctrl* c) {
     if (!s || !c) return fail(QSPUSH_ERR_ARG, "NULL argument");
-    s->ctrl = *c; return QSPUSH_OK;
+    s->ctrl = *c; drop_step_graphs(s); return QSPUSH_OK;
 }
 }  // extern "C"
 
@@ -445,11 +464,13 @@ int qspush_set(qspush_solver* s, qspush_field f, int stage, int lo, int hi, cons
         else if (stage == -1) for (int k = 0; k < N; ++k) std::memcpy(&s->W[(size_t)k * 36], data, 36 * 8);
         else return fail(QSPUSH_ERR_ARG, "cost_W: stage out of range");
         s->cost_dirty = true;
+        drop_step_graphs(s);
         return QSPUSH_OK;
     }
     if (f == QSPUSH_LH || f == QSPUSH_UH) {
         if (mem != QSPUSH_MEM_HOST) return fail(QSPUSH_ERR_ARG, "bounds must be passed from host memory");
         for (int i = 0; i < 3; ++i) (f == QSPUSH_LH ? s->dev.lh : s->dev.uh)[i] = data[i];
+        drop_step_graphs(s);                                    // the bounds travel with the kernel arguments
         return QSPUSH_OK;
     }
     FieldInfo fi;
@@ -545,17 +566,17 @@ static CtrlDev ctrl_dev(const qspush_solver* s) {
 int qspush_prepare(qspush_solver* s) {
     if (!s) return fail(QSPUSH_ERR_ARG, "NULL solver");
     CK(cudaSetDevice(s->device));
-    CK(cudaEventRecord(s->ev[4], s->stream));
-    k_prepare<<<(s->B + 127) / 128, 128, model_smem_bytes(s->nmodels), s->stream>>>(s->dev, ctrl_dev(s));
+    CK(rec_event(s, 4));
+    k_prepare<<<(s->B + 127) / 128, 128, model_smem_bytes(s->nmodels), s->stream>>>(s->dev, ctrl_dev(s), LoopDev{}, nullptr, nullptr);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(s->ev[5], s->stream));
+    CK(rec_event(s, 5));
     s->launches++;
     return QSPUSH_OK;
 }
 
 // launch the QP kernel selected by opts.qp_kernel: 1 (default when the horizon fits) = warp kernel (one or two problems per warp),
 // parallel-in-time; 0 = one problem per thread (any horizon)
-static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, int ppw, int apply) {
+static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, int ppw, int apply, bool order_ready = false) {
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device);
     // throughput mapping (two problems per warp up to N = 55) unless the batch is so small that every problem gets an SM
@@ -595,9 +616,12 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
     SolverDev Dq = D;
     Dq.order = nullptr;
     if (s->B > nsm * Wl * ppw_seg && !std::getenv("QSPUSH_NO_ORDER")) {                // more problems than resident slots
-        k_qp_order<<<1, 1024, 0, s->stream>>>(D, s->d_order);
+        if (!order_ready) {                                     // (qspush_step: k_step_out of the previous period wrote the order)
+            k_qp_order<<<1, 1024, 0, s->stream>>>(D, s->d_order);
+            s->launches++;
+            s->order_valid = true;
+        }
         Dq.order = s->d_order;
-        s->launches++;
     }
 #define QW_LAUNCH(CC, HV, SEG)                                                                                     \
     CK(cudaFuncSetAttribute(k_qp_warp<CC, HV, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
@@ -645,27 +669,32 @@ static int pick_ppw(const qspush_solver* s) {
     return 8;
 }
 
+static int solve_impl(qspush_solver* s, bool order_ready);
 int qspush_solve(qspush_solver* s) {
     if (!s) return fail(QSPUSH_ERR_ARG, "NULL solver");
     CK(cudaSetDevice(s->device));
     RET(flush_cost(s));
+    return solve_impl(s, false);
+}
+}  // extern "C"
+static int solve_impl(qspush_solver* s, bool order_ready) {
     const qspush_opts& o = s->opts;
     IpmOpts io{o.qp_max_iter, o.qp_tol, o.qp_mu0, o.qp_thr, o.qp_tau, o.qp_tol_comp, o.qp_t_min, o.qp_gamma_f, o.qp_stall};
     const int ppw = pick_ppw(s);
     const size_t smem = model_smem_bytes(s->nmodels);
     const size_t nlin = (size_t)(s->N + 1) * s->Bp;
     const unsigned lin_blocks = (unsigned)((nlin + 127) / 128);
-    CK(cudaEventRecord(s->ev[0], s->stream));
+    CK(rec_event(s, 0));
     if (o.mode == QSPUSH_MODE_RTI) {
         SolverDev D = s->dev; D.done = nullptr;
         apply_variant(s, D);
         k_linearise<<<lin_blocks, 128, smem, s->stream>>>(D);
-        CK(cudaEventRecord(s->ev[1], s->stream));
-        RET(launch_qp(s, D, io, ppw, 1));
-        CK(cudaEventRecord(s->ev[2], s->stream));
+        CK(rec_event(s, 1));
+        RET(launch_qp(s, D, io, ppw, 1, order_ready));
+        CK(rec_event(s, 2));
         CK(cudaGetLastError());
         s->launches += 2;
-        CK(cudaEventRecord(s->ev[3], s->stream));
+        CK(rec_event(s, 3));
         return QSPUSH_OK;
     }
     // ---- full SQP (NMPC_controller.m:271-276): host-driven loop, per-problem convergence on the device
@@ -686,12 +715,112 @@ int qspush_solve(qspush_solver* s) {
         k_linesearch<<<(unsigned)((s->B + 31) / 32), dim3(32, LS_CHUNKS), smem, s->stream>>>(D, so, it);
         s->launches += 2;
     }
-    CK(cudaEventRecord(s->ev[1], s->stream));
-    CK(cudaEventRecord(s->ev[2], s->stream));
+    CK(rec_event(s, 1));
+    CK(rec_event(s, 2));
     k_cost<<<(s->B + 127) / 128, 128, 0, s->stream>>>(D);
     CK(cudaGetLastError());
     s->launches++;
-    CK(cudaEventRecord(s->ev[3], s->stream));
+    CK(rec_event(s, 3));
+    return QSPUSH_OK;
+}
+extern "C" {
+
+// DFMA issue-rate microbenchmark: best of 5 launches, CUDA-event timed; *tflops = 2 flop per DFMA
+int qspush_measure_fp64_peak(int device, double* tflops) {
+    if (!tflops) return fail(QSPUSH_ERR_ARG, "NULL argument");
+    RET(need_device(device));
+    CK(cudaSetDevice(device));
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+    const int blocks = nsm * 8, threads = 256, iters = 4096;
+    double* d = nullptr;
+    CK(cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CK(cudaEventRecord(e0));
+        k_fp64_peak<<<blocks, threads>>>(d, iters, 0.999999, 1e-7);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 16.0 * 8.0 * iters * (double)blocks * threads / ((double)ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops = best;
+    return QSPUSH_OK;
+}
+
+int qspush_snapshot_guess(qspush_solver* s) {
+    if (!s) return fail(QSPUSH_ERR_ARG, "NULL solver");
+    CK(cudaSetDevice(s->device));
+    const size_t bytes = (size_t)s->N * 2 * s->Bp * sizeof(double);
+    if (!s->d_guess) CK(cudaMalloc(&s->d_guess, bytes));
+    CK(cudaMemcpyAsync(s->d_guess, s->dev.u, bytes, cudaMemcpyDeviceToDevice, s->stream));
+    return QSPUSH_OK;
+}
+
+// launches per period of the RTI step graph: k_prepare, k_linearise, k_qp_warp (or k_qp), k_step_out (+ k_shift)
+int qspush_step(qspush_solver* s, const double* x0, int idx, unsigned flags, double* u0, int* status, qspush_mem mem) {
+    if (!s || !x0 || !u0 || !status) return fail(QSPUSH_ERR_ARG, "NULL argument");
+    if (flags & ~3u) return fail(QSPUSH_ERR_ARG, "qspush_step: unknown flag");
+    if (s->opts.mode != QSPUSH_MODE_RTI) return fail(QSPUSH_ERR_ARG, "qspush_step is the RTI control period; full SQP goes through qspush_prepare / qspush_solve");
+    if (idx < 1) return fail(QSPUSH_ERR_ARG, "qspush_step: idx is 1-based");
+    if ((flags & QSPUSH_STEP_RESTORE_GUESS) && !s->d_guess) return fail(QSPUSH_ERR_ARG, "qspush_step: no snapshot (qspush_snapshot_guess)");
+    CK(cudaSetDevice(s->device));
+    RET(flush_cost(s));
+    const size_t B = (size_t)s->B;
+    if (!s->d_idx) CK(cudaMalloc(&s->d_idx, sizeof(int)));
+    double* d_x0 = s->d_stage;                                   // staging: x0 [B][4] | u0 [B][2]
+    double* d_u0 = s->d_stage + 4 * (size_t)s->Bp;
+    const cudaMemcpyKind in_kind = mem == QSPUSH_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    CK(cudaMemcpyAsync(d_x0, x0, B * 4 * sizeof(double), in_kind, s->stream));
+    CK(cudaMemcpyAsync(s->d_idx, &idx, sizeof(int), cudaMemcpyHostToDevice, s->stream));   // pageable source: staged before the call returns
+    cudaGraphExec_t& exec = s->step_exec[flags & 3u];
+    if (!exec) {
+        if (!s->order_valid) {                                   // a valid permutation for the first period
+            k_qp_order<<<1, 1024, 0, s->stream>>>(s->dev, s->d_order);
+            CK(cudaGetLastError());
+            s->order_valid = true;
+        }
+        const size_t msm = model_smem_bytes(s->nmodels);
+        cudaGraph_t graph = nullptr;
+        const long long launches0 = s->launches;
+        CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeRelaxed));
+        s->capturing = true;
+        int rc = QSPUSH_OK;
+        do {
+            if (flags & QSPUSH_STEP_RESTORE_GUESS)
+                if (cudaMemcpyAsync(s->dev.u, s->d_guess, (size_t)s->N * 2 * s->Bp * sizeof(double), cudaMemcpyDeviceToDevice, s->stream) != cudaSuccess) { rc = QSPUSH_ERR_CUDA; break; }
+            LoopDev L{};
+            L.traj = s->d_ref_traj; L.off = s->d_ref_off; L.T = s->ref_T;
+            rec_event(s, 4);
+            k_prepare<<<(unsigned)((B + 127) / 128), 128, msm, s->stream>>>(s->dev, ctrl_dev(s), L, s->d_idx, d_x0);
+            rec_event(s, 5);
+            s->launches++;
+            rc = solve_impl(s, true);
+            if (rc != QSPUSH_OK) break;
+            k_step_out<<<(unsigned)((B + 1023) / 1024 + 1), 1024, 0, s->stream>>>(s->dev, d_u0, s->d_istage, s->d_order);
+            s->launches++;
+            if (flags & QSPUSH_STEP_SHIFT) { dim3 grid((unsigned)((B + 127) / 128), 16); k_shift<<<grid, 128, 0, s->stream>>>(s->dev); s->launches++; }
+        } while (0);
+        s->capturing = false;
+        const cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
+        s->step_launches = (int)(s->launches - launches0);
+        s->launches = launches0;
+        if (rc != QSPUSH_OK || ce != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc != QSPUSH_OK ? rc : fail(QSPUSH_ERR_CUDA, "qspush_step: graph capture failed"); }
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { exec = nullptr; return fail(QSPUSH_ERR_CUDA, cudaGetErrorString(ie)); }
+    }
+    CK(cudaGraphLaunch(exec, s->stream));
+    s->launches += s->step_launches;
+    const cudaMemcpyKind out_kind = mem == QSPUSH_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    CK(cudaMemcpyAsync(u0, d_u0, B * 2 * sizeof(double), out_kind, s->stream));
+    CK(cudaMemcpyAsync(status, s->d_istage, B * sizeof(int), out_kind, s->stream));
+    if (mem == QSPUSH_MEM_HOST) CK(cudaStreamSynchronize(s->stream));
     return QSPUSH_OK;
 }
 

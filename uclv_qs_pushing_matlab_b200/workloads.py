@@ -19,6 +19,14 @@ def packaged_tables():
         return json.load(f)
 
 
+def packaged_model(name):
+    """Product-side slider model (C-ABI handle) of one objects_database entry, built from the packaged outline tables."""
+    from .capi import Model
+    from .object_selection import OBJECT_TABLE
+    t = packaged_tables()[name]
+    return Model.from_tables(t["knots"], t["ctrl_xy"], 3, OBJECT_TABLE[name]["mu_sp"], t["c_ellipse"], True)
+
+
 def reference_line(x0, N, dt, speed=0.01):
     """Straight-line reference x_ref = x0.x + speed*t, y_ref = x0.y, theta = s = 0, u_ref = 0 (config 1 / 3)."""
     x0 = np.atleast_2d(x0)
