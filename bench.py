@@ -263,6 +263,7 @@ def run_ours(args):
     B, N = len(wl["x0"]), HORIZON
     gms = [packaged_model(n) for n in names]
     solver = q.Solver(gms, N, DT, B, device=local_rank, qp_tol=QP_TOL, qp_tol_comp=QP_TOL_COMP, problems_per_warp=args.ppw, qp_kernel=args.qp_kernel)
+    solver.order_with_torch = False                              # this file orders the streams itself (synchronize before every timed step)
     stream = torch.cuda.ExternalStream(solver.stream, device=dev)
     if len(names) > 1:
         solver.set_int("object_id", wl["object_id"])
@@ -546,7 +547,7 @@ def single_gpu_extras(q, torch, dev, local_rank, gm, wl, solver, fp64_peak_tf, h
     perm, _ = SHARD.bucket_by_object(w4["object_id"], 1)
     w4 = {k: np.ascontiguousarray(v[perm]) for k, v in w4.items()}
     s4 = q.Solver([packaged_model(n) for n in OBJECT_ORDER], HORIZON, DT, C4_TOTAL, device=local_rank, qp_tol=QP_TOL, qp_tol_comp=QP_TOL_COMP)
-    s4.set_int("object_id", w4["object_id"])
+    s4.set_int("object_id", w4["object_id"]); s4.order_with_torch = False
     traj = np.zeros((HORIZON, 6)); traj[:, 0] = 0.01 * (np.arange(HORIZON) * DT)
     off = np.zeros((C4_TOTAL, 6)); off[:, :2] = w4["x0"][:, :2]
     s4.set_reference_trajectory(traj, off)

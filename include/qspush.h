@@ -100,7 +100,8 @@ typedef enum {
     QSPUSH_COLD = 36      /* 1 = no previous solution (isempty(utraj), NMPC_controller.m:351) */
 } qspush_field;
 
-/* scalar statistics of the last qspush_solve (helper.m:264-269), seconds, CUDA-event timed */
+/* scalar statistics of the last qspush_solve (helper.m:264-269), seconds, CUDA-event timed; in full-SQP mode TIME_LIN
+ * (linearisation + residuals) and TIME_QP (QP + line search) are sums over the SQP iterations, like acados' */
 typedef enum { QSPUSH_TIME_TOT = 0, QSPUSH_TIME_LIN = 1, QSPUSH_TIME_QP = 2, QSPUSH_TIME_PREP = 3 } qspush_stat;
 
 const char* qspush_last_error(void);
@@ -158,7 +159,9 @@ void qspush_solver_free(qspush_solver* s);
 int qspush_solver_set_opts(qspush_solver* s, const qspush_opts* opts);
 int qspush_solver_set_ctrl(qspush_solver* s, const qspush_ctrl* ctrl);
 
-/* stage = -1 addresses all stages of the field at once ([batch][stage][dim]); problems [batch_lo, batch_hi). */
+/* stage = -1 addresses all stages of the field at once ([batch][stage][dim]); problems [batch_lo, batch_hi).
+ * Fields with a single stage (constr_x0, cost_y_ref_e, cost, residuals) ignore `stage`: the reference calls
+ * set('cost_y_ref_e', y, Hp) (NMPC_controller.m:348). */
 int qspush_set(qspush_solver* s, qspush_field f, int stage, int batch_lo, int batch_hi, const double* data, qspush_mem mem);
 int qspush_get(qspush_solver* s, qspush_field f, int stage, int batch_lo, int batch_hi, double* out, qspush_mem mem);
 int qspush_set_int(qspush_solver* s, qspush_field f, int batch_lo, int batch_hi, const int* data, qspush_mem mem);

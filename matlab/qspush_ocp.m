@@ -19,6 +19,9 @@ classdef qspush_ocp < handle
         end
         function set(self, field, value, stage)
             if nargin < 4, stage = -1; end
+            % single-stage fields: the reference passes set('cost_y_ref_e', y, Hp) (NMPC_controller.m:348); the C-ABI ignores the
+            % stage of such fields as well, this keeps older libraries working
+            if any(strcmp(field, {'constr_x0','cost_y_ref_e'})), stage = -1; end
             qspush_mex('set', self.s, self.F.(field), stage, double(value));
         end
         function solve(self), qspush_mex('solve', self.s); end   % the x0 wrap / rollout stay in NMPC_controller.solve

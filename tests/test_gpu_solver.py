@@ -549,6 +549,19 @@ def test_device_resident_closed_loop():
     c.set_reference_trajectory(traj.T)
     out = q.helper.closed_loop_device(p, c, x0s, (steps - 1) * dt, offset=off)
     assert out[0].shape == (B, steps) and np.array_equal(np.stack([out[4], out[5]], -1), np.transpose(r["u_log"], (1, 0, 2))) and out[7].all()
+    # torch CUDA x0: everything is asynchronous on the solver's own (non-blocking) stream; the Solver orders it against torch's
+    # current stream on both sides, so the returned tensors can be consumed by torch ops right away (they were read
+    # from torch.empty buffers before the ~7 * steps kernels had run)
+    import torch
+    c2 = q.NMPC_controller("NMPC", p, dt, N, batch=B, nlp_solver="sqp_rti")
+    c2.create_ocp_solver(); c2.set_delay_comp(0.0)
+    c2.set_reference_trajectory(traj.T)
+    xd = torch.from_numpy(x0s).cuda() * 1.0                       # produced by a torch op on torch's stream
+    od = torch.from_numpy(off).cuda()
+    outd = q.helper.closed_loop_device(p, c2, xd, (steps - 1) * dt, offset=od)
+    un_sum = outd[4].sum()                                        # consumed by a torch op, no explicit synchronisation
+    assert outd[7].all() and torch.equal(outd[4].cpu(), torch.from_numpy(out[4])) and torch.equal(outd[0].cpu(), torch.from_numpy(out[0]))
+    assert abs(float(un_sum) - float(out[4].sum())) < 1e-9
 
 
 @pytest.mark.parametrize("N", [1, 7, 15, 16, 31, 32, 47, 48, 63, 64, 96, 127])

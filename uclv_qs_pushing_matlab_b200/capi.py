@@ -152,7 +152,33 @@ _IFIELDS = {"status": L.STATUS, "sqp_iter": L.SQP_ITER, "qp_iter": L.QP_ITER, "o
 
 
 class Solver:
-    """Batched OCP solver = the acados_ocp replacement (qspush_solver)."""
+    """Batched OCP solver = the acados_ocp replacement (qspush_solver).
+
+    Stream contract.  The solver owns a non-blocking CUDA stream (`Solver.stream`); every call enqueues its work there.
+    Calls with HOST buffers return after their copies have completed.  Calls with torch CUDA tensors are asynchronous;
+    with `order_with_torch = True` (default) every such call makes the solver's stream wait for the work already queued
+    on torch's current stream (the producer of the tensors) and makes torch's current stream wait for the call's work
+    (the consumer), so tensors can be used right away like the results of any torch op.  Set it to False when the caller
+    orders the streams itself (bench.py does, to keep its CUDA-event windows free of extra event traffic)."""
+
+    order_with_torch = True
+
+    class _Ordered:
+        def __init__(self, solver, mem):
+            self.on = solver.order_with_torch and mem == L.MEM_DEVICE and torch is not None
+            self.s = solver
+
+        def __enter__(self):
+            if self.on:
+                dev = torch.device("cuda", self.s.device)
+                self.ext = torch.cuda.ExternalStream(self.s.stream, device=dev)
+                self.ext.wait_stream(torch.cuda.current_stream(dev))
+            return self
+
+        def __exit__(self, *exc):
+            if self.on:
+                torch.cuda.current_stream(torch.device("cuda", self.s.device)).wait_stream(self.ext)
+            return False
 
     def __init__(self, models, N, dt, batch, device=0, **opts):
         self.models = list(models) if isinstance(models, (list, tuple)) else [models]
@@ -208,9 +234,8 @@ class Solver:
         have = keep.numel() if (torch is not None and isinstance(keep, torch.Tensor)) else keep.size
         if have != want:
             raise L.QspushError(f"{field}: expected {want} values, got {have}")
-        L.check(L.lib().qspush_set(self._h, _FIELDS[field], int(stage), lo, hi, ptr, mem))
-        if mem == L.MEM_HOST and not (torch is not None and isinstance(keep, torch.Tensor) and keep.is_pinned()):
-            pass  # pageable host memory: cudaMemcpyAsync has already staged the data
+        with self._Ordered(self, mem):
+            L.check(L.lib().qspush_set(self._h, _FIELDS[field], int(stage), lo, hi, ptr, mem))
         self._keep = keep
 
     def get(self, field, stage=-1, lo=0, hi=None, out=None):
@@ -223,7 +248,8 @@ class Solver:
         if out is None:
             out = np.zeros(shape)
         ptr, mem, keep = _buf(out, writable=True)
-        L.check(L.lib().qspush_get(self._h, _FIELDS[field], int(stage), lo, hi, ptr, mem))
+        with self._Ordered(self, mem):
+            L.check(L.lib().qspush_get(self._h, _FIELDS[field], int(stage), lo, hi, ptr, mem))
         if field == "cost" and isinstance(out, np.ndarray):
             return out.reshape(-1)
         return out
@@ -231,14 +257,16 @@ class Solver:
     def set_int(self, field, data, lo=0, hi=None):
         hi = self.batch if hi is None else hi
         ptr, mem, keep = _buf(data, dtype=np.int32)
-        L.check(L.lib().qspush_set_int(self._h, _IFIELDS[field], lo, hi, ptr, mem))
+        with self._Ordered(self, mem):
+            L.check(L.lib().qspush_set_int(self._h, _IFIELDS[field], lo, hi, ptr, mem))
 
     def get_int(self, field, lo=0, hi=None, out=None):
         hi = self.batch if hi is None else hi
         if out is None:
             out = np.zeros(hi - lo, dtype=np.int32)
         ptr, mem, keep = _buf(out, dtype=np.int32, writable=True)
-        L.check(L.lib().qspush_get_int(self._h, _IFIELDS[field], lo, hi, ptr, mem))
+        with self._Ordered(self, mem):
+            L.check(L.lib().qspush_get_int(self._h, _IFIELDS[field], lo, hi, ptr, mem))
         return out
 
     def prepare(self):
@@ -256,7 +284,8 @@ class Solver:
         pu, mem_u, ku = _buf(u)
         if mem != mem_u:
             raise L.QspushError("x and u must live in the same memory space")
-        L.check(L.lib().qspush_plant_step(self._h, px, pu, mem))
+        with self._Ordered(self, mem):
+            L.check(L.lib().qspush_plant_step(self._h, px, pu, mem))
         return x
 
     def closed_loop(self, traj, x, steps, offset=None, idx0=1, noise_sigma=(0.0, 0.0, 0.0, 0.0), seed=0, t_dist=0,
@@ -295,7 +324,8 @@ class Solver:
         lo.amplitude_dist = float(amplitude_dist); lo.xwidth = float(xwidth)
         for i in range(4):
             lo.noise_sigma[i] = float(noise_sigma[i])
-        L.check(L.lib().qspush_closed_loop(self._h, pt, int(T), po, px, int(steps), C.byref(lo), plx, plu, pls, mem))
+        with self._Ordered(self, mem):
+            L.check(L.lib().qspush_closed_loop(self._h, pt, int(T), po, px, int(steps), C.byref(lo), plx, plu, pls, mem))
         return dict(x=x, x_log=lx, u_log=lu, status_log=ls)
 
     def set_reference_trajectory(self, traj, offset=None):
@@ -311,7 +341,8 @@ class Solver:
                 raise L.QspushError("offset must be (batch, 6)")
         if len(kt.shape) != 2 or kt.shape[1] != 6:
             raise L.QspushError("traj must be (T, 6)")
-        L.check(L.lib().qspush_set_reference_trajectory(self._h, pt, int(kt.shape[0]), po, mem))
+        with self._Ordered(self, mem):
+            L.check(L.lib().qspush_set_reference_trajectory(self._h, pt, int(kt.shape[0]), po, mem))
 
     def set_reference_window(self, idx):
         """Reference window of control period idx (1-based) into cost_y_ref / cost_y_ref_e of every stage
@@ -333,7 +364,8 @@ class Solver:
         if mem_u != mem or mem_s != mem:
             raise L.QspushError("x0, u0 and status must live in the same memory space")
         flags = (L.STEP_SHIFT if shift else 0) | (L.STEP_RESTORE_GUESS if restore_guess else 0)
-        L.check(L.lib().qspush_step(self._h, px, int(idx), flags, pu, ps, mem))
+        with self._Ordered(self, mem):
+            L.check(L.lib().qspush_step(self._h, px, int(idx), flags, pu, ps, mem))
         return u0, status
 
     def snapshot_guess(self):

@@ -53,6 +53,9 @@ struct qspush_solver {
     std::vector<double> W, We;     // host copies: N x 36 (y order, column-major), 16
     bool cost_dirty = true;
     cudaEvent_t ev[6];
+    cudaEvent_t evs[4] = {nullptr, nullptr, nullptr, nullptr};   // full SQP: per-iteration phase events (linearise+residuals, QP+line search)
+    double acc_lin = 0.0, acc_qp = 0.0;                          // ... accumulated over the iterations of the last solve (seconds)
+    bool acc_valid = false;
     double t_tot = 0, t_lin = 0, t_qp = 0, t_prep = 0;
     long long launches = 0;
     bool smem_attr_set = false;
@@ -309,6 +312,7 @@ int qspush_solver_create(const qspush_model* const* models, int nmodels, int N, 
     qspush_ctrl_default(&s->ctrl);
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto& e : s->ev) CK(cudaEventCreate(&e));
+    for (auto& e : s->evs) CK(cudaEventCreate(&e));
     CK(cudaMallocHost(&s->h_ndone, sizeof(int)));
     const size_t Bp = (size_t)s->Bp;
     // rows of every slab
@@ -384,6 +388,7 @@ void qspush_solver_free(qspush_solver* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : s->evs) if (e) cudaEventDestroy(e);
     if (s->arena) cudaFree(s->arena);
     if (s->d_ref_traj) cudaFree(s->d_ref_traj);
     if (s->d_ref_off) cudaFree(s->d_ref_off);
@@ -476,6 +481,7 @@ int qspush_set(qspush_solver* s, qspush_field f, int stage, int lo, int hi, cons
     FieldInfo fi;
     if (!field_info(s, f, fi) || !fi.settable) return fail(QSPUSH_ERR_ARG, "field cannot be set");
     if (lo < 0 || hi > s->B || lo >= hi) return fail(QSPUSH_ERR_ARG, "batch range out of bounds");
+    if (fi.nst == 1) stage = -1;          // single-stage fields: the reference passes set('cost_y_ref_e', y, Hp) (NMPC_controller.m:348)
     if (stage < -1 || stage >= fi.nst) return fail(QSPUSH_ERR_ARG, "stage out of range");
     const int nb = hi - lo;
     const int R = (stage < 0) ? fi.nst * fi.dim : fi.dim;
@@ -506,6 +512,7 @@ int qspush_get(qspush_solver* s, qspush_field f, int stage, int lo, int hi, doub
     FieldInfo fi;
     if (!field_info(s, f, fi)) return fail(QSPUSH_ERR_ARG, "unknown field");
     if (lo < 0 || hi > s->B || lo >= hi) return fail(QSPUSH_ERR_ARG, "batch range out of bounds");
+    if (fi.nst == 1) stage = -1;          // single-stage fields: the reference passes set('cost_y_ref_e', y, Hp) (NMPC_controller.m:348)
     if (stage < -1 || stage >= fi.nst) return fail(QSPUSH_ERR_ARG, "stage out of range");
     const int nb = hi - lo;
     const int R = (stage < 0) ? fi.nst * fi.dim : fi.dim;
@@ -686,6 +693,7 @@ static int solve_impl(qspush_solver* s, bool order_ready) {
     const unsigned lin_blocks = (unsigned)((nlin + 127) / 128);
     CK(rec_event(s, 0));
     if (o.mode == QSPUSH_MODE_RTI) {
+        s->acc_valid = false;
         SolverDev D = s->dev; D.done = nullptr;
         apply_variant(s, D);
         k_linearise<<<lin_blocks, 128, smem, s->stream>>>(D);
@@ -704,15 +712,27 @@ static int solve_impl(qspush_solver* s, bool order_ready) {
     CK(cudaMemsetAsync(D.done, 0, s->Bp * sizeof(int), s->stream));
     CK(cudaMemsetAsync(D.qp_iter, 0, s->Bp * sizeof(int), s->stream));
     CK(cudaMemsetAsync(D.ndone, 0, sizeof(int), s->stream));
+    // time_lin / time_qp_sol of the reference's stat print (helper.m:264-269) are sums over the SQP iterations: event pairs per
+    // iteration, read after the host synchronisation the loop needs anyway (convergence count)
+    s->acc_lin = 0.0; s->acc_qp = 0.0; s->acc_valid = true;
+    bool qp_pending = false;
     for (int it = 0; it <= o.max_sqp_iter; ++it) {
+        CK(cudaEventRecord(s->evs[0], s->stream));
         k_linearise<<<lin_blocks, 128, smem, s->stream>>>(D);
         k_nlp_res<<<(unsigned)((s->B + 31) / 32), dim3(32, LS_CHUNKS), 0, s->stream>>>(D, so, it);
+        CK(cudaEventRecord(s->evs[1], s->stream));
         s->launches += 2;
         CK(cudaMemcpyAsync(s->h_ndone, D.ndone, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
+        { float ms = 0.f; if (cudaEventElapsedTime(&ms, s->evs[0], s->evs[1]) == cudaSuccess) s->acc_lin += 1e-3 * ms;
+          if (qp_pending && cudaEventElapsedTime(&ms, s->evs[2], s->evs[3]) == cudaSuccess) s->acc_qp += 1e-3 * ms;
+          qp_pending = false; }
         if (*s->h_ndone >= s->B || it == o.max_sqp_iter) break;
+        CK(cudaEventRecord(s->evs[2], s->stream));
         RET(launch_qp(s, D, io, ppw, 0));
         k_linesearch<<<(unsigned)((s->B + 31) / 32), dim3(32, LS_CHUNKS), smem, s->stream>>>(D, so, it);
+        CK(cudaEventRecord(s->evs[3], s->stream));
+        qp_pending = true;
         s->launches += 2;
     }
     CK(rec_event(s, 1));
@@ -963,8 +983,8 @@ int qspush_get_stat(qspush_solver* s, qspush_stat which, double* out) {
     cudaError_t e = cudaSuccess;
     switch (which) {
         case QSPUSH_TIME_TOT: e = cudaEventElapsedTime(&ms, s->ev[0], s->ev[3]); break;
-        case QSPUSH_TIME_LIN: e = cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]); break;
-        case QSPUSH_TIME_QP: e = cudaEventElapsedTime(&ms, s->ev[1], s->ev[2]); break;
+        case QSPUSH_TIME_LIN: if (s->acc_valid) { *out = s->acc_lin; return QSPUSH_OK; } e = cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]); break;
+        case QSPUSH_TIME_QP: if (s->acc_valid) { *out = s->acc_qp; return QSPUSH_OK; } e = cudaEventElapsedTime(&ms, s->ev[1], s->ev[2]); break;
         case QSPUSH_TIME_PREP: e = cudaEventElapsedTime(&ms, s->ev[4], s->ev[5]); break;
         default: return fail(QSPUSH_ERR_ARG, "unknown stat");
     }

@@ -135,12 +135,18 @@ class helper:
                     xi[b, 3] = s0_spline
             if sim_noise:                                           # :240-242
                 xi += rng.standard_normal((B, 4)) * np.array([1e-5, 1e-5, 1e-3, 1e-4])
-            xk_sim = np.stack([controller.delay_buffer_sim(plant, xi[b]) for b in range(B)]) if controller.delay_buff_comp else xi.copy()
+            if controller.delay_buff_comp:                          # every problem is rolled forward with ITS OWN past inputs
+                xk_sim = controller.delay_buffer_sim(plant, xi) if controller.u_buff_contr.ndim == 3 else controller.delay_buffer_sim(plant, xi[0])[None]
+            else:
+                xk_sim = xi.copy()
             x_sim[:, i - 1] = xk_sim
             ui = controller.solve(xk_sim if batched else xk_sim[0], i + controller.delay_buff_comp)   # :248
             u[:, i - 1] = np.asarray(ui).reshape(B, 2)
-            if controller.delay_buff_comp:
-                controller.u_buff_contr = np.concatenate([u[0, i - 1].reshape(2, 1), controller.u_buff_contr[:, :-1]], axis=1)  # :252
+            if controller.delay_buff_comp:                          # :252
+                if controller.u_buff_contr.ndim == 3:
+                    controller.u_buff_contr = np.concatenate([u[:, i - 1][:, :, None], controller.u_buff_contr[:, :, :-1]], axis=2)
+                else:
+                    controller.u_buff_contr = np.concatenate([u[0, i - 1].reshape(2, 1), controller.u_buff_contr[:, :-1]], axis=1)
             status = np.atleast_1d(controller.ocp_solver.get("status"))
             found_sol[:, i - 1] = status == 0                        # :253-260
             if print_:                                              # :263-273

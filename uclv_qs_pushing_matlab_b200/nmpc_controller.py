@@ -70,13 +70,15 @@ class NMPC_controller:
     def set_delay_comp(self, delay):
         self.delay_compensation = delay
         self.delay_buff_comp = int(math.ceil(self.delay_compensation / self.sample_time))
-        self.u_buff_contr = np.zeros((self.sym_model["nu"], self.delay_buff_comp))
+        # (nu, d) like the reference for one instance; one buffer per problem, (batch, nu, d), for a batch
+        shape = (self.sym_model["nu"], self.delay_buff_comp)
+        self.u_buff_contr = np.zeros(shape if getattr(self, "batch", 1) == 1 else (self.batch, *shape))
 
-    # :112-120
+    # :112-120 (x: (4,) with a (nu, d) buffer, or (batch, 4) with a (batch, nu, d) buffer)
     def delay_buffer_sim(self, plant, x):
         xk_sim = np.array(x, dtype=np.float64)
         for k in range(1, self.delay_buff_comp + 1):
-            x_dot_sim = plant.evalModelVariableShape(xk_sim, self.u_buff_contr[:, -k])
+            x_dot_sim = plant.evalModelVariableShape(xk_sim, self.u_buff_contr[..., -k])
             xk_sim = xk_sim + self.sample_time * x_dot_sim
         return xk_sim
 
