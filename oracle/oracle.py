@@ -195,7 +195,14 @@ DEFAULT_OPTS = dict(
     qp_max_iter=50, qp_tol=1e-11, qp_mu0=0.1, qp_thr=1e-3, qp_tau=0.9995,
     alpha_min=0.05, alpha_reduction=0.7, eps_sufficient_descent=1e-4, globalization=1, local_spline=1,
     qp_tol_comp=1e-18, qp_t_min=1e-12, qp_gamma_f=0.05, qp_stall=10,
+    # recalled acados semantics as switches (qs_oracle.hpp); defaults = what the restatement believes
+    sem_cost_scale=0, sem_h0_s_row=0, sem_full_step_dual=0, sem_merit_weights=0, sem_armijo=0, sem_erk_steps=1,
+    sem_qp_maxiter_fails=0, sem_mod_strict=0,
 )
+SEMANTIC_SWITCHES = {          # name -> the alternatives to try when acados golden vectors disagree
+    "sem_cost_scale": (1, 2), "sem_h0_s_row": (1,), "sem_full_step_dual": (1,), "sem_merit_weights": (1, 2), "sem_armijo": (1,),
+    "sem_erk_steps": (2, 4), "sem_qp_maxiter_fails": (1,), "sem_mod_strict": (1,),
+}
 _OPT_ORDER = list(DEFAULT_OPTS.keys())
 
 

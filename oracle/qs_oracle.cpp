@@ -256,8 +256,9 @@ static F matlab_mod_t(F x, F y, F eps) {
     return r;
 }
 static double matlab_mod(const Model& m, double s) {
-    if (m.single_quirk) return (double)matlab_mod_t<float>((float)s, (float)m.b, 1.1920929e-7f);
-    return matlab_mod_t<double>(s, m.b, 2.220446049250313e-16);
+    double r = m.single_quirk ? (double)matlab_mod_t<float>((float)s, (float)m.b, 1.1920929e-7f) : matlab_mod_t<double>(s, m.b, 2.220446049250313e-16);
+    if (m.mod_strict && r >= m.b) r -= m.b;                 // sem_mod_strict: the variant that keeps the result inside [0, b)
+    return r;
 }
 
 // =========================================================================================
@@ -389,6 +390,27 @@ static void erk4_sens(const Model& m, const double x[4], const double u[2], doub
     for (int i = 0; i < 8; ++i) B[i] = Xn[20 + i];
 }
 
+// num_steps ERK4 steps of dt / num_steps each with chained sensitivities (sim_method_num_steps; 1 in the reference's configuration)
+static void erk4_sens_steps(const Model& m, const double x[4], const double u[2], double dt, int steps, bool local,
+                            double Phi[4], double A[16], double B[8]) {
+    if (steps <= 1) { erk4_sens(m, x, u, dt, local, Phi, A, B); return; }
+    double xc[4] = {x[0], x[1], x[2], x[3]}, Ac[16], Bc[8];
+    for (int i = 0; i < 16; ++i) Ac[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    for (int i = 0; i < 8; ++i) Bc[i] = 0.0;
+    for (int st = 0; st < steps; ++st) {
+        double P1[4], A1[16], B1[8], An[16], Bn[8];
+        erk4_sens(m, xc, u, dt / steps, local, P1, A1, B1);
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double a = 0; for (int l = 0; l < 4; ++l) a += A1[4 * i + l] * Ac[4 * l + j]; An[4 * i + j] = a; }
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 2; ++j) { double a = B1[2 * i + j]; for (int l = 0; l < 4; ++l) a += A1[4 * i + l] * Bc[2 * l + j]; Bn[2 * i + j] = a; }
+        for (int i = 0; i < 16; ++i) Ac[i] = An[i];
+        for (int i = 0; i < 8; ++i) Bc[i] = Bn[i];
+        for (int i = 0; i < 4; ++i) xc[i] = P1[i];
+    }
+    for (int i = 0; i < 4; ++i) Phi[i] = xc[i];
+    for (int i = 0; i < 16; ++i) A[i] = Ac[i];
+    for (int i = 0; i < 8; ++i) B[i] = Bc[i];
+}
+
 // ERK4 without sensitivities (merit-function evaluations of the line search)
 static void erk4(const Model& m, const double x[4], const double u[2], double dt, bool local, double Phi[4]) {
     double k1[4], k2[4], k3[4], k4[4], xs[4];
@@ -422,6 +444,7 @@ struct QP {
     std::vector<StageQP> st;
     double QN[4][4], qN[4];
     double dx0[4];
+    bool infeasible = false;                 // sem_h0_s_row: the constant s row of stage 0 violates its bound
 };
 struct QPSol {
     std::vector<double> du, dx, pi, lam, t;   // du N*2, dx (N+1)*4, pi N*4 (pi_{k+1}), lam/t N*6 [lower;upper]
@@ -710,13 +733,15 @@ static double h_of(const Ocp& ocp, const Traj& tr, int k, int c, bool local, dou
 }
 
 static void linearise(const Ocp& ocp, const RefData& rd, const Traj& tr, bool local, QP& qp) {
+    qp.infeasible = false;
     const int N = ocp.N; const double dt = ocp.dt;
+    const double cs = (ocp.opts.sem_cost_scale == 1) ? 1.0 : dt, ce = (ocp.opts.sem_cost_scale == 2) ? dt : 1.0;   // stage / terminal cost scaling
     qp.N = N; qp.st.resize(N);
     for (int k = 0; k < N; ++k) {
         StageQP& s = qp.st[k];
         const double* xk = &tr.x[(size_t)k * 4]; const double* uk = &tr.u[(size_t)k * 2];
         double Phi[4], A[16], B[8];
-        erk4_sens(*ocp.model, xk, uk, dt, local, Phi, A, B);
+        erk4_sens_steps(*ocp.model, xk, uk, dt, ocp.opts.sem_erk_steps, local, Phi, A, B);
         for (int i = 0; i < 4; ++i) {
             for (int j = 0; j < 4; ++j) s.A[i][j] = A[4 * i + j];
             s.B[i][0] = B[2 * i]; s.B[i][1] = B[2 * i + 1];
@@ -732,8 +757,8 @@ static void linearise(const Ocp& ocp, const RefData& rd, const Traj& tr, bool lo
         for (int i = 0; i < 6; ++i) {
             double a = 0.0;
             for (int j = 0; j < 6; ++j) {
-                s.H[i][j] = dt * W[perm(i) + 6 * perm(j)];
-                a += dt * W[perm(i) + 6 * j] * r[j];
+                s.H[i][j] = cs * W[perm(i) + 6 * perm(j)];
+                a += cs * W[perm(i) + 6 * j] * r[j];
             }
             s.g[i] = a;
         }
@@ -741,14 +766,18 @@ static void linearise(const Ocp& ocp, const RefData& rd, const Traj& tr, bool lo
             double h = h_of(ocp, tr, k, c, local, &s.beta[c]);
             s.dl[c] = ocp.lh[c] - h; s.du[c] = ocp.uh[c] - h;
             s.on[c] = ocp.h_variant ? true : !(k == 0 && c == 0);
+            if (ocp.opts.sem_h0_s_row && !ocp.h_variant && k == 0 && c == 0) {     // the row is a constant (x_0 is fixed): it can only be (in)feasible
+                const double v = rd.x0bar[3];
+                if (v < ocp.lh[0] - 1e-12 || v > ocp.uh[0] + 1e-12) qp.infeasible = true;
+            }
             s.ci[c] = ocp.h_variant ? (c == 0 ? 0 : 1) : CIDX[c];
         }
     }
     for (int i = 0; i < 4; ++i) {
         double a = 0.0;
         for (int j = 0; j < 4; ++j) {
-            qp.QN[i][j] = ocp.We[i + 4 * j];
-            a += ocp.We[i + 4 * j] * (tr.x[(size_t)N * 4 + j] - rd.yref_e[j]);
+            qp.QN[i][j] = ce * ocp.We[i + 4 * j];
+            a += ce * ocp.We[i + 4 * j] * (tr.x[(size_t)N * 4 + j] - rd.yref_e[j]);
         }
         qp.qN[i] = a;
         qp.dx0[i] = rd.x0bar[i] - tr.x[i];
@@ -765,12 +794,12 @@ static double eval_cost(const Ocp& ocp, const RefData& rd, const Traj& tr) {
         for (int i = 0; i < 2; ++i) r[4 + i] = tr.u[(size_t)k * 2 + i] - rd.yref[(size_t)k * 6 + 4 + i];
         double q = 0.0;
         for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) q += r[i] * W[i + 6 * j] * r[j];
-        c += 0.5 * ocp.dt * q;
+        c += 0.5 * ((ocp.opts.sem_cost_scale == 1) ? 1.0 : ocp.dt) * q;
     }
     double q = 0.0;
     for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j)
         q += (tr.x[(size_t)N * 4 + i] - rd.yref_e[i]) * ocp.We[i + 4 * j] * (tr.x[(size_t)N * 4 + j] - rd.yref_e[j]);
-    return c + 0.5 * q;
+    return c + 0.5 * ((ocp.opts.sem_cost_scale == 2) ? ocp.dt : 1.0) * q;
 }
 
 // =========================================================================================
@@ -780,8 +809,9 @@ static void apply_step(const Ocp& ocp, const QPSol& qs, double alpha, Traj& tr) 
     const int N = ocp.N;
     for (size_t i = 0; i < (size_t)(N + 1) * 4; ++i) tr.x[i] += alpha * qs.dx[i];
     for (size_t i = 0; i < (size_t)N * 2; ++i) tr.u[i] += alpha * qs.du[i];
-    for (size_t i = 0; i < (size_t)N * 4; ++i) tr.pi[i] = (1.0 - alpha) * tr.pi[i] + alpha * qs.pi[i];
-    for (size_t i = 0; i < (size_t)N * 6; ++i) tr.lam[i] = (1.0 - alpha) * tr.lam[i] + alpha * qs.lam[i];
+    const double ad = ocp.opts.sem_full_step_dual ? 1.0 : alpha;
+    for (size_t i = 0; i < (size_t)N * 4; ++i) tr.pi[i] = (1.0 - ad) * tr.pi[i] + ad * qs.pi[i];
+    for (size_t i = 0; i < (size_t)N * 6; ++i) tr.lam[i] = (1.0 - ad) * tr.lam[i] + ad * qs.lam[i];
 }
 
 // One real-time iteration: linearise at (x,u), solve the QP, take the full step,
@@ -792,8 +822,8 @@ static void rti_step(const Ocp& ocp, const RefData& rd, Traj& tr, bool local, So
     qp_solve_ipm(qp, ocp.opts, qs);
     apply_step(ocp, qs, 1.0, tr);
     st.sqp_iter = 1; st.qp_iter = qs.iters;
-    st.status = (qs.status == 0) ? 0 : (qs.status == 1 ? 0 : 4);   // QP max-iter is tolerated (A2.4)
-    if (qs.status == 1) st.status = 0;
+    st.status = (qs.status == 0) ? 0 : (qs.status == 1 ? (ocp.opts.sem_qp_maxiter_fails ? 4 : 0) : 4);   // QP max-iter is tolerated (A2.4)
+    if (qp.infeasible) st.status = 4;
     for (size_t i = 0; i < tr.u.size(); ++i) if (!(tr.u[i] == tr.u[i])) st.status = 1;
     st.cost = eval_cost(ocp, rd, tr);
     for (int i = 0; i < 4; ++i) st.res[i] = qs.res[i];
@@ -835,7 +865,8 @@ static double merit(const Ocp& ocp, const RefData& rd, const Traj& tr, bool loca
     for (int i = 0; i < 4; ++i) mval += wx0[i] * std::fabs(rd.x0bar[i] - tr.x[i]);
     for (int k = 0; k < N; ++k) {
         double Phi[4];
-        erk4(*ocp.model, &tr.x[(size_t)k * 4], &tr.u[(size_t)k * 2], ocp.dt, local, Phi);
+        if (ocp.opts.sem_erk_steps <= 1) erk4(*ocp.model, &tr.x[(size_t)k * 4], &tr.u[(size_t)k * 2], ocp.dt, local, Phi);
+        else { double A_[16], B_[8]; erk4_sens_steps(*ocp.model, &tr.x[(size_t)k * 4], &tr.u[(size_t)k * 2], ocp.dt, ocp.opts.sem_erk_steps, local, Phi, A_, B_); }
         for (int i = 0; i < 4; ++i) mval += wpi[(size_t)k * 4 + i] * std::fabs(Phi[i] - tr.x[(size_t)(k + 1) * 4 + i]);
         for (int c = 0; c < 3; ++c) {
             if (ocp.h_variant == 0 && k == 0 && c == 0) continue;
@@ -864,12 +895,13 @@ static void sqp_solve(const Ocp& ocp, const RefData& rd, Traj& tr, bool local, S
         if (it >= o.max_sqp_iter) { st.status = 2; break; }
         qp_solve_ipm(qp, o, qs);
         st.qp_iter += qs.iters;
-        if (qs.status == 2) { st.status = 4; ++it; break; }
+        if (qs.status == 2 || qp.infeasible || (qs.status == 1 && o.sem_qp_maxiter_fails)) { st.status = 4; ++it; break; }
         double alpha = 1.0;
         if (o.globalization == 1) {
             // merit weights: |multipliers_qp| at the first iteration, then max(|m|, (w+|m|)/2)
-            for (size_t i = 0; i < wpi.size(); ++i) { double a = std::fabs(qs.pi[i]); wpi[i] = (it == 0) ? a : std::max(a, 0.5 * (wpi[i] + a)); }
-            for (size_t i = 0; i < wlam.size(); ++i) { double a = std::fabs(qs.lam[i]); wlam[i] = (it == 0) ? a : std::max(a, 0.5 * (wlam[i] + a)); }
+            auto wupd = [&](double w, double a) { return (it == 0 || o.sem_merit_weights == 1) ? a : (o.sem_merit_weights == 2 ? std::max(w, a) : std::max(a, 0.5 * (w + a))); };
+            for (size_t i = 0; i < wpi.size(); ++i) wpi[i] = wupd(wpi[i], std::fabs(qs.pi[i]));
+            for (size_t i = 0; i < wlam.size(); ++i) wlam[i] = wupd(wlam[i], std::fabs(qs.lam[i]));
             // multiplier of the x0 equality: costate at stage 0 (from stage-0 stationarity)
             {
                 const StageQP& s = qp.st[0];
@@ -879,7 +911,7 @@ static void sqp_solve(const Ocp& ocp, const RefData& rd, Traj& tr, bool local, S
                     for (int l = 0; l < 4; ++l) a += s.A[l][j] * qs.pi[l];
                     if (j == 3) for (int c = 0; c < 3; ++c) a += s.beta[c] * (qs.lam[3 + c] - qs.lam[c]);
                     a = std::fabs(a);
-                    wx0[j] = (it == 0) ? a : std::max(a, 0.5 * (wx0[j] + a));
+                    wx0[j] = wupd(wx0[j], a);
                 }
             }
             const double m0 = merit(ocp, rd, tr, local, wpi, wlam, wx0);
@@ -906,7 +938,7 @@ static void sqp_solve(const Ocp& ocp, const RefData& rd, Traj& tr, bool local, S
                 for (size_t i = 0; i < trial.x.size(); ++i) trial.x[i] += alpha * qs.dx[i];
                 for (size_t i = 0; i < trial.u.size(); ++i) trial.u[i] += alpha * qs.du[i];
                 const double m1 = merit(ocp, rd, trial, local, wpi, wlam, wx0);
-                if (m1 <= m0 + o.eps_sufficient_descent * alpha * dmerit) break;
+                if (o.sem_armijo ? (m1 < m0) : (m1 <= m0 + o.eps_sufficient_descent * alpha * dmerit)) break;
                 if (!(m1 == m1) && alpha <= o.alpha_min) break;
                 alpha *= o.alpha_reduction;
                 if (alpha < o.alpha_min) { alpha = o.alpha_min; break; }
@@ -1146,7 +1178,8 @@ void orc_ocp_set_bounds(void* o_, const double* lh, const double* uh) {
 }
 // opts: [max_sqp_iter, tol_stat, tol_eq, tol_ineq, tol_comp, qp_max_iter, qp_tol, qp_mu0, qp_thr, qp_tau,
 //        alpha_min, alpha_reduction, eps_sufficient_descent, globalization, local_spline,
-//        qp_tol_comp, qp_t_min, qp_gamma_f, qp_stall]
+//        qp_tol_comp, qp_t_min, qp_gamma_f, qp_stall,
+//        sem_cost_scale, sem_h0_s_row, sem_full_step_dual, sem_merit_weights, sem_armijo, sem_erk_steps, sem_qp_maxiter_fails, sem_mod_strict]
 void orc_ocp_set_opts(void* o_, const double* v) {
     OrcOcp* o = (OrcOcp*)o_; OcpOpts& p = o->ocp.opts;
     p.max_sqp_iter = (int)v[0]; p.tol_stat = v[1]; p.tol_eq = v[2]; p.tol_ineq = v[3]; p.tol_comp = v[4];
@@ -1154,6 +1187,9 @@ void orc_ocp_set_opts(void* o_, const double* v) {
     p.alpha_min = v[10]; p.alpha_reduction = v[11]; p.eps_sufficient_descent = v[12]; p.globalization = (int)v[13];
     o->local = v[14] != 0.0;
     p.qp_tol_comp = v[15]; p.qp_t_min = v[16]; p.qp_gamma_f = v[17]; p.qp_stall = (int)v[18];
+    p.sem_cost_scale = (int)v[19]; p.sem_h0_s_row = (int)v[20]; p.sem_full_step_dual = (int)v[21]; p.sem_merit_weights = (int)v[22];
+    p.sem_armijo = (int)v[23]; p.sem_erk_steps = (int)v[24]; p.sem_qp_maxiter_fails = (int)v[25]; p.sem_mod_strict = (int)v[26];
+    const_cast<Model*>(o->ocp.model)->mod_strict = p.sem_mod_strict != 0;
 }
 // h_variant 1: h = [u_n; u_t - v_bound(s); u_t + v_bound(s)]; the caller sets the matching lh / uh
 // ([u_n_lb, 2 u_t_lb, 0] / [u_n_ub, 0, 2 u_t_ub], NMPC_controller.m:247-248) with orc_ocp_set_bounds.

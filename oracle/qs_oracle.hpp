@@ -117,6 +117,7 @@ struct Model {
     double mu_sp = 0.0;        // slider/pusher friction               (object_selection.m)
     double c_ellipse = 0.0;    // tau_max / f_max                      (PusherSliderModel.m:53-55)
     bool single_quirk = true;  // reproduce MATLAB `single` arithmetic inherited from pcread
+    bool mod_strict = false;   // OcpOpts::sem_mod_strict
     // knot difference as the reference computes it (single - single when S is single)
     double kd(int i_hi, int i_lo) const {   // 1-based indices like the reference
         if (single_quirk) return (double)((float)S[i_hi - 1] - (float)S[i_lo - 1]);
@@ -143,6 +144,17 @@ struct OcpOpts {
     double qp_t_min = 1e-12;           // slack floor: pairs with t <= 4 t_min count as converged, their centering target is lam * t_min (bounds lam / t)
     double qp_gamma_f = 0.05;          // step to the boundary: blocking pair keeps gamma_f * (predicted mu reduction) of its value
     int    qp_stall = 10;              // iterations without halving the normalised residual before a point below 1e-6 is accepted
+    // ---- RECALLED acados v0.2.1 semantics as switches (none of it could be run here).  The defaults are
+    // what the restatement believes; when golden vectors from a real acados run (tools/acados_golden.m) disagree,
+    // tests/test_acados_golden.py flips these one at a time and reports which flip removes the mismatch.
+    int    sem_cost_scale = 0;         // 0: stage cost x dt, terminal unscaled (A2.2); 1: nothing scaled; 2: stage and terminal x dt
+    int    sem_h0_s_row = 0;           // 0: the s row of h is void at stage 0 (x_0 is fixed); 1: kept -> a violated bound makes the QP infeasible (status 4)
+    int    sem_full_step_dual = 0;     // 0: pi, lam <- (1 - alpha) old + alpha qp (A2.4); 1: multipliers replaced by the QP's whatever alpha
+    int    sem_merit_weights = 0;      // 0: w <- |m| first, then max(|m|, (w + |m|) / 2) (A2.5); 1: w <- |m| every iteration; 2: w <- max(w, |m|)
+    int    sem_armijo = 0;             // 0: m1 <= m0 + eps alpha dmerit (line_search_use_sufficient_descent = 1); 1: plain decrease m1 < m0
+    int    sem_erk_steps = 1;          // ERK4 steps per shooting interval (sim_method_num_steps, A2.1)
+    int    sem_qp_maxiter_fails = 0;   // 0: a QP that hits its iteration limit is accepted (A2.4); 1: it ends the solve with status 4
+    int    sem_mod_strict = 0;         // 0: MATLAB's mod as its builtin computes it (may return b); 1: result forced into [0, b)
 };
 
 struct Ocp {
