@@ -460,7 +460,11 @@ struct RiccatiFactor {
 };
 
 // Backward matrix recursion with the barrier-augmented Hessian diag term Hb (N x 6).
-static bool riccati_factor(const QP& qp, const std::vector<double>& Hb, const std::vector<double>& Hx, RiccatiFactor& F) {
+// Division by a Cholesky pivot: a dropped pivot (stored as 0) zeroes the quotient — BLASFEO's dpotrf sets the inverse
+// diagonal of a non-positive pivot to 0 instead of failing [BLASFEO-RECALL], so HPIPM's Riccati never aborts on one.
+static inline double pdiv(double a, double l) { return l > 0.0 ? a / l : 0.0; }
+
+static bool riccati_factor(const QP& qp, const std::vector<double>& Hb, const std::vector<double>& Hx, RiccatiFactor& F, bool pivot_fails) {
     const int N = qp.N;
     F.K.assign((size_t)N * 8, 0.0); F.Linv.assign((size_t)N * 3, 0.0); F.P.assign((size_t)(N + 1) * 16, 0.0);
     for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) F.P[(size_t)N * 16 + 4 * i + j] = qp.QN[i][j];
@@ -478,20 +482,21 @@ static bool riccati_factor(const QP& qp, const std::vector<double>& Hb, const st
         for (int i = 0; i < 6; ++i) M[i][i] += Hb[(size_t)k * 6 + i];
         M[5][1] += Hx[k]; M[1][5] += Hx[k];                  // barrier cross term (s, u_t) of the coupled rows
         // Cholesky of the 2x2 input block
-        double l00 = std::sqrt(M[0][0]);
-        if (!(l00 > 0.0)) return false;
-        double l10 = M[1][0] / l00;
+        if (!(M[0][0] == M[0][0]) || !(M[1][1] == M[1][1]) || !(M[1][0] == M[1][0])) return false;    // NaN: no factorisation
+        double l00 = M[0][0] > 0.0 ? std::sqrt(M[0][0]) : 0.0;
+        if (pivot_fails && !(l00 > 0.0)) return false;
+        double l10 = pdiv(M[1][0], l00);
         double d11 = M[1][1] - l10 * l10;
-        if (!(d11 > 0.0)) return false;
-        double l11 = std::sqrt(d11);
+        if (pivot_fails && !(d11 > 0.0)) return false;
+        double l11 = d11 > 0.0 ? std::sqrt(d11) : 0.0;
         F.Linv[(size_t)k * 3 + 0] = l00; F.Linv[(size_t)k * 3 + 1] = l10; F.Linv[(size_t)k * 3 + 2] = l11;
         // K = Muu^{-1} Mux  (2x4)
         double* K = &F.K[(size_t)k * 8];
         for (int j = 0; j < 4; ++j) {
-            double y0 = M[0][2 + j] / l00;
-            double y1 = (M[1][2 + j] - l10 * y0) / l11;
-            double k1 = y1 / l11;
-            double k0 = (y0 - l10 * k1) / l00;
+            double y0 = pdiv(M[0][2 + j], l00);
+            double y1 = pdiv(M[1][2 + j] - l10 * y0, l11);
+            double k1 = pdiv(y1, l11);
+            double k0 = pdiv(y0 - l10 * k1, l00);
             K[j] = k0; K[4 + j] = k1;
         }
         double* Pk = &F.P[(size_t)k * 16];
@@ -522,8 +527,8 @@ static void riccati_solve(const QP& qp, const std::vector<double>& Hb, const Ric
         for (int j = 0; j < 2; ++j) { double a = rg[(size_t)k * 6 + j]; for (int l = 0; l < 4; ++l) a += s.B[l][j] * w[l]; mvec[j] = a; }
         for (int j = 0; j < 4; ++j) { double a = rg[(size_t)k * 6 + 2 + j]; for (int l = 0; l < 4; ++l) a += s.A[l][j] * w[l]; mvec[2 + j] = a; }
         const double l00 = F.Linv[(size_t)k * 3], l10 = F.Linv[(size_t)k * 3 + 1], l11 = F.Linv[(size_t)k * 3 + 2];
-        double y0 = mvec[0] / l00, y1 = (mvec[1] - l10 * y0) / l11;
-        double k1 = y1 / l11, k0 = (y0 - l10 * k1) / l00;
+        double y0 = pdiv(mvec[0], l00), y1 = pdiv(mvec[1] - l10 * y0, l11);
+        double k1 = pdiv(y1, l11), k0 = pdiv(y0 - l10 * k1, l00);
         kff[(size_t)k * 2] = k0; kff[(size_t)k * 2 + 1] = k1;
         // p_k = m_x - Mxu kff, with Mxu = K' Muu  ->  Mxu kff = K' (Muu kff) = K' m_u
         const double* K = &F.K[(size_t)k * 8];
@@ -642,7 +647,7 @@ static void qp_solve_ipm(const QP& qp, const OcpOpts& o, QPSol& sol) {
             Hb[(size_t)k * 6 + 5] += be * be * D;
             Hx[k] += be * D;                                   // (beta != 0 only for rows on u_t: ci = 1)
         }
-        if (!riccati_factor(qp, Hb, Hx, F)) { sol.status = 2; break; }
+        if (!riccati_factor(qp, Hb, Hx, F, o.sem_qp_pivot_fails != 0)) { sol.status = 2; break; }
         const double zero4[4] = {0, 0, 0, 0};
         auto solve_with = [&](const std::vector<double>& rmv, std::vector<double>& dz_, std::vector<double>& dxN_, std::vector<double>& dpi_) {
             rgt = rg;
@@ -1179,7 +1184,8 @@ void orc_ocp_set_bounds(void* o_, const double* lh, const double* uh) {
 // opts: [max_sqp_iter, tol_stat, tol_eq, tol_ineq, tol_comp, qp_max_iter, qp_tol, qp_mu0, qp_thr, qp_tau,
 //        alpha_min, alpha_reduction, eps_sufficient_descent, globalization, local_spline,
 //        qp_tol_comp, qp_t_min, qp_gamma_f, qp_stall,
-//        sem_cost_scale, sem_h0_s_row, sem_full_step_dual, sem_merit_weights, sem_armijo, sem_erk_steps, sem_qp_maxiter_fails, sem_mod_strict]
+//        sem_cost_scale, sem_h0_s_row, sem_full_step_dual, sem_merit_weights, sem_armijo, sem_erk_steps, sem_qp_maxiter_fails, sem_mod_strict,
+//        sem_qp_pivot_fails]
 void orc_ocp_set_opts(void* o_, const double* v) {
     OrcOcp* o = (OrcOcp*)o_; OcpOpts& p = o->ocp.opts;
     p.max_sqp_iter = (int)v[0]; p.tol_stat = v[1]; p.tol_eq = v[2]; p.tol_ineq = v[3]; p.tol_comp = v[4];
@@ -1189,6 +1195,7 @@ void orc_ocp_set_opts(void* o_, const double* v) {
     p.qp_tol_comp = v[15]; p.qp_t_min = v[16]; p.qp_gamma_f = v[17]; p.qp_stall = (int)v[18];
     p.sem_cost_scale = (int)v[19]; p.sem_h0_s_row = (int)v[20]; p.sem_full_step_dual = (int)v[21]; p.sem_merit_weights = (int)v[22];
     p.sem_armijo = (int)v[23]; p.sem_erk_steps = (int)v[24]; p.sem_qp_maxiter_fails = (int)v[25]; p.sem_mod_strict = (int)v[26];
+    p.sem_qp_pivot_fails = (int)v[27];
     const_cast<Model*>(o->ocp.model)->mod_strict = p.sem_mod_strict != 0;
 }
 // h_variant 1: h = [u_n; u_t - v_bound(s); u_t + v_bound(s)]; the caller sets the matching lh / uh

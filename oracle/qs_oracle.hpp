@@ -155,6 +155,7 @@ struct OcpOpts {
     int    sem_erk_steps = 1;          // ERK4 steps per shooting interval (sim_method_num_steps, A2.1)
     int    sem_qp_maxiter_fails = 0;   // 0: a QP that hits its iteration limit is accepted (A2.4); 1: it ends the solve with status 4
     int    sem_mod_strict = 0;         // 0: MATLAB's mod as its builtin computes it (may return b); 1: result forced into [0, b)
+    int    sem_qp_pivot_fails = 0;     // 0: a non-positive Cholesky pivot of the Riccati input block is dropped (inverse diagonal 0, BLASFEO dpotrf) and the IPM goes on; 1: it ends the QP (status 4 in SQP)
 };
 
 struct Ocp {

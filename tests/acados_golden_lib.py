@@ -169,7 +169,7 @@ def make_standin(nlp, sem, n_single=4, loop_steps=6, Hp=10, dt=0.05, obj="santal
     loader / replayer / bisector work (a file made this way pins nothing)."""
     from uclv_qs_pushing_matlab_b200.workloads import make_rti_workload
     W = np.diag([1.0, 1.0, 1e-3, 0.0, 1e-3, 1e-3]); We = np.diag([2e5, 2e5, 20.0, 0.0])
-    lh = np.array([-10.0, 0.0, -0.05]); uh = np.array([10.0, 0.03, 0.05])            # NMPC_controller.m:23-26, 82-83
+    lh = np.array([-0.06, 0.0, -0.05]); uh = np.array([0.011, 0.03, 0.05])          # NMPC_controller.m:23-26, 251-252
     t = packaged_tables()[obj]
     base = dict(nlp=nlp, object=obj, Hp=float(Hp), dt=dt, W=W, We=We, lh=lh, uh=uh, b=t["b"], knots=np.asarray(t["knots"]),
                 ctrl=np.asarray(t["ctrl_xy"]))

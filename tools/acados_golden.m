@@ -73,7 +73,8 @@ fprintf('wrote acados_golden_%s.mat with %d recorded solves\n', nlp, numel(cases
 function c = record_solve(controller, ocp, cfg, x0, index_time, nlp, name)
     c = struct();
     c.name = name; c.nlp = nlp; c.object = cfg.object; c.Hp = double(cfg.Hp); c.dt = cfg.dt; c.W = cfg.W; c.We = cfg.We;
-    c.lh = controller.h_constr_lb(:); c.uh = controller.h_constr_ub(:);
+    lb = controller.h_constr_lb(:); ub = controller.h_constr_ub(:);
+    c.lh = [-0.06; lb(2:end)]; c.uh = [0.011; ub(2:end)];                                              % the bounds the OCP is built with, NMPC_controller.m:251-252
     c.x0 = x0(:); c.index_time = index_time;
     c.first_call = isempty(controller.utraj) || isempty(controller.xtraj);
     c.utraj_in = controller.utraj; c.xtraj_in = controller.xtraj; c.ptraj_in = controller.ptraj;

@@ -354,6 +354,89 @@ QS_HD void elem_combine(Elem& e1, const double A2[16], const double C2[10], cons
         }
 }
 
+// e <- e (x) E for a SINGLE-STAGE element e on the left: its C is the rank-2 matrix Bh Bh' (Bh = B Lr^-T, columns bh0, bh1),
+// so (I + C1 J2)^-1 = I - Bh (I2 + Bh' J2 Bh)^-1 Bh' J2 (Woodbury) needs one 2x2 Cholesky instead of the two 4x4 ones of the
+// general combine.  With G = J2 Bh, S = I2 + Bh'G = Ls Ls', Y = Ls^-1 G', V = Ls^-1 Bh':
+//   A = A2 (A1 - V'(Y A1)),   C = (A2 V')(A2 V')' + C2,   J = A1' (J2 - Y'Y) A1 + J1.
+// S >= I in exact arithmetic; C and J stay symmetric PSD by construction like in elem_combine.
+// 372 instead of 620 fused multiply-adds and 2 instead of 8 reciprocal square roots on the dependent chain.
+// In: e.A = A1, e.J = J1 (e.C is not read).  Out: e = the aggregate.
+QS_HD void elem_stage_combine(Elem& e, const double bh0[4], const double bh1[4], const double A2[16], const double C2[10], const double J2[10]) {
+    double G0[4], G1[4];
+    sym4_mul(J2, bh0, G0); sym4_mul(J2, bh1, G1);
+    const double s00 = 1.0 + dot4(bh0, G0), s10 = dot4(bh1, G0), s11 = 1.0 + dot4(bh1, G1);
+    // (J2 is PSD up to rounding; with the coupled rows of h_variant 1 its (s, s) entry is the difference of two barrier terms of
+    // ~1e24 and can come out as negative noise: a non-positive pivot is dropped like in chol4_psd)
+    const bool p0 = s00 > 0.0;
+    const double i00 = p0 ? qs_rsqrt(s00) : 0.0, l10 = s10 * i00, d11 = s11 - l10 * l10;
+    const double i11 = d11 > 0.0 ? qs_rsqrt(d11) : 0.0;
+    double y0[4], y1[4], v0[4], v1[4], t0[4], t1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        y0[i] = G0[i] * i00; y1[i] = (G1[i] - l10 * y0[i]) * i11;
+        v0[i] = bh0[i] * i00; v1[i] = (bh1[i] - l10 * v0[i]) * i11;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) { a = fma(y0[p], e.A[4 * p + j], a); b = fma(y1[p], e.A[4 * p + j], b); }
+        t0[j] = a; t1[j] = b;
+    }
+    // X = J2 - Y'Y ;  J = A1' X A1 + J1   (A1 is still needed: J first)
+    double X[10], XA[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) X[LT(i, j)] = J2[LT(i, j)] - fma(y0[i], y0[j], y1[i] * y1[j]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double a = 0.0;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) a = fma(X[LT(i, p)], e.A[4 * p + j], a);
+            XA[4 * i + j] = a;
+        }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            double a = e.J[LT(i, j)];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) a = fma(e.A[4 * p + i], XA[4 * p + j], a);
+            e.J[LT(i, j)] = a;
+        }
+    // FA = A1 - V'(Y A1) ;  A = A2 FA
+    double FA[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) FA[4 * i + j] = e.A[4 * i + j] - fma(v0[i], t0[j], v1[i] * t1[j]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double a = 0.0;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) a = fma(A2[4 * i + p], FA[4 * p + j], a);
+            e.A[4 * i + j] = a;
+        }
+    // C = (A2 V')(A2 V')' + C2
+    double w0[4], w1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) { a = fma(A2[4 * i + p], v0[p], a); b = fma(A2[4 * i + p], v1[p], b); }
+        w0[i] = a; w1[i] = b;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) e.C[LT(i, j)] = C2[LT(i, j)] + fma(w0[i], w0[j], w1[i] * w1[j]);
+}
+
 // affine maps v -> M v + d ; own <- own o partner  (own is applied AFTER partner)
 QS_HD void aff_compose(double M[16], double d[4], const double Mp[16], const double dp[4]) {
     double Mn[16], dn[4];
@@ -927,13 +1010,13 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             qw_ld_lin(w, j * qw_tm_stage(C), L);
             qw_ld_h(w, j * qw_tm_stage(C), hk);
             // barrier terms first: slack reciprocals and D go to the TMEM block (warp-collective store), affine rhs to R_GT
-            double it8[8], D[4];
+            double it8[8], D[4], Dc[3] = {0.0, 0.0, 0.0};
 #pragma unroll
             for (int i = 0; i < 8; ++i) it8[i] = 0.0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) D[i] = 0.0;
             if (act && k < N) {
-                double gt[6], z6[6], Dc[3];
+                double gt[6], z6[6];
 #pragma unroll
                 for (int i = 0; i < 6; ++i) { gt[i] = QW_SM(R_RG + i, j); z6[i] = QW_SM(R_Z + i, j); }
 #pragma unroll
@@ -987,13 +1070,25 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int q = 0; q <= i; ++q) {
-                    e.C[LT(i, q)] = fma(bh0[i], bh0[q], bh1[i] * bh1[q]);
-                    e.J[LT(i, q)] = Hk[LT(2 + i, 2 + q)] - fma(sh0[i], sh0[q], sh1[i] * sh1[q]);
-                }
-            e.J[LT(3, 3)] += D[0];
+                for (int q = 0; q <= i; ++q) e.J[LT(i, q)] = Hk[LT(2 + i, 2 + q)] - fma(sh0[i], sh0[q], sh1[i] * sh1[q]);
+            if constexpr (hvar) {
+                // coupled rows: D_ss - sh1_s^2 = beta^2 (D1 + D2) - (sigma + beta (D2 - D1))^2 / (rho + D1 + D2) is a difference of two
+                // barrier terms of up to ~1e24 whose exact value is O(rho); expanded with (D1 + D2)^2 - (D2 - D1)^2 = 4 D1 D2 every large
+                // term is positive:  [beta^2 (rho (D1 + D2) + 4 D1 D2) - sigma (sigma + 2 beta (D2 - D1))] / (rho + D1 + D2)
+                const double be = hk[3], rho = Hk[LT(1, 1)] - l10 * l10, sig = Hk[LT(5, 1)] - l10 * sh0[3];
+                const double num = be * be * fma(rho, Dc[1] + Dc[2], 4.0 * Dc[1] * Dc[2]) - sig * fma(2.0 * be, Dc[2] - Dc[1], sig);
+                e.J[LT(3, 3)] = Hk[LT(5, 5)] - sh0[3] * sh0[3] + num * (i11 * i11);
+            } else {
+                e.J[LT(3, 3)] += D[0];
+            }
             // (stage 0 needs no special case: dx_0 = 0 is imposed by the forward scan, the element of stage 0 only feeds lanes left of it)
-            if (!E_is_identity) elem_combine(e, E.A, E.C, E.J);   // E <- e (x) E
+            if (!E_is_identity) elem_stage_combine(e, bh0, bh1, E.A, E.C, E.J);   // E <- e (x) E, rank-2 form
+            else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int q = 0; q <= i; ++q) e.C[LT(i, q)] = fma(bh0[i], bh0[q], bh1[i] * bh1[q]);
+            }
             E = e;
             E_is_identity = false;
         }
