@@ -367,14 +367,18 @@ def run_ours(args):
         t_max, t_e2e_max, t_e2e_fields_max = t_local, t_e2e_local, t_e2e_fields_local
 
     # ---- config 5 (full SQP to convergence, N = 100, mixed sticking / sliding start, four shapes): this rank's share
-    c5 = None
+    c5 = c5f = None
     if world > 1 or args.config5:
-        part = config5_share(q, torch, dev, local_rank, world, rank)
-        parts = [part]
-        if world > 1:
-            parts = [None] * world
-            dist.all_gather_object(parts, part)
-        c5 = merge_config5(parts)
+        for feasible in (False, True):
+            part = config5_share(q, torch, dev, local_rank, world, rank, feasible=feasible)
+            parts = [part]
+            if world > 1:
+                parts = [None] * world
+                dist.all_gather_object(parts, part)
+            if feasible:
+                c5f = merge_config5(parts, feasible=True)
+            else:
+                c5 = merge_config5(parts)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -456,6 +460,7 @@ def run_ours(args):
         line["per_rank_s"] = {"device": [a[0] for a in per_rank], "e2e": [a[1] for a in per_rank]}
     if c5 is not None:
         line["config5"] = c5
+        line["config5_feasible_start"] = c5f
     line.update(extras)
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -463,12 +468,19 @@ def run_ours(args):
     return 0
 
 
-def config5_share(q, torch, dev, local_rank, world, rank):
+def config5_share(q, torch, dev, local_rank, world, rank, feasible=False):
     """This rank's share of BASELINE config 5: 262 144 instances over the job, N = 100, full SQP (<= 30 iterations, merit
-    backtracking) from a mixed sticking / sliding start, four shapes.  One timed solve after one warm-up solve."""
+    backtracking) from a mixed sticking / sliding start, four shapes.  One timed solve after one warm-up solve.
+    feasible = True: the feasible-start variant (tracking-size errors, initial guess inside the friction cone, the symmetric
+    outline only — workloads.make_feasible_start_workload), a quarter of the job size, where full SQP converges."""
     from uclv_qs_pushing_matlab_b200.workloads import packaged_model
     n_job = C5_TOTAL if world > 1 else C5_TOTAL // 8              # a single GPU runs the share it would own on 8
-    w5 = WL.make_rti_workload(n_job, C5_HORIZON, dt=DT, seed=4, n_objects=4, mixed_modes=True)
+    if feasible:
+        n_job //= 4
+        w5 = WL.make_feasible_start_workload(n_job, C5_HORIZON, dt=DT, seed=4)
+        w5["object_id"][:] = OBJECT_ORDER.index("balea")
+    else:
+        w5 = WL.make_rti_workload(n_job, C5_HORIZON, dt=DT, seed=4, n_objects=4, mixed_modes=True)
     lo, hi = SHARD.shard_range(n_job, world, rank)
     sub = {k: v[lo:hi] for k, v in w5.items()}
     del w5
@@ -496,7 +508,7 @@ def config5_share(q, torch, dev, local_rank, world, rank):
     return {"rank": rank, "instances": B5, "ms": ms, "sqp_iter_sum": int(sqp_it.sum()), "per_shape": per_shape, "n_job": n_job}
 
 
-def merge_config5(parts):
+def merge_config5(parts, feasible=False):
     tot = sum(p["instances"] for p in parts)
     t = max(p["ms"] for p in parts) * 1e-3
     its = sum(p["sqp_iter_sum"] for p in parts)
@@ -508,8 +520,11 @@ def merge_config5(parts):
         shapes[n] = {"instances": inst, "status": stt, "converged_frac": stt["0"] / max(inst, 1), "mean_sqp_iter": sq / max(inst, 1),
                      "mean_ipm_iter_per_qp": sum(p["per_shape"][n]["qp_iter_sum"] for p in parts) / max(1, sq)}
     conv = sum(s["status"]["0"] for s in shapes.values())
-    return {"workload": f"config5: {tot} instances (job size {parts[0]['n_job']}), N={C5_HORIZON}, full SQP <= 30 iterations, merit backtracking, "
-                        "mixed sticking/sliding start, 4 shapes, seed 4",
+    shapes = {n: v for n, v in shapes.items() if v["instances"]}
+    what = ("feasible start (tracking-size errors, guess inside the friction cone), symmetric outline (balea), seed 4" if feasible
+            else "mixed sticking/sliding start, 4 shapes, seed 4")
+    return {"workload": f"config5{'-feasible-start' if feasible else ''}: {tot} instances (job size {parts[0]['n_job']}), N={C5_HORIZON}, full SQP <= 30 iterations, "
+                        f"merit backtracking, {what}",
             "instances": tot, "seconds": t, "sqp_iterations_per_s": its / t, "instances_per_s": tot / t, "converged_frac": conv / tot,
             "status_legend": "0 converged, 1 NaN, 2 iteration limit, 3 minimum step, 4 QP failure (acados v0.2.1 enum)",
             "per_shape": shapes, "per_rank_ms": [p["ms"] for p in parts]}

@@ -194,7 +194,7 @@ DEFAULT_OPTS = dict(
     max_sqp_iter=30, tol_stat=1e-6, tol_eq=1e-6, tol_ineq=1e-6, tol_comp=1e-6,
     qp_max_iter=50, qp_tol=1e-11, qp_mu0=0.1, qp_thr=1e-3, qp_tau=0.9995,
     alpha_min=0.05, alpha_reduction=0.7, eps_sufficient_descent=1e-4, globalization=1, local_spline=1,
-    qp_tol_comp=1e-18, qp_t_min=1e-12, qp_gamma_f=0.05, qp_stall=10,
+    qp_tol_comp=1e-18, qp_t_min=1e-12, qp_gamma_f=0.01, qp_stall=10,
     # recalled acados semantics as switches (qs_oracle.hpp); defaults = what the restatement believes
     sem_cost_scale=0, sem_h0_s_row=0, sem_full_step_dual=0, sem_merit_weights=0, sem_armijo=0, sem_erk_steps=1,
     sem_qp_maxiter_fails=0, sem_mod_strict=0, sem_qp_pivot_fails=0,

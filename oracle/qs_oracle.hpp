@@ -142,7 +142,7 @@ struct OcpOpts {
     // (tests/test_qp_exact.py compares it with the extended-precision arbiter, oracle/qs_arbiter.cpp).
     double qp_tol_comp = 1e-18;        // tolerance on max lam * t
     double qp_t_min = 1e-12;           // slack floor: pairs with t <= 4 t_min count as converged, their centering target is lam * t_min (bounds lam / t)
-    double qp_gamma_f = 0.05;          // step to the boundary: blocking pair keeps gamma_f * (predicted mu reduction) of its value
+    double qp_gamma_f = 0.01;          // step to the boundary: blocking pair keeps gamma_f * (predicted mu reduction) of its value
     int    qp_stall = 10;              // iterations without halving the normalised residual before a point below 1e-6 is accepted
     // ---- RECALLED acados v0.2.1 semantics as switches (none of it could be run here).  The defaults are
     // what the restatement believes; when golden vectors from a real acados run (tools/acados_golden.m) disagree,

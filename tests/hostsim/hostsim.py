@@ -110,7 +110,7 @@ class Model:
 
 def solve(models, N, dt, x0, yref, yref_e, x, u, pi=None, lam=None, cold=None, objid=None, W=None, We=None,
           lh=(-0.06, 0.0, -0.05), uh=(0.011, 0.03, 0.05), mode="rti", prepare=False, shift=False,
-          qp_tol=1e-11, qp_mu0=0.1, qp_thr=1e-3, qp_tau=0.9995, qp_tol_comp=1e-18, qp_t_min=1e-12, qp_gamma_f=0.05, qp_stall=10, qp_max_iter=50, max_sqp_iter=30,
+          qp_tol=1e-11, qp_mu0=0.1, qp_thr=1e-3, qp_tau=0.9995, qp_tol_comp=1e-18, qp_t_min=1e-12, qp_gamma_f=0.01, qp_stall=10, qp_max_iter=50, max_sqp_iter=30,
           tol=(1e-6, 1e-6, 1e-6, 1e-6), globalization=1, alpha_min=0.05, alpha_red=0.7, eps_sd=1e-4,
           single_quirk=True, ctrl=(1.0, 0.0, 3.0, 0.05, 0.0), qp_kernel=1, h_variant=0):
     nb = np.asarray(x0).shape[0]
@@ -143,7 +143,7 @@ def solve(models, N, dt, x0, yref, yref_e, x, u, pi=None, lam=None, cold=None, o
 
 def closed_loop(models, N, dt, traj, x, steps, offset=None, objid=None, W=None, We=None,
                 lh=(-0.06, 0.0, -0.05), uh=(0.011, 0.03, 0.05), mode="rti",
-                qp_tol=1e-11, qp_mu0=0.1, qp_thr=1e-3, qp_tau=0.9995, qp_tol_comp=1e-18, qp_t_min=1e-12, qp_gamma_f=0.05, qp_stall=10, qp_max_iter=50, max_sqp_iter=30,
+                qp_tol=1e-11, qp_mu0=0.1, qp_thr=1e-3, qp_tau=0.9995, qp_tol_comp=1e-18, qp_t_min=1e-12, qp_gamma_f=0.01, qp_stall=10, qp_max_iter=50, max_sqp_iter=30,
                 tol=(1e-6, 1e-6, 1e-6, 1e-6), globalization=1, alpha_min=0.05, alpha_red=0.7, eps_sd=1e-4,
                 single_quirk=True, ctrl=(1.0, 0.0, 3.0, 0.05, 0.0), qp_kernel=1, h_variant=0,
                 idx0=1, noise_sigma=(0.0, 0.0, 0.0, 0.0), seed=0, t_dist=0, amplitude_dist=0.0, xwidth=0.0):

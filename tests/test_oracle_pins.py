@@ -328,3 +328,22 @@ def test_velocity_constraint_variant_derivative_and_kkt_certificate():
             worst = max(worst, np.abs(lin["A"][b, k] @ dx[k] + lin["B"][b, k] @ du[k] + lin["b"][b, k] - dx[k + 1]).max())
         worst = max(worst, np.abs(We @ dx[N] + lin["qN"][b] - pi[N - 1]).max())
     assert worst < 1.5e-11 and active >= 10, (worst, active)
+
+
+def test_feasible_start_variant_of_config5_converges():
+    """Full SQP (N = 100, merit backtracking, <= 30 iterations) from the feasible start on the symmetric outline converges for
+    >= 90 % of the instances; from the mixed sticking / sliding start of config 5 the three asymmetric outlines end at the iteration
+    limit (the minimiser sits on the u_n = 0 kink) and, with BLASFEO's pivot rule, no instance ends as a QP failure."""
+    from tests.workloads import make_feasible_start_workload
+    N, B = 100, 64
+    wl = make_feasible_start_workload(B, N)
+    ocp = orc.Ocp(oracle_model("balea"), N, 0.05)
+    pr = ocp.prepare(wl["x0"], np.zeros(B, dtype=np.int32), np.zeros((B, N + 1, 4)), wl["u_init"])
+    r = ocp.solve("sqp", pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"], nthreads=8)
+    assert (r["status"] == 0).mean() >= 0.9 and set(np.unique(r["status"])) <= {0, 2}
+    wl = make_rti_workload(None, batch=32, N=N, seed=4, mixed_modes=True)
+    for name, pivot_fails, expect4 in (("pulirapid", 0, False), ("pulirapid", 1, True)):
+        ocp = orc.Ocp(oracle_model(name), N, 0.05, sem_qp_pivot_fails=pivot_fails)
+        pr = ocp.prepare(wl["x0"], np.zeros(32, dtype=np.int32), np.zeros((32, N + 1, 4)), wl["u_init"])
+        r = ocp.solve("sqp", pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"], nthreads=8)
+        assert ((r["status"] == 4).mean() > 0.1) == expect4, (name, pivot_fails, np.bincount(r["status"], minlength=5))

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from uclv_qs_pushing_matlab_b200.workloads import (OBJECT_ORDER, make_rti_workload as _mk, make_samples_config2,  # noqa: E402,F401
+from uclv_qs_pushing_matlab_b200.workloads import (OBJECT_ORDER, make_feasible_start_workload, make_rti_workload as _mk, make_samples_config2,  # noqa: E402,F401
                                                     packaged_tables, reference_line)
 from uclv_qs_pushing_matlab_b200.object_selection import OBJECT_TABLE  # noqa: E402
 

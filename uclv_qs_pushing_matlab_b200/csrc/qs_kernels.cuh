@@ -197,23 +197,45 @@ constexpr int QW_MAX_WARPS = 8;
 // neighbours in the order need about the same number of iterations, so a segment rarely idles while its partner
 // finishes (random pairs lose ~10 % of the segment-iterations).  In closed loop the previous count is a good
 // predictor; the order never changes a result (every problem's arithmetic is independent of its partner).
-constexpr int QO_BINS = 64;
-__global__ void __launch_bounds__(1024) k_qp_order(SolverDev S, int* __restrict__ order) {
+constexpr int QO_BINS = 64;          // qp_order_cta scans the bins with one warp, two per lane
+static_assert(QO_BINS == 64, "qp_order_cta: two bins per lane");
+// counting sort of the problems by descending previous IPM iteration count, by ONE CTA.  The batch has a handful of distinct
+// counts, so plain shared-memory atomics serialise (4096 increments on ~10 addresses: 22 us); lanes with equal keys are grouped
+// with match.any, one atomic per group (1 us).
+__device__ __forceinline__ void qp_order_cta(const SolverDev& S, int* __restrict__ order) {
     __shared__ int cnt[QO_BINS], pos[QO_BINS];
+    const int lane = threadIdx.x & 31;
     if (threadIdx.x < QO_BINS) cnt[threadIdx.x] = 0;
     __syncthreads();
-    for (int b = threadIdx.x; b < S.B; b += blockDim.x) {
-        const int k = S.qp_last[b];
-        atomicAdd(&cnt[QO_BINS - 1 - (k < 0 ? 0 : (k > QO_BINS - 1 ? QO_BINS - 1 : k))], 1);
+    for (int b0 = 0; b0 < S.B; b0 += blockDim.x) {               // uniform trip count: match.any is warp-collective
+        const int b = b0 + threadIdx.x;
+        const int k = b < S.B ? S.qp_last[b] : 0;
+        const int key = b < S.B ? QO_BINS - 1 - (k < 0 ? 0 : (k > QO_BINS - 1 ? QO_BINS - 1 : k)) : QO_BINS;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (key < QO_BINS && lane == __ffs(peers) - 1) atomicAdd(&cnt[key], __popc(peers));
     }
     __syncthreads();
-    if (threadIdx.x == 0) { int a = 0; for (int i = 0; i < QO_BINS; ++i) { pos[i] = a; a += cnt[i]; } }
+    if (threadIdx.x < 32) {                                      // exclusive prefix sum of the 64 bins by one warp
+        const int c0 = cnt[2 * lane], c1 = cnt[2 * lane + 1];
+        int a = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, a, o); if (lane >= o) a += t; }
+        pos[2 * lane] = a - c0 - c1; pos[2 * lane + 1] = a - c1;
+    }
     __syncthreads();
-    for (int b = threadIdx.x; b < S.B; b += blockDim.x) {
-        const int k = S.qp_last[b];
-        order[atomicAdd(&pos[QO_BINS - 1 - (k < 0 ? 0 : (k > QO_BINS - 1 ? QO_BINS - 1 : k))], 1)] = b;
+    for (int b0 = 0; b0 < S.B; b0 += blockDim.x) {
+        const int b = b0 + threadIdx.x;
+        const int k = b < S.B ? S.qp_last[b] : 0;
+        const int key = b < S.B ? QO_BINS - 1 - (k < 0 ? 0 : (k > QO_BINS - 1 ? QO_BINS - 1 : k)) : QO_BINS;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(peers) - 1;
+        int base = 0;
+        if (key < QO_BINS && lane == leader) base = atomicAdd(&pos[key], __popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (key < QO_BINS) order[base + __popc(peers & ((1u << lane) - 1u))] = b;
     }
 }
+__global__ void __launch_bounds__(1024) k_qp_order(SolverDev S, int* __restrict__ order) { qp_order_cta(S, order); }
 template <int C, int HV, int SEG>
 __global__ void __launch_bounds__(32 * QW_MAX_WARPS, 1) k_qp_warp(SolverDev S, IpmOpts o, int apply, int per_problem_doubles) {
     extern __shared__ __align__(16) double qw_smem[];
@@ -383,23 +405,7 @@ __global__ void __launch_bounds__(128) k_prepare(SolverDev S, CtrlDev cp, LoopDe
     prepare_one(S, cp, Mall, b);
 }
 __global__ void __launch_bounds__(1024) k_step_out(SolverDev S, double* __restrict__ u0, int* __restrict__ status, int* __restrict__ order) {
-    if (blockIdx.x + 1 == gridDim.x) {                          // last CTA: counting sort, descending previous iteration count
-        __shared__ int cnt[QO_BINS], pos[QO_BINS];
-        if (threadIdx.x < QO_BINS) cnt[threadIdx.x] = 0;
-        __syncthreads();
-        for (int b = threadIdx.x; b < S.B; b += blockDim.x) {
-            const int k = S.qp_last[b];
-            atomicAdd(&cnt[QO_BINS - 1 - (k < 0 ? 0 : (k > QO_BINS - 1 ? QO_BINS - 1 : k))], 1);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) { int a = 0; for (int i = 0; i < QO_BINS; ++i) { pos[i] = a; a += cnt[i]; } }
-        __syncthreads();
-        for (int b = threadIdx.x; b < S.B; b += blockDim.x) {
-            const int k = S.qp_last[b];
-            order[atomicAdd(&pos[QO_BINS - 1 - (k < 0 ? 0 : (k > QO_BINS - 1 ? QO_BINS - 1 : k))], 1)] = b;
-        }
-        return;
-    }
+    if (blockIdx.x + 1 == gridDim.x) { qp_order_cta(S, order); return; }   // last CTA: counting sort, descending previous iteration count
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= S.B) return;
     reinterpret_cast<double2*>(u0)[b] = make_double2(QS_EL(S.u, 0, b), QS_EL(S.u, 1, b));

@@ -271,7 +271,7 @@ void qspush_opts_default(qspush_opts* o) {
     o->tol_stat = o->tol_eq = o->tol_ineq = o->tol_comp = 1e-6;
     o->qp_max_iter = 50;
     o->qp_tol = 1e-11; o->qp_mu0 = 0.1; o->qp_thr = 1e-3; o->qp_tau = 0.9995;   // mu0 tuned on config 3: K_ipm 12.3 -> 11.0
-    o->qp_tol_comp = 1e-18; o->qp_t_min = 1e-12; o->qp_gamma_f = 0.05; o->qp_stall = 10;   // end game: DESIGN.md 2.1
+    o->qp_tol_comp = 1e-18; o->qp_t_min = 1e-12; o->qp_gamma_f = 0.01; o->qp_stall = 10;   // end game: DESIGN.md 2.1
     o->globalization = 1;                                      // merit_backtracking, :272
     o->alpha_min = 0.05; o->alpha_reduction = 0.7; o->eps_sufficient_descent = 1e-4;
     o->matlab_single_quirk = 1;

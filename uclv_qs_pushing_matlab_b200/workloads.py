@@ -55,6 +55,25 @@ def make_rti_workload(batch, N, dt=0.05, seed=2, n_objects=1, mixed_modes=False)
     return dict(x0=x0, yref=yref, yref_e=yref_e, u_init=u, object_id=obj)
 
 
+def make_feasible_start_workload(batch, N, dt=0.05, seed=4, n_objects=1):
+    """Config 5, feasible-start variant: the same horizon and solver settings, but a start from which the NLP is well posed —
+    lateral / heading errors of a tracking controller (+-3 mm, +-1 deg instead of +-30 mm, +-10 deg), the contact point near the
+    middle of the pushed edge (s in [-10, 5] mm) and an initial guess inside the friction cone (|u_t| <= 0.1 u_n, sticking).
+    Meant for the symmetric outline (balea), where the no-rotation contact point is s = 0 and the minimiser lies inside the sticking
+    mode; on the other three outlines the minimiser slides along the edge with u_n at its bound 0, i.e. ON the kink of the mode
+    indicators, and full SQP chatters whatever the start."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    x0 = np.stack([rng.uniform(-0.03, 0.03, batch), 0.1 * rng.uniform(-0.03, 0.03, batch),
+                   0.1 * np.deg2rad(rng.uniform(-10.0, 10.0, batch)), rng.uniform(-0.01, 0.005, batch)], axis=1)
+    yref, yref_e = reference_line(x0, N, dt)
+    yref[:, :, 1] = 0.0; yref_e[:, 1] = 0.0                       # the reference line is y = 0: the lateral error is x0's
+    u = np.zeros((batch, N, 2))
+    u[:, :, 0] = rng.uniform(0.002, 0.02, (batch, N))
+    u[:, :, 1] = u[:, :, 0] * rng.uniform(-0.1, 0.1, (batch, N))
+    obj = (np.arange(batch) % n_objects).astype(np.int32)
+    return dict(x0=x0, yref=yref, yref_e=yref_e, u_init=u, object_id=obj)
+
+
 def make_samples_config2(b, n, seed=1, n_adversarial=4096, knots=None):
     """Config 2: n (x, u) samples populating all three contact modes plus adversarial corner cases."""
     rng = np.random.Generator(np.random.PCG64(seed))
