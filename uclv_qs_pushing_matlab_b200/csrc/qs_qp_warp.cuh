@@ -40,36 +40,34 @@ namespace qs {
 struct WarpCtxDev {
     int lane_;
     unsigned tm_;        // TMEM address of this warp's private block: (32 * (warp % 4)) << 16 | first column
+    // The 32-bit destination registers are asm OUTPUTS (not block-local temporaries copied out with mov.b64): the register
+    // allocator then places the LDTM destination block where the consumers read it, each aligned pair being one double —
+    // with block-local temporaries every load was followed by one MOV per 32-bit register (6 % of the kernel's instructions).
     template <int n> __device__ __forceinline__ void tm_ld(int off, double* v) const {
         static_assert(n == 4 || n == 8 || n == 16, "tm_ld: 4, 8 or 16 doubles");
         const unsigned a = tm_ + 2u * (unsigned)off;
+        unsigned r[2 * n];
         __syncwarp();
         if constexpr (n == 4) {
-            asm volatile("{\n\t.reg .b32 t<8>;\n\t"
-                         "tcgen05.ld.sync.aligned.32x32b.x8.b32 {" QW_TM_REGS8 "}, [%4];\n\t"
-                         "tcgen05.wait::ld.sync.aligned;\n\t"
-                         "mov.b64 %0, {t0,t1};\n\tmov.b64 %1, {t2,t3};\n\tmov.b64 %2, {t4,t5};\n\tmov.b64 %3, {t6,t7};\n\t}"
-                         : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "r"(a) : "memory");
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t"
+                         "tcgen05.wait::ld.sync.aligned;"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(a) : "memory");
         } else if constexpr (n == 8) {
-            asm volatile("{\n\t.reg .b32 t<16>;\n\t"
-                         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {" QW_TM_REGS16 "}, [%8];\n\t"
-                         "tcgen05.wait::ld.sync.aligned;\n\t"
-                         "mov.b64 %0, {t0,t1};\n\tmov.b64 %1, {t2,t3};\n\tmov.b64 %2, {t4,t5};\n\tmov.b64 %3, {t6,t7};\n\t"
-                         "mov.b64 %4, {t8,t9};\n\tmov.b64 %5, {t10,t11};\n\tmov.b64 %6, {t12,t13};\n\tmov.b64 %7, {t14,t15};\n\t}"
-                         : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]), "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7])
-                         : "r"(a) : "memory");
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+                         "tcgen05.wait::ld.sync.aligned;"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(a) : "memory");
         } else {
-            asm volatile("{\n\t.reg .b32 t<32>;\n\t"
-                         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {" QW_TM_REGS32 "}, [%16];\n\t"
-                         "tcgen05.wait::ld.sync.aligned;\n\t"
-                         "mov.b64 %0, {t0,t1};\n\tmov.b64 %1, {t2,t3};\n\tmov.b64 %2, {t4,t5};\n\tmov.b64 %3, {t6,t7};\n\t"
-                         "mov.b64 %4, {t8,t9};\n\tmov.b64 %5, {t10,t11};\n\tmov.b64 %6, {t12,t13};\n\tmov.b64 %7, {t14,t15};\n\t"
-                         "mov.b64 %8, {t16,t17};\n\tmov.b64 %9, {t18,t19};\n\tmov.b64 %10, {t20,t21};\n\tmov.b64 %11, {t22,t23};\n\t"
-                         "mov.b64 %12, {t24,t25};\n\tmov.b64 %13, {t26,t27};\n\tmov.b64 %14, {t28,t29};\n\tmov.b64 %15, {t30,t31};\n\t}"
-                         : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]), "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7]),
-                           "=d"(v[8]), "=d"(v[9]), "=d"(v[10]), "=d"(v[11]), "=d"(v[12]), "=d"(v[13]), "=d"(v[14]), "=d"(v[15])
-                         : "r"(a) : "memory");
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                         "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+                         "tcgen05.wait::ld.sync.aligned;"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) : "r"(a) : "memory");
         }
+#pragma unroll
+        for (int i = 0; i < n; ++i) v[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
     }
     template <int n> __device__ __forceinline__ void tm_st(int off, const double* v) const {
         static_assert(n == 4 || n == 8, "tm_st: 4 or 8 doubles (16: tm_st16)");
