@@ -181,12 +181,15 @@ int qspush_plant_step(qspush_solver* s, double* x, const double* u, qspush_mem m
  *     disturbance (helper.m:221-236, optional) and state noise (:240-242, optional) on the plant state,
  *     constr_x0 <- state, reference window of period idx0 + i - 1 (NMPC_controller.m:307-313, 343-348),
  *     qspush_prepare, qspush_solve, u = get('u', 0) (:403), Euler plant step (helper.m:294, 307), qspush_shift.
- * In RTI mode nothing synchronises with the host until the final copy-out.  Plant / controller input delays
- * (helper.m:205-212, NMPC_controller.m:106-120) are not part of this entry point (host mirror only).
+ * In RTI mode nothing synchronises with the host until the final copy-out.  Input delays (helper.m:205-212, 244, 250,
+ * 290-298; NMPC_controller.m:106-120), counted in control periods: with delay_plant = ceil(plant.time_delay / dt) the plant
+ * applies the input of delay_plant periods ago (zeros at first); with delay_comp = controller.delay_buff_comp the controller
+ * is handed the state rolled forward through the delay_comp inputs already sent (delay_buffer_sim) and the caller passes the
+ * padded reference of set_reference_trajectory with idx0 = 1 + delay_comp (helper.m:248).
  *   traj  [T][6]       reference columns [x_ref(4); u_ref(2)] shared by all problems
  *   offset[batch][6]   added to every column per problem (NULL: none)
  *   x     [batch][4]   plant state, in: initial, out: after `steps` periods
- *   log_x [steps][batch][4] state handed to the controller, log_u [steps][batch][2], log_status [steps][batch] (each may be NULL)
+ *   log_x [steps][batch][4] state handed to the controller (after delay_buffer_sim), log_u [steps][batch][2], log_status [steps][batch] (each may be NULL)
  * All arrays live in `mem`. */
 typedef struct {
     int    idx0;                 /* reference index of the first period (1-based; helper.m: i = 1)            */
@@ -195,6 +198,8 @@ typedef struct {
     int    t_dist;               /* period of the lateral shove (1-based), 0 = none       helper.m:222        */
     double amplitude_dist;       /* helper.m:224                                                               */
     double xwidth;               /* slider_params.xwidth: contact target of the re-projection  helper.m:228   */
+    int    delay_plant;          /* delay_buff_plant, control periods (helper.m:211), 0 = none                */
+    int    delay_comp;           /* controller.delay_buff_comp, control periods (NMPC_controller.m:108)        */
 } qspush_loop_opts;
 int qspush_closed_loop(qspush_solver* s, const double* traj, int T, const double* offset, double* x, int steps,
                        const qspush_loop_opts* lo, double* log_x, double* log_u, int* log_status, qspush_mem mem);

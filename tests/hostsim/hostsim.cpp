@@ -399,7 +399,7 @@ int hs_solve(void* const* models, int nmodels, int N, double dt, int nb, const i
 }
 
 // mirrors qspush_closed_loop (qspush_capi.cu): the same kernel bodies in the same order on host slabs.
-//   loop_d: [sigma0..3, amplitude_dist, xwidth]   loop_i: [idx0, t_dist]   seed: noise seed
+//   loop_d: [sigma0..3, amplitude_dist, xwidth]   loop_i: [idx0, t_dist, delay_plant, delay_comp]   seed: noise seed
 int hs_closed_loop(void* const* models, int nmodels, int N, double dt, int nb, const int* objid,
                    const double* W, const double* We, const double* lh, const double* uh,
                    const double* opts_d, const int* opts_i, const double* ctrl5,
@@ -413,13 +413,16 @@ int hs_closed_loop(void* const* models, int nmodels, int N, double dt, int nb, c
     L.traj = traj; L.off = offset; L.T = T;
     for (int i = 0; i < 4; ++i) L.sigma[i] = loop_d[i];
     L.seed = seed; L.t_dist = loop_i[1]; L.amp = loop_d[4]; L.xwidth = loop_d[5]; L.single = R.single;
+    L.dp = loop_i[2]; L.dc = loop_i[3];
+    std::vector<double> ring_p((size_t)L.dp * nb * 2, 0.0), ring_c((size_t)L.dc * nb * 2, 0.0);
+    L.ring_plant = ring_p.data(); L.ring_contr = ring_c.data();
     for (int i = 1; i <= steps; ++i) {
         for (int b = 0; b < nb; ++b) loop_state_one(R.S, L, R.Mall(), i, x, log_x ? log_x + (size_t)(i - 1) * nb * 4 : nullptr, b);
         for (int k = 0; k < N; ++k) for (int b = 0; b < nb; ++b) loop_window_one(R.S, L, loop_i[0] + i - 1, k, b);
         R.prepare();
         R.solve();
         for (int b = 0; b < nb; ++b)
-            loop_post_one(R.S, R.Mall(), x, log_u ? log_u + (size_t)(i - 1) * nb * 2 : nullptr, log_status ? log_status + (size_t)(i - 1) * nb : nullptr, b);
+            loop_post_one(R.S, L, R.Mall(), i, x, log_u ? log_u + (size_t)(i - 1) * nb * 2 : nullptr, log_status ? log_status + (size_t)(i - 1) * nb : nullptr, b);
         R.shift();
     }
     return 0;

@@ -146,7 +146,7 @@ def closed_loop(models, N, dt, traj, x, steps, offset=None, objid=None, W=None, 
                 qp_tol=1e-11, qp_mu0=0.1, qp_thr=1e-3, qp_tau=0.9995, qp_tol_comp=1e-18, qp_t_min=1e-12, qp_gamma_f=0.01, qp_stall=10, qp_max_iter=50, max_sqp_iter=30,
                 tol=(1e-6, 1e-6, 1e-6, 1e-6), globalization=1, alpha_min=0.05, alpha_red=0.7, eps_sd=1e-4,
                 single_quirk=True, ctrl=(1.0, 0.0, 3.0, 0.05, 0.0), qp_kernel=1, h_variant=0,
-                idx0=1, noise_sigma=(0.0, 0.0, 0.0, 0.0), seed=0, t_dist=0, amplitude_dist=0.0, xwidth=0.0):
+                idx0=1, noise_sigma=(0.0, 0.0, 0.0, 0.0), seed=0, t_dist=0, amplitude_dist=0.0, xwidth=0.0, delay_plant=0, delay_comp=0):
     """Host mirror of qspush_closed_loop (same kernel bodies, same order)."""
     x = _c(x).copy(); nb = x.shape[0]
     if W is None:
@@ -159,7 +159,7 @@ def closed_loop(models, N, dt, traj, x, steps, offset=None, objid=None, W=None, 
     od = _c([qp_tol, qp_mu0, qp_thr, qp_tau, *tol, alpha_min, alpha_red, eps_sd, qp_tol_comp, qp_t_min, qp_gamma_f, qp_stall])
     oi = _c([{"rti": 0, "sqp": 1}[mode], qp_max_iter, max_sqp_iter, globalization, int(single_quirk), 1, 1, int(qp_kernel), int(h_variant)], np.int32)
     c5 = _c(ctrl); lh = _c(lh); uh = _c(uh)
-    ld = _c([*noise_sigma, amplitude_dist, xwidth]); li = _c([idx0, t_dist], np.int32)
+    ld = _c([*noise_sigma, amplitude_dist, xwidth]); li = _c([idx0, t_dist, delay_plant, delay_comp], np.int32)
     lx = np.zeros((steps, nb, 4)); lu = np.zeros((steps, nb, 2)); ls = np.zeros((steps, nb), dtype=np.int32)
     off = None if offset is None else _c(offset)
     arr = (C.c_void_p * len(models))(*[m.h for m in models])

@@ -586,6 +586,42 @@ def test_device_resident_closed_loop():
     assert abs(float(un_sum) - float(out[4].sum())) < 1e-9
 
 
+@pytest.mark.parametrize("delay_plant,delay_comp", [(0.1, 0.0), (0.0, 0.15), (0.1, 0.15)])
+def test_closed_loop_input_delays_on_device(delay_plant, delay_comp):
+    """Input delays (helper.m:205-212, 244-250, 290-298; NMPC_controller.m:106-120) inside qspush_closed_loop: plant ring and
+    controller ring on the device, against (i) the host execution of the same kernel bodies and (ii) the MATLAB-shaped mirror
+    helper.closed_loop_matlab, which drives the solver period by period from the host."""
+    from tests.hostsim import hostsim as hs
+    from tests.workloads import hostsim_model
+    N, dt, B, steps = 10, 0.05, 8, 24
+    T = 120
+    t = np.arange(T) * dt
+    traj = np.zeros((T, 6)); traj[:, 0] = np.minimum(0.01 * t, 0.10)
+    rng = np.random.default_rng(9)
+    x0s = np.stack([rng.uniform(-0.002, 0.002, B), rng.uniform(-0.002, 0.002, B), rng.uniform(-0.03, 0.03, B), rng.uniform(-0.01, 0.004, B)], 1)
+    sel = q.object_selection("santal")
+    outs = []
+    for device_loop in (True, False):
+        p = q.PusherSliderModel("real_plant", sel, delay_plant, sel.cad_model_path, 3, sel.pcl_path, "santal")
+        p.symbolic_model_variable_shape()
+        c = q.NMPC_controller("NMPC", p, dt, N, batch=B, nlp_solver="sqp_rti")
+        c.create_ocp_solver(); c.set_delay_comp(delay_comp)
+        c.set_reference_trajectory(traj.T)
+        if device_loop:
+            o = q.helper.closed_loop_device(p, c, x0s, (steps - 1) * dt)
+            outs.append((np.stack([o[0], o[1], o[2], o[3]], -1), np.stack([o[4], o[5]], -1), o[7]))
+        else:
+            o = q.helper.closed_loop_matlab(p, c, x0s, (steps - 1) * dt)
+            outs.append((o[1], np.stack([o[6], o[7]], -1), o[10]))      # x_sim = the state handed to the controller
+    (xd, ud, fd), (xm, um, fm) = outs
+    assert fd.all() and fm.all()
+    assert np.abs(ud - um).max() < 1e-10 and np.abs(xd - xm).max() < 1e-10
+    dp, dc = int(np.ceil(delay_plant / dt)), int(np.ceil(delay_comp / dt))
+    pad = np.zeros((dc, 6)); pad[:, 5] = traj[0, 5]
+    h = hs.closed_loop([hostsim_model("santal")], N, dt, np.concatenate([pad, traj]), x0s, steps, idx0=1 + dc, delay_plant=dp, delay_comp=dc)
+    assert np.abs(np.transpose(h["u_log"], (1, 0, 2)) - ud).max() < 1e-8 and np.abs(np.transpose(h["x_log"], (1, 0, 2)) - xd).max() < 1e-8
+
+
 @pytest.mark.parametrize("N", [1, 7, 15, 16, 31, 32, 47, 48, 63, 64, 96, 127])
 def test_every_warp_mapping_vs_thread_kernel(N):
     """The warp QP kernel in every mapping (16- / 32-lane segments, C = 1..4, full and partial last lanes, odd batch:

@@ -256,6 +256,61 @@ def test_closed_loop_bodies_vs_oracle():
     assert 0 < np.abs(d0[:, 2]).max() < 6e-3 and np.abs(d0[:, 0]).max() < 6e-5
 
 
+def _delayed_loop_oracle(om, ocp, x0, traj, steps, dp, dc, dt):
+    """helper.closed_loop_matlab with input delays restated with the oracle's primitives (helper.m:205-212, 244-250, 290-307;
+    NMPC_controller.m:106-120, 425-431): plant ring u_buff_plant, controller ring u_buff_contr, delay_buffer_sim, padded reference."""
+    N = ocp.N
+    pad = np.zeros((dc, 6)); pad[:, 5] = traj[0, 5]
+    yref_full = np.concatenate([pad, traj], axis=0)                          # set_reference_trajectory
+    T = yref_full.shape[0]
+    x = np.array(x0, dtype=float); ubp = np.zeros((2, dp)); ubc = np.zeros((2, dc))
+    tr = dict(x=np.zeros((1, N + 1, 4)), u=np.zeros((1, N, 2)), pi=np.zeros((1, N, 4)), lam=np.zeros((1, N, 6)))
+    xs, us = [], []
+    for i in range(1, steps + 1):
+        xk = x.copy()
+        for k in range(1, dc + 1):                                           # delay_buffer_sim
+            xk = xk + dt * om.dynamics(xk[None], ubc[:, -k][None])[0]
+        idx = i + dc
+        cols = np.minimum(idx + np.arange(N), T) - 1
+        yref = yref_full[cols][None]; yref_e = yref[:, N - 1, :4].copy()
+        p = ocp.prepare(xk[None], np.array([1 if i == 1 else 0], dtype=np.int32), tr["x"], tr["u"], tr["pi"], tr["lam"])
+        r = ocp.solve("rti", p["x0"], yref, yref_e, p["x"], p["u"], p["pi"], p["lam"])
+        u = r["u"][0, 0].copy()
+        tr = ocp.shift(r["x"], r["u"], r["pi"], r["lam"])
+        xs.append(xk); us.append(u)
+        if dc:
+            ubc = np.concatenate([u[:, None], ubc[:, :-1]], axis=1)
+        ua = u if dp == 0 else ubp[:, -1].copy()
+        if dp:
+            ubp = np.concatenate([u[:, None], ubp[:, :-1]], axis=1)
+        x = x + dt * om.dynamics(x[None], ua[None])[0]
+    return np.array(xs), np.array(us), x
+
+
+@pytest.mark.parametrize("dp,dc", [(2, 0), (0, 3), (2, 2), (1, 4)])
+def test_closed_loop_input_delays_vs_oracle(dp, dc):
+    """Input delays inside the device-resident loop bodies (ring buffers on the device): plant delay, controller delay
+    compensation and both, against the reference's loop restated with the oracle's primitives."""
+    om, hm = oracle_model("santal"), hostsim_model("santal")
+    N, dt, steps, T = 10, 0.05, 25, 120
+    t = np.arange(T) * dt
+    traj = np.zeros((T, 6)); traj[:, 0] = np.minimum(0.01 * t, 0.10)
+    x0s = np.array([[0, 0, 0, 0], [0.001, -0.002, 0.02, -0.01]], dtype=float)
+    pad = np.zeros((dc, 6)); pad[:, 5] = traj[0, 5]
+    r = hs.closed_loop([hm], N, dt, np.concatenate([pad, traj], axis=0), x0s, steps, idx0=1 + dc, delay_plant=dp, delay_comp=dc)
+    assert (r["status_log"] == 0).all()
+    ocp = orc.Ocp(om, N, dt)
+    for b in range(2):
+        xs, us, xf = _delayed_loop_oracle(om, ocp, x0s[b], traj, steps, dp, dc, dt)
+        assert np.abs(r["u_log"][:, b] - us).max() < 1e-8 and np.abs(r["x_log"][:, b] - xs).max() < 1e-8
+        assert np.abs(r["x"][b] - xf).max() < 1e-8
+    r0 = hs.closed_loop([hm], N, dt, traj, x0s, steps)
+    if dp != dc:                                                             # the delays do change the loop ...
+        assert np.abs(r["u_log"] - r0["u_log"]).max() > 1e-5
+    else:                                                                    # ... unless the compensation matches the plant delay exactly
+        assert np.abs(r["u_log"] - r0["u_log"]).max() < 1e-9                 #     (perfect model, no noise): the controller sees the undelayed loop
+
+
 @pytest.mark.parametrize("N,hv", [(40, 0), (10, 0), (100, 0), (40, 1), (55, 0)])
 def test_warp_kernel_is_independent_of_lane_scheduling(N, hv):
     """Racecheck substitute (compute-sanitizer is not available on the GPU pool): the warp emulator runs the lanes

@@ -46,7 +46,7 @@ class Ctrl(C.Structure):
 class LoopOpts(C.Structure):
     """qspush_loop_opts (include/qspush.h)."""
     _fields_ = [("idx0", C.c_int), ("noise_sigma", C.c_double * 4), ("seed", C.c_ulonglong), ("t_dist", C.c_int),
-                ("amplitude_dist", C.c_double), ("xwidth", C.c_double)]
+                ("amplitude_dist", C.c_double), ("xwidth", C.c_double), ("delay_plant", C.c_int), ("delay_comp", C.c_int)]
 
 
 # qspush_field / qspush_mem / qspush_mode / qspush_stat

@@ -289,13 +289,14 @@ class Solver:
         return x
 
     def closed_loop(self, traj, x, steps, offset=None, idx0=1, noise_sigma=(0.0, 0.0, 0.0, 0.0), seed=0, t_dist=0,
-                    amplitude_dist=0.0, xwidth=0.0, log=True):
+                    amplitude_dist=0.0, xwidth=0.0, log=True, delay_plant=0, delay_comp=0):
         """Device-resident closed loop (qspush_closed_loop; helper.closed_loop_matlab for the whole batch).
 
         traj (T,6) reference columns [x_ref; u_ref]; x (batch,4) initial plant state (updated in place); offset
         (batch,6) optional per-problem shift of the reference.  numpy arrays (host) or torch CUDA tensors (device, no
         host round trip at all); returns dict(x=final state, x_log (steps,batch,4), u_log (steps,batch,2),
-        status_log (steps,batch)) in the same memory space."""
+        status_log (steps,batch)) in the same memory space.  delay_plant / delay_comp: input delays in control periods
+        (helper.m:211, NMPC_controller.m:108); with delay_comp pass the padded reference and idx0 = 1 + delay_comp."""
         on_dev = torch is not None and isinstance(x, torch.Tensor) and x.is_cuda
         B = self.batch
         pt, mem_t, kt = _buf(traj)
@@ -322,6 +323,7 @@ class Solver:
         lo = L.LoopOpts()
         lo.idx0 = int(idx0); lo.seed = int(seed); lo.t_dist = int(t_dist)
         lo.amplitude_dist = float(amplitude_dist); lo.xwidth = float(xwidth)
+        lo.delay_plant = int(delay_plant); lo.delay_comp = int(delay_comp)
         for i in range(4):
             lo.noise_sigma[i] = float(noise_sigma[i])
         with self._Ordered(self, mem):

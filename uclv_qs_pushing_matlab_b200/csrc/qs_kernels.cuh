@@ -355,11 +355,11 @@ __global__ void __launch_bounds__(128) k_loop_state(SolverDev S, LoopDev L, int 
     if (b >= S.B) return;
     loop_state_one(S, L, Mall, step, xs, log_x, b);
 }
-__global__ void __launch_bounds__(128) k_loop_post(SolverDev S, double* xs, double* log_u, int* log_status) {
+__global__ void __launch_bounds__(128) k_loop_post(SolverDev S, LoopDev L, int step, double* xs, double* log_u, int* log_status) {
     const double* Mall = stage_models(S.models, S.nmodels);
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= S.B) return;
-    loop_post_one(S, Mall, xs, log_u, log_status, b);
+    loop_post_one(S, L, Mall, step, xs, log_u, log_status, b);
 }
 
 

@@ -710,6 +710,11 @@ struct LoopDev {
     int t_dist;             // 1-based step of the lateral shove (helper.m:222), 0 = none
     double amp, xwidth;     // amplitude_dist, slider_params.xwidth
     int single;             // MATLAB `single` rounding of mod(s, b) inside evalSpline
+    // input delays (helper.m:205-212, 244, 250, 290-298; NMPC_controller.m:106-120), in control periods; rings [slot][B][2],
+    // slot of the input of period j = (j - 1) mod d, zero-initialised (u_buff_plant / u_buff_contr start as zeros)
+    int dp, dc;             // delay_buff_plant = ceil(plant.time_delay / dt), delay_buff_comp = ceil(delay_compensation / dt)
+    double* ring_plant;     // [dp][B][2]
+    double* ring_contr;     // [dc][B][2]
 };
 
 // reference window of control period `idx` (1-based, NMPC_controller.m:307-313, 343-348): stage k uses column
@@ -784,22 +789,44 @@ QS_HD void loop_state_one(const SolverDev& S, const LoopDev& L, const double* __
         for (int i = 0; i < 4; ++i) x[i] += L.sigma[i] * loop_randn(L.seed, step, b, i);
     }
 #pragma unroll
+    for (int i = 0; i < 4; ++i) xs[(size_t)b * 4 + i] = x[i];
+    // controller.delay_buffer_sim (NMPC_controller.m:112-120): the state handed to the controller is the plant state rolled
+    // forward through the dc inputs already sent but not yet applied, oldest first (u_buff_contr(:, end - k + 1))
+    for (int k = 1; k <= L.dc; ++k) {
+        const int j = step - L.dc + k - 1;                                   // period whose input is applied k-th (<= 0: zeros)
+        const size_t slot = (size_t)(((j - 1) % L.dc + L.dc) % L.dc);
+        const double un = L.ring_contr[(slot * S.B + b) * 2], ut = L.ring_contr[(slot * S.B + b) * 2 + 1];
+        Dyn d;
+        dyn_eval<false>(M, x[2], x[3], un, ut, d);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = fma(S.dt, d.f[i], x[i]);
+    }
+#pragma unroll
     for (int i = 0; i < 4; ++i) {
-        xs[(size_t)b * 4 + i] = x[i];
         QS_EL(S.x0, i, b) = x[i];
         if (log_x) log_x[(size_t)b * 4 + i] = x[i];
     }
 }
 
 // end of the control period: u = get('u', 0) (NMPC_controller.m:403), forward-Euler plant step (helper.m:294, 307), logs
-QS_HD void loop_post_one(const SolverDev& S, const double* __restrict__ Mall, double* xs, double* log_u, int* log_status, int b) {
+QS_HD void loop_post_one(const SolverDev& S, const LoopDev& L, const double* __restrict__ Mall, int step, double* xs, double* log_u, int* log_status, int b) {
     const double* M = Mall + (size_t)S.objid[b] * MODEL_DOUBLES;
     const double un = QS_EL(S.u, 0, b), ut = QS_EL(S.u, 1, b);
+    if (L.dc > 0) {                                                          // helper.m:250  u_buff_contr = [u(:,i) u_buff_contr(:,1:end-1)]
+        const size_t slot = (size_t)((step - 1) % L.dc);
+        L.ring_contr[(slot * S.B + b) * 2] = un; L.ring_contr[(slot * S.B + b) * 2 + 1] = ut;
+    }
+    double ua_n = un, ua_t = ut;                                             // input that reaches the plant in this period
+    if (L.dp > 0) {                                                          // helper.m:294-298: u_buff_plant(:, end), then push u(:,i)
+        const size_t slot = (size_t)((step - 1) % L.dp);                     // slot of period step - dp = the oldest = the one overwritten
+        ua_n = L.ring_plant[(slot * S.B + b) * 2]; ua_t = L.ring_plant[(slot * S.B + b) * 2 + 1];
+        L.ring_plant[(slot * S.B + b) * 2] = un; L.ring_plant[(slot * S.B + b) * 2 + 1] = ut;
+    }
     double x[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) x[i] = xs[(size_t)b * 4 + i];
     Dyn d;
-    dyn_eval<false>(M, x[2], x[3], un, ut, d);
+    dyn_eval<false>(M, x[2], x[3], ua_n, ua_t, d);
 #pragma unroll
     for (int i = 0; i < 4; ++i) xs[(size_t)b * 4 + i] = fma(S.dt, d.f[i], x[i]);
     if (log_u) { log_u[(size_t)b * 2] = un; log_u[(size_t)b * 2 + 1] = ut; }

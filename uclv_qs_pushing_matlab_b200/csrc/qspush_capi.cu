@@ -877,6 +877,7 @@ int qspush_closed_loop(qspush_solver* s, const double* traj, int T, const double
                        const qspush_loop_opts* lo, double* log_x, double* log_u, int* log_status, qspush_mem mem) {
     if (!s || !traj || !x || !lo) return fail(QSPUSH_ERR_ARG, "NULL argument");
     if (T < 1 || steps < 1 || lo->idx0 < 1) return fail(QSPUSH_ERR_ARG, "closed loop: need T >= 1, steps >= 1, idx0 >= 1");
+    if (lo->delay_plant < 0 || lo->delay_comp < 0) return fail(QSPUSH_ERR_ARG, "closed loop: delays are counted in control periods, >= 0");
     CK(cudaSetDevice(s->device));
     const size_t B = (size_t)s->B;
     // device views of the caller arrays (host memory: staged once before and copied back once after the loop)
@@ -903,6 +904,15 @@ int qspush_closed_loop(qspush_solver* s, const double* traj, int T, const double
     for (int i = 0; i < 4; ++i) L.sigma[i] = lo->noise_sigma[i];
     L.seed = lo->seed; L.t_dist = lo->t_dist; L.amp = lo->amplitude_dist; L.xwidth = lo->xwidth;
     L.single = s->opts.matlab_single_quirk;
+    L.dp = lo->delay_plant; L.dc = lo->delay_comp; L.ring_plant = nullptr; L.ring_contr = nullptr;
+    for (int r = 0; r < 2; ++r) {                                // u_buff_plant / u_buff_contr start as zeros (helper.m:212, NMPC_controller.m:109)
+        const int d = r ? L.dc : L.dp;
+        if (d == 0) continue;
+        void* ring = nullptr;
+        CK(cudaMalloc(&ring, (size_t)d * B * 2 * sizeof(double))); tmp.p.push_back(ring);
+        CK(cudaMemsetAsync(ring, 0, (size_t)d * B * 2 * sizeof(double), s->stream));
+        (r ? L.ring_contr : L.ring_plant) = (double*)ring;
+    }
     const size_t msm = model_smem_bytes(s->nmodels);
     CK(cudaFuncSetAttribute(k_loop_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
     CK(cudaFuncSetAttribute(k_loop_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
@@ -918,7 +928,7 @@ int qspush_closed_loop(qspush_solver* s, const double* traj, int T, const double
         s->launches += 2;
         RET(qspush_prepare(s));
         RET(qspush_solve(s));
-        k_loop_post<<<pb, 128, msm, s->stream>>>(s->dev, (double*)d_x, lu, ls);
+        k_loop_post<<<pb, 128, msm, s->stream>>>(s->dev, L, i, (double*)d_x, lu, ls);
         CK(cudaGetLastError());
         s->launches++;
         RET(qspush_shift(s));

@@ -57,11 +57,13 @@ class helper:
         """helper.closed_loop_matlab (helper.m:195-322) for a whole batch WITHOUT host round trips: the loop of reference
         window -> prepare -> solve -> plant step -> shift runs on the GPU (qspush_closed_loop).  x0: (B,4) numpy array or
         torch CUDA tensor; the controller's reference (6,T) is shared by the batch, `offset` (B,6) shifts it per problem.
-        Input delays (plant.time_delay, controller.set_delay_comp) are only handled by closed_loop_matlab.
-        Returns (x_s, y_s, theta_s, s_s, u_n, u_t, time_sim_vec, found_sol) with a leading batch axis, in x0's memory space."""
-        if plant.time_delay or controller.delay_buff_comp:
-            raise NotImplementedError("input delays: use closed_loop_matlab")
+        Input delays (plant.time_delay, controller.set_delay_comp; helper.m:205-212, 244-250, 290-298) run on the device too.
+        Returns (x_s, y_s, theta_s, s_s, u_n, u_t, time_sim_vec, found_sol) with a leading batch axis, in x0's memory space;
+        the states are the ones handed to the controller (closed_loop_matlab's x_sim: the plant state rolled through the
+        delay-compensation buffer; the plant state itself when there is no compensation)."""
         dt = controller.sample_time
+        delay_plant = int(math.ceil(plant.time_delay / dt))                                       # helper.m:211
+        delay_comp = int(controller.delay_buff_comp)                                              # NMPC_controller.m:108
         time_sim_vec = np.arange(0.0, time_sim + 1e-12, dt)
         T = len(time_sim_vec)
         solver = controller.ocp_solver.solver
@@ -79,7 +81,7 @@ class helper:
         if controller._cold:
             solver.set_int("cold", np.ones(controller.batch, dtype=np.int32)); controller._cold = False
         sig = (1e-5, 1e-5, 1e-3, 1e-4) if sim_noise else (0.0, 0.0, 0.0, 0.0)                    # helper.m:241
-        r = solver.closed_loop(traj, x, T, offset=off, idx0=1, noise_sigma=sig, seed=seed,
+        r = solver.closed_loop(traj, x, T, offset=off, idx0=1 + delay_comp, noise_sigma=sig, seed=seed, delay_plant=delay_plant, delay_comp=delay_comp,
                                t_dist=(t_dist if disturbance_ and t_dist <= T else 0), amplitude_dist=amplitude_dist,
                                xwidth=plant.slider_params["xwidth"])
         xl, ul, st = r["x_log"], r["u_log"], r["status_log"]
