@@ -79,6 +79,26 @@ def _oracle_rti(mo, wl, N, **opts):
     return ocp, pr
 
 
+@pytest.mark.parametrize("name", ["santal", "pulirapid"])
+def test_x0_wrap_is_bit_exact_on_adversarial_contact_coordinates(name):
+    """x0(4) = mod(x0(4), b) - b (x0(4) < 0) (NMPC_controller.m:332) through the kernel's MATLAB-mod (with its fast path for
+    0 < |s| < b / 2) against the oracle's independent restatement of the builtin's algorithm: bit for bit on random, tiny,
+    half-period and seam-adjacent contact coordinates."""
+    mo, mh = oracle_model(name), hostsim_model(name)
+    b, rng, n, N = mo.b, np.random.default_rng(0), 4000, 2
+    s = np.concatenate([rng.uniform(-0.3, 0.3, n), rng.uniform(-1e-7, 1e-7, n), b * rng.integers(-3, 4, n) + rng.uniform(-1e-9, 1e-9, n),
+                        0.5 * b + rng.uniform(-1e-8, 1e-8, n), -0.5 * b + rng.uniform(-1e-8, 1e-8, n),
+                        [0.0, -0.0, 1e-40, -1e-40, 1e-320, 1e-31, -1e-31, 1e-29, -1e-29, 0.5 * b, -0.5 * b, float(np.float32(0.5 * b)), b, -b]])
+    B = len(s)
+    x0 = np.zeros((B, 4)); x0[:, 3] = s
+    u = np.zeros((B, N, 2)); u[:, :, 0] = 0.01
+    ocp = orc.Ocp(mo, N, 0.05)
+    pr = ocp.prepare(x0, np.zeros(B, dtype=np.int32), np.zeros((B, N + 1, 4)), u)
+    yref = np.zeros((B, N, 6))
+    qh = hs.solve([mh], N, 0.05, x0, yref, np.zeros((B, 4)), np.zeros((B, N + 1, 4)), u, mode="qp", prepare=True, qp_kernel=0)
+    assert np.array_equal(qh["x0"].view(np.uint64), pr["x0"].view(np.uint64))
+
+
 @pytest.mark.parametrize("qp_kernel", [1, 0], ids=["warp_scan", "thread"])
 @pytest.mark.parametrize("name,N", [("santal", 40), ("pulirapid", 10), ("balea", 100)])
 def test_prepare_linearise_qp_rti(name, N, qp_kernel):

@@ -93,8 +93,11 @@ QS_HD void curve_dd(const double* __restrict__ M, double sg, double& ex, double&
 // x / y is an integer within eps |x / y|, otherwise r += y when the signs differ.  The result can EQUAL y: for a tiny negative
 // x the sum rounds to y (in single precision for |x| < 1.5e-8 at b = 0.28), and x0(4) = mod(x0(4), b) - b (x0(4) < 0) is 0.
 QS_HD double matlab_mod(double s, double b, bool single) {
+    // Fast path, bit-identical to the algorithm below: for 0 < |x| < y / 2 fmod returns x itself, x / y is further than eps from
+    // every integer (the quotient cannot underflow above the 1e-30 / 1e-290 guard), so r = x (+ y when x < 0).  Every contact coordinate the controller meets lies there (|s| < 0.14 at b >= 0.22).
     if (single) {
         const float x = (float)s, y = (float)b;
+        { const float ax = fabsf(x); if (ax > 1e-30f && ax < 0.5f * y) return (double)(x < 0.f ? x + y : x); }
         if (y == 0.f) return (double)x;
         if (!(x == x) || !(y == y) || fabsf(x) == (float)INFINITY) return (double)NAN;
         if (x == 0.f) return (double)(0.f / y);
@@ -106,6 +109,7 @@ QS_HD double matlab_mod(double s, double b, bool single) {
         return (double)r;
     }
     const double x = s, y = b;
+    { const double ax = fabs(x); if (ax > 1e-290 && ax < 0.5 * y) return x < 0.0 ? x + y : x; }
     if (y == 0.0) return x;
     if (!(x == x) || !(y == y) || fabs(x) == (double)INFINITY) return (double)NAN;
     if (x == 0.0) return 0.0 / y;

@@ -17,7 +17,8 @@ namespace qs {
 // ------------------------------------------------------------------------------------------------
 // model staging: one bulk TMA copy global -> shared per CTA, completion on an mbarrier
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ const double* stage_models(const double* __restrict__ gmodels, int nmodels) {
+// Two halves so that a kernel can put model-independent work between the issue of the bulk copy and the wait for it.
+__device__ __forceinline__ void stage_models_issue(const double* __restrict__ gmodels, int nmodels) {
     extern __shared__ __align__(128) unsigned char qs_smem[];
     uint64_t* mbar = reinterpret_cast<uint64_t*>(qs_smem);
     double* dst = reinterpret_cast<double*>(qs_smem + 128);
@@ -36,12 +37,20 @@ __device__ __forceinline__ const double* stage_models(const double* __restrict__
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(dst_s), "l"(gmodels), "r"(bytes), "r"(mbar_s) : "memory");
     }
+}
+__device__ __forceinline__ const double* stage_models_wait() {
+    extern __shared__ __align__(128) unsigned char qs_smem[];
+    const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(qs_smem);
     uint32_t done = 0;
     while (!done) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(mbar_s), "r"(0u) : "memory");
     }
-    return dst;
+    return reinterpret_cast<const double*>(qs_smem + 128);
+}
+__device__ __forceinline__ const double* stage_models(const double* __restrict__ gmodels, int nmodels) {
+    stage_models_issue(gmodels, nmodels);
+    return stage_models_wait();
 }
 inline size_t model_smem_bytes(int nmodels) { return 128 + (size_t)nmodels * MODEL_DOUBLES * 8; }
 
@@ -390,18 +399,26 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* __restrict__ out, int
 // K6.  ONE kernel for both entry points (two instantiations of prepare_one were contracted differently by the compiler and
 // disagreed in the last bit): qspush_prepare passes x0 = nullptr / L.traj = nullptr and the kernel works on the slabs as set;
 // qspush_step passes the caller's [B][4] state and the device-resident reference trajectory.
-__global__ void __launch_bounds__(128) k_prepare(SolverDev S, CtrlDev cp, LoopDev L, const int* __restrict__ idx, const double* __restrict__ x0) {
-    const double* Mall = stage_models(S.models, S.nmodels);
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= S.B) return;
-    if (x0) {
+// 256 threads per 128 problems: threads 0..127 run the (serial, latency-bound) rollout of one problem each, threads 128..255 write
+// the reference window of the same problems meanwhile (r02: the window loop was 18 % and the wait for the model tables 10 % of
+// the kernel when one thread did everything in sequence).
+constexpr int PREP_PROBLEMS = 128;
+__global__ void __launch_bounds__(2 * PREP_PROBLEMS) k_prepare(SolverDev S, CtrlDev cp, LoopDev L, const int* __restrict__ idx, const double* __restrict__ x0) {
+    stage_models_issue(S.models, S.nmodels);
+    const int b = blockIdx.x * PREP_PROBLEMS + (threadIdx.x & (PREP_PROBLEMS - 1));
+    if (threadIdx.x >= PREP_PROBLEMS) {                         // window threads: no model needed
+        if (b < S.B && L.traj) {
+            const int i0 = *idx;
+            for (int k = 0; k < S.N; ++k) loop_window_one(S, L, i0, k, b);
+        }
+        return;
+    }
+    if (b < S.B && x0) {
         const double2 a = reinterpret_cast<const double2*>(x0)[2 * b], c = reinterpret_cast<const double2*>(x0)[2 * b + 1];
         QS_EL(S.x0, 0, b) = a.x; QS_EL(S.x0, 1, b) = a.y; QS_EL(S.x0, 2, b) = c.x; QS_EL(S.x0, 3, b) = c.y;
     }
-    if (L.traj) {
-        const int i0 = *idx;
-        for (int k = 0; k < S.N; ++k) loop_window_one(S, L, i0, k, b);
-    }
+    const double* Mall = stage_models_wait();
+    if (b >= S.B) return;
     prepare_one(S, cp, Mall, b);
 }
 __global__ void __launch_bounds__(1024) k_step_out(SolverDev S, double* __restrict__ u0, int* __restrict__ status, int* __restrict__ order) {

@@ -574,7 +574,7 @@ int qspush_prepare(qspush_solver* s) {
     if (!s) return fail(QSPUSH_ERR_ARG, "NULL solver");
     CK(cudaSetDevice(s->device));
     CK(rec_event(s, 4));
-    k_prepare<<<(s->B + 127) / 128, 128, model_smem_bytes(s->nmodels), s->stream>>>(s->dev, ctrl_dev(s), LoopDev{}, nullptr, nullptr);
+    k_prepare<<<(s->B + PREP_PROBLEMS - 1) / PREP_PROBLEMS, 2 * PREP_PROBLEMS, model_smem_bytes(s->nmodels), s->stream>>>(s->dev, ctrl_dev(s), LoopDev{}, nullptr, nullptr);
     CK(cudaGetLastError());
     CK(rec_event(s, 5));
     s->launches++;
@@ -817,7 +817,7 @@ int qspush_step(qspush_solver* s, const double* x0, int idx, unsigned flags, dou
             LoopDev L{};
             L.traj = s->d_ref_traj; L.off = s->d_ref_off; L.T = s->ref_T;
             rec_event(s, 4);
-            k_prepare<<<(unsigned)((B + 127) / 128), 128, msm, s->stream>>>(s->dev, ctrl_dev(s), L, s->d_idx, d_x0);
+            k_prepare<<<(unsigned)((B + PREP_PROBLEMS - 1) / PREP_PROBLEMS), 2 * PREP_PROBLEMS, msm, s->stream>>>(s->dev, ctrl_dev(s), L, s->d_idx, d_x0);
             rec_event(s, 5);
             s->launches++;
             rc = solve_impl(s, true);
