@@ -9,7 +9,6 @@ defaults and be repaired by exactly that flip.
 import glob
 import os
 
-import numpy as np
 import pytest
 
 from oracle import oracle as orc

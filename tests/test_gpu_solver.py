@@ -622,6 +622,32 @@ def test_closed_loop_input_delays_on_device(delay_plant, delay_comp):
     assert np.abs(np.transpose(h["u_log"], (1, 0, 2)) - ud).max() < 1e-8 and np.abs(np.transpose(h["x_log"], (1, 0, 2)) - xd).max() < 1e-8
 
 
+@pytest.mark.parametrize("qp_kernel", [1, 0], ids=["warp_scan", "thread"])
+def test_empty_single_and_poisoned_instances(qp_kernel):
+    """Edge cases of the batch: an empty batch is an argument error; a batch of one equals the same instance solved inside a
+    larger batch (instances are independent, whatever shares their warp); an instance with NaN input ends with a non-zero status
+    (acados: 1 = NaN) and leaves every other instance — its warp partner included — bit-identical to the clean run."""
+    gm, om = packaged_model_pair("santal")
+    N = 40
+    with pytest.raises(q.QspushError):
+        q.Solver([gm], N, 0.05, 0)
+    wl = make_rti_workload(None, batch=7, N=N, seed=11)
+    def run(sub, B):
+        s = q.Solver([gm], N, 0.05, B, qp_kernel=qp_kernel)
+        _load(s, sub); s.prepare(); s.solve()
+        return s.get("u"), s.get_int("status"), s.get_int("qp_iter")
+    u7, st7, it7 = run(wl, 7)
+    assert (st7 == 0).all()
+    one = {k: v[3:4] for k, v in wl.items()}
+    u1, st1, it1 = run(one, 1)
+    assert np.array_equal(u1[0], u7[3]) and st1[0] == 0 and it1[0] == it7[3]
+    bad = {k: v.copy() for k, v in wl.items()}
+    bad["x0"][2, 0] = np.nan                                          # instance 2 shares a warp with instance 3 (two problems per warp)
+    ub, stb, _ = run(bad, 7)
+    assert stb[2] != 0 and (np.delete(stb, 2) == 0).all()
+    assert np.array_equal(np.delete(ub, 2, axis=0), np.delete(u7, 2, axis=0))
+
+
 @pytest.mark.parametrize("N", [1, 7, 15, 16, 31, 32, 47, 48, 63, 64, 96, 127])
 def test_every_warp_mapping_vs_thread_kernel(N):
     """The warp QP kernel in every mapping (16- / 32-lane segments, C = 1..4, full and partial last lanes, odd batch:
