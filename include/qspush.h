@@ -61,8 +61,8 @@ typedef struct {
     int    h_variant;               /* constraint set h of the OCP: 0 = [s; u_n; u_t] (NMPC_controller.m:237, default);
                                        1 = the authors' parked set [u_n; u_t - v_bound(s); u_t + v_bound(s)] (:226-238) with
                                        v_bound from qspush_ctrl; selecting it resets constr_lh / constr_uh to
-                                       [u_n_lb, -2 u_t_ub, 0] / [u_n_ub(0.03), 0, 2 u_t_ub] (:247-248).  Needs the warp QP kernel
-                                       (N <= 127): qspush_solve fails with QSPUSH_ERR_ARG otherwise                          */
+                                       [u_n_lb, -2 u_t_ub, 0] / [u_n_ub(0.03), 0, 2 u_t_ub] (:247-248).  Both QP kernels
+                                       implement it (r02: the one-problem-per-thread kernel too, so any horizon)            */
     /* IPM end game (appended in r02; the fields above keep their offsets).  Complementarity is driven far below the other
      * residuals: multipliers of this QP are as small as 1e-9 (input weight 5e-5), so lam*t <= 1e-12 would leave du 1e-5 away
      * from the QP solution; at 1e-18 the returned point is within 1e-9 of it whatever path the IPM took. */

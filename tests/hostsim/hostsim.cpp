@@ -332,7 +332,6 @@ struct HostRun {
         cp = CtrlDev{ctrl5[0], ctrl5[1], ctrl5[2], ctrl5[3], ctrl5[4], opts_i[4]};
         single = opts_i[4];
         use_warp = opts_i[7] && qp_warp_chunk(N) <= 4;
-        if (S.h_variant && !use_warp) err = "h_variant 1 needs the warp QP kernel";
     }
     // AoS <-> SoA (k_aos_to_soa / k_soa_to_aos)
     void in(const double* src, std::vector<double>& dst, int R) { for (int b = 0; b < nb; ++b) for (int r = 0; r < R; ++r) dst[(size_t)r * Bp + b] = src[(size_t)b * R + r]; }

@@ -450,7 +450,7 @@ def test_open_loop_driver():
 def test_velocity_constraint_variant_vs_oracle():
     """h_variant 1 = the constraint set the authors parked in comments (NMPC_controller.m:226-238, :247-248):
     h = [u_n; u_t - v_bound(s); u_t + v_bound(s)], rows that couple ds and du_t.  k_linearise writes h and v_bound'(s),
-    the warp QP kernel solves the coupled QP; RTI and full SQP vs the oracle, error path of the thread kernel, and
+    the warp QP kernel solves the coupled QP; RTI and full SQP vs the oracle, the thread kernel (any horizon), and
     the NMPC_controller mirror option."""
     from tests.workloads import VARIANT_LH, VARIANT_UH, make_vbound_workload
     gm, om = packaged_model_pair("santal")
@@ -488,11 +488,17 @@ def test_velocity_constraint_variant_vs_oracle():
     u, x = s.get("u")[conv], s.get("x")[conv]
     vb = np.array([[ocp.v_bound_sym(sv)[0] for sv in row] for row in x[:, :N, 3]])
     assert (np.abs(u[:, :, 1]) <= vb + 1e-6).all()
-    # the thread-per-problem kernel implements h = [s; u_n; u_t] only
-    s0 = q.Solver([gm], N, 0.05, B, h_variant=1, qp_kernel=0)
-    _load(s0, wl); s0.prepare()
-    with pytest.raises(q.QspushError):
-        s0.solve()
+    # the one-problem-per-thread kernel carries the coupled rows too (r02), which opens the variant to horizons beyond the warp
+    # kernel's 127 stages: RTI vs the oracle at N = 10 (explicit kernel choice) and N = 130 (only the thread kernel fits)
+    for Nt, Bt, kern in ((10, 16, 0), (130, 12, 2)):
+        wlt = make_vbound_workload(Bt, Nt)
+        ocpt = orc.Ocp(om, Nt, 0.05); ocpt.set_h_variant(1)
+        prt = ocpt.prepare(wlt["x0"], np.zeros(Bt, dtype=np.int32), np.zeros((Bt, Nt + 1, 4)), wlt["u_init"])
+        rot = ocpt.solve("rti", prt["x0"], wlt["yref"], wlt["yref_e"], prt["x"], prt["u"], nthreads=8)
+        s0 = q.Solver([gm], Nt, 0.05, Bt, h_variant=1, qp_kernel=kern)
+        _load(s0, wlt); s0.prepare(); s0.solve()
+        assert (s0.get_int("status") == 0).all() and np.abs(s0.get_int("qp_iter") - rot["qp_iter"]).max() <= 2
+        assert np.abs(s0.get("u") - rot["u"]).max() < 1e-8 and rel_err(s0.get("cost"), rot["cost"]) < 1e-8
     # switching the set on an existing solver resets the bounds
     s.set_opts(h_variant=0)
     assert np.allclose(s.get("lh"), [-0.06, 0.0, -0.05]) and np.allclose(s.get("uh"), [0.011, 0.03, 0.05])

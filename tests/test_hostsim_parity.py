@@ -199,7 +199,7 @@ def test_full_sqp_iterates():
 def test_velocity_constraint_variant_vs_oracle(N):
     """h_variant 1: h = [u_n; u_t - v_bound(s); u_t + v_bound(s)] (the authors' parked constraint set,
     NMPC_controller.m:226-238): rows couple ds and du_t.  Warp-kernel bodies (emulated warp) vs the oracle for the QP,
-    one RTI step and full SQP; the thread-per-problem kernel refuses the variant."""
+    one RTI step and full SQP; the thread-per-problem kernel solves the same QP."""
     from tests.workloads import VARIANT_LH, VARIANT_UH, make_vbound_workload
     om, hm = oracle_model("santal"), hostsim_model("santal")
     B, dt = 16, 0.05
@@ -225,9 +225,13 @@ def test_velocity_constraint_variant_vs_oracle(N):
         # cost (1e-6) may stop elsewhere inside the convergence tolerance when a rounding-level change moves one line-search decision
         e = np.abs(r["u"][same] - so["u"][same]).max(axis=(1, 2))
         assert (e < 1e-8).mean() >= 0.9 and e.max() < 1e-5
-    import ctypes
-    with pytest.raises(Exception):
-        hs.solve([hm], N, dt, pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"], mode="qp", qp_kernel=0, **kw)
+    # the one-problem-per-thread kernel (any horizon) carries the coupled rows as well (r02)
+    rt = hs.solve([hm], N, dt, pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"], mode="qp", qp_kernel=0, **kw)
+    assert (rt["status"] == 0).all() and np.abs(rt["qp_iter"] - q["iters"]).max() <= 1
+    assert np.abs(rt["du"] - q["du"]).max() < 1e-9 and np.abs(rt["dx"] - q["dx"]).max() < 1e-9
+    assert np.abs(rt["qp_lam"] - q["lam"]).max() < 1e-7 * max(1.0, np.abs(q["lam"]).max())
+    rt = hs.solve([hm], N, dt, pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"], mode="rti", qp_kernel=0, **kw)
+    assert np.abs(rt["u"] - ro["u"]).max() < 1e-9 and rel_err(rt["cost"], ro["cost"]) < 1e-9
 
 
 def test_closed_loop_bodies_vs_oracle():
@@ -274,6 +278,21 @@ def test_closed_loop_bodies_vs_oracle():
     assert np.array_equal(ra["x_log"], rb["x_log"]) and not np.array_equal(ra["x_log"], rc["x_log"])
     d0 = ra["x_log"][0] - x0s
     assert 0 < np.abs(d0[:, 2]).max() < 6e-3 and np.abs(d0[:, 0]).max() < 6e-5
+
+
+def test_velocity_constraint_variant_long_horizon_thread_kernel():
+    """h_variant 1 beyond the warp kernel's 127 stages: the one-problem-per-thread kernel on N = 130 vs the oracle."""
+    from tests.workloads import VARIANT_LH, VARIANT_UH, make_vbound_workload
+    om, hm = oracle_model("santal"), hostsim_model("santal")
+    B, N, dt = 6, 130, 0.05
+    wl = make_vbound_workload(B, N)
+    ocp = orc.Ocp(om, N, dt); ocp.set_h_variant(1)
+    pr = ocp.prepare(wl["x0"], np.zeros(B, dtype=np.int32), np.zeros((B, N + 1, 4)), wl["u_init"])
+    q = ocp.qp(pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"])
+    r = hs.solve([hm], N, dt, pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"], mode="qp", h_variant=1, lh=VARIANT_LH, uh=VARIANT_UH)
+    assert (q["status"] == 0).all() and (r["status"] == 0).all() and np.abs(r["qp_iter"] - q["iters"]).max() <= 1
+    assert np.abs(r["du"] - q["du"]).max() < 1e-9 and np.abs(r["dx"] - q["dx"]).max() < 1e-9
+    assert (np.abs(q["lam"][:, 1:, [1, 2, 4, 5]]).max(axis=(1, 2)) > 1e-3).sum() >= B // 2     # the coupled rows are active
 
 
 def _delayed_loop_oracle(om, ocp, x0, traj, steps, dp, dc, dt):

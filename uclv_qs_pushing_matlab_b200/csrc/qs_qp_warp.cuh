@@ -537,18 +537,6 @@ QS_HD void qw_ld_it(const Ctx& w, int base, double* it8) { w.template tm_ld<8>(b
 // h_k (3 values) at the linearisation point and beta_k = v_bound'(s_k) (0 unless h_variant 1): 4 doubles
 template <class Ctx>
 QS_HD void qw_ld_h(const Ctx& w, int base, double* h4) { w.template tm_ld<4>(base + QW_TM_HH, h4); }
-// value of constraint row c on a stage vector z6 = [u_n, u_t, x, y, theta, s]
-// (the coupling term sits behind a warp-uniform branch: the default constraint set pays nothing for it)
-QS_HD double qw_row(int hv, int c, double beta, const double* z6) {
-    if (!hv) return z6[cidx(c)];
-    return z6[c == 0 ? 0 : 1] + h_bcoef(1, c, beta) * z6[5];
-}
-// scatter w * row c into a stage gradient
-QS_HD void qw_row_add(int hv, int c, double beta, double w, double* g6) {
-    if (!hv) { g6[cidx(c)] += w; return; }
-    g6[c == 0 ? 0 : 1] += w; g6[5] += h_bcoef(1, c, beta) * w;
-}
-
 // One Newton solve with the current factorisation: rhs gt (R_GT rows) and r_b (R_RB) ->
 // step dz (R_GT rows, aliased), costate offsets p_k (R_PV), feed-forward k_ff (R_KFF).
 template <class Ctx, int C, int SEG>

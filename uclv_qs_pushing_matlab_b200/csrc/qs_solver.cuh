@@ -267,7 +267,7 @@ QS_HD void qp_one(const SolverDev& S, const IpmOpts& o, int b, int apply) {
     C.N = S.N; C.H = S.H; C.QN = S.QN;
 #pragma unroll
     for (int i = 0; i < 3; ++i) { C.lh[i] = S.lh[i]; C.uh[i] = S.uh[i]; }
-    C.h_variant = 0;                           // the thread-per-problem kernel implements h = [s; u_n; u_t] only
+    C.h_variant = S.h_variant;
     C.max_iter = o.max_iter; C.tol = o.tol; C.mu0 = o.mu0; C.thr = o.thr; C.tau = o.tau;
     C.tol_cp = o.tol_cp; C.t_min = o.t_min; C.gamma_f = o.gamma_f; C.stall = o.stall;
     QpView V;

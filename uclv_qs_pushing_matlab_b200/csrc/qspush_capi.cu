@@ -609,7 +609,6 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
     const bool warp = want_warp && C <= 4 && W >= 2;
     if (!warp && s->opts.qp_kernel == 2 && s->opts.problems_per_warp == 0) ppw = (s->B >= 12288) ? 32 : ppw;
     if (!warp) {
-        if (D.h_variant) return fail(QSPUSH_ERR_ARG, "h_variant 1 needs the warp QP kernel (qp_kernel 1 or 2, N <= 127)");
         k_qp<<<(unsigned)((s->B + ppw - 1) / ppw), 32, 0, s->stream>>>(D, io, ppw, apply);
         return QSPUSH_OK;
     }
