@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(2 * PREP_PROBLEMS) k_prepare(SolverDev S, Ctrl
     prepare_one(S, cp, Mall, b);
 }
 __global__ void __launch_bounds__(1024) k_step_out(SolverDev S, double* __restrict__ u0, int* __restrict__ status, int* __restrict__ order) {
-    if (blockIdx.x + 1 == gridDim.x) { qp_order_cta(S, order); return; }   // last CTA: counting sort, descending previous iteration count
+    if (blockIdx.x + 1 == gridDim.x) { if (order) qp_order_cta(S, order); return; }   // last CTA: counting sort, descending previous iteration count
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= S.B) return;
     reinterpret_cast<double2*>(u0)[b] = make_double2(QS_EL(S.u, 0, b), QS_EL(S.u, 1, b));

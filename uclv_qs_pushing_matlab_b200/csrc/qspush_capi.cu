@@ -66,6 +66,7 @@ struct qspush_solver {
     int step_launches = 0;         // kernels inside one step graph
     bool capturing = false;        // the step graph is being captured
     bool order_valid = false;      // d_order holds a permutation (written by k_step_out / k_qp_order)
+    bool order_frozen = false;     // development aid (QSPUSH_DEV_ORDER builds): the order was set by the host and is kept
 };
 // phase events: plain records outside a capture; inside the capture of the step graph they must be EXTERNAL event-record
 // nodes (a plain cudaEventRecord on a capturing stream only creates a capture-internal dependency, not a timed event)
@@ -772,6 +773,18 @@ int qspush_measure_fp64_peak(int device, double* tflops) {
     return QSPUSH_OK;
 }
 
+#ifdef QSPUSH_DEV_ORDER
+// development aid (not part of the C-ABI): host-supplied work-queue order, kept until the solver is destroyed
+int qsdev_set_order(qspush_solver* s, const int* order) {
+    CK(cudaSetDevice(s->device));
+    CK(cudaMemcpyAsync(s->d_order, order, (size_t)s->B * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->order_valid = true; s->order_frozen = true;
+    drop_step_graphs(s);
+    return QSPUSH_OK;
+}
+#endif
+
 int qspush_snapshot_guess(qspush_solver* s) {
     if (!s) return fail(QSPUSH_ERR_ARG, "NULL solver");
     CK(cudaSetDevice(s->device));
@@ -821,7 +834,7 @@ int qspush_step(qspush_solver* s, const double* x0, int idx, unsigned flags, dou
             s->launches++;
             rc = solve_impl(s, true);
             if (rc != QSPUSH_OK) break;
-            k_step_out<<<(unsigned)((B + 1023) / 1024 + 1), 1024, 0, s->stream>>>(s->dev, d_u0, s->d_istage, s->d_order);
+            k_step_out<<<(unsigned)((B + 1023) / 1024 + 1), 1024, 0, s->stream>>>(s->dev, d_u0, s->d_istage, s->order_frozen ? nullptr : s->d_order);
             s->launches++;
             if (flags & QSPUSH_STEP_SHIFT) { dim3 grid((unsigned)((B + 127) / 128), 16); k_shift<<<grid, 128, 0, s->stream>>>(s->dev); s->launches++; }
         } while (0);
