@@ -850,7 +850,6 @@ QS_HD void qw_init(const Ctx& w, double* __restrict__ sm, const QpConst& Q, cons
 #pragma unroll
                 for (int i = 0; i < 4; ++i) QW_SM(R_Z + 2 + i, j) = V.dx0[i * V.stride];
             }
-#pragma unroll
             double z6[6];
 #pragma unroll
             for (int i = 0; i < 6; ++i) z6[i] = QW_SM(R_Z + i, j);
@@ -1287,7 +1286,6 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                 for (int i = 0; i < 4; ++i) QW_SM(R_PIK + i, j) = fma(alpha, dp[i] + QW_SM(R_PV + i, j), QW_SM(R_PIK + i, j));
             }
             if (k < N) {
-#pragma unroll
                 double z6[6];
 #pragma unroll
                 for (int i = 0; i < 6; ++i) z6[i] = QW_SM(R_Z + i, j);
