@@ -112,6 +112,40 @@ def replay(cases, lam_carry="keep", **sem):
     return out
 
 
+def replay_product(cases):
+    """The same replay through the PRODUCT (C-ABI, GPU), default semantics only: one batch-1 solver per configuration, the
+    recorded warm start set field by field like NMPC_controller.solve does (constr_x0, cost_y_ref per window, init_u / init_pi,
+    prepare, solve).  lam is whatever the solver keeps between solves, as in acados."""
+    import uclv_qs_pushing_matlab_b200 as q
+    from uclv_qs_pushing_matlab_b200.workloads import packaged_model
+    out, solvers, prev_group = [], {}, None
+    for c in cases:
+        Hp = c["Hp"]
+        key = (c["object"], Hp, float(c["dt"]), c["nlp"], c["W"].tobytes(), c["We"].tobytes(), c["lh"].tobytes(), c["uh"].tobytes())
+        if key not in solvers:
+            s = q.Solver([packaged_model(c["object"])], Hp, float(c["dt"]), 1, mode=0 if c["nlp"] == "sqp_rti" else 1)
+            for k in range(Hp):
+                s.set("W", np.asfortranarray(c["W"]), stage=k)
+            s.set("W", np.asfortranarray(c["We"]), stage=Hp)
+            s.set("lh", c["lh"]); s.set("uh", c["uh"])
+            solvers[key] = s
+        s = solvers[key]
+        yref, yref_e = _window(c)
+        s.set("x0", c["x0"][None]); s.set("yref", yref); s.set("yref_e", yref_e)
+        s.set_int("cold", np.array([1 if c["first_call"] else 0], dtype=np.int32))
+        if not c["first_call"]:
+            s.set("u", c["utraj_in"].T[None].copy()); s.set("pi", c["ptraj_in"].T[None].copy())
+        group = c["name"].rsplit("_", 1)[0]
+        if not ("_loop" in c["name"] and group == prev_group and not c["first_call"]):
+            s.set("lam", np.zeros((1, Hp, 6)))                   # independent solves start from zero multipliers like replay()
+        prev_group = group
+        s.prepare(); s.solve()
+        u, x, pi = s.get("u")[0], s.get("x")[0], s.get("pi")[0]
+        out.append(dict(u0=u[0].copy(), x=x.T.copy(), u=u.T.copy(), pi=pi.T.copy(), status=int(s.get_int("status")[0]),
+                        sqp_iter=int(s.get_int("sqp_iter")[0]), cost=float(s.get("cost")[0])))
+    return out
+
+
 def compare(cases, answers):
     """-> dict of worst-case disagreements over the cases acados solved (status 0) + integer agreement rates."""
     err = dict(u0=0.0, x=0.0, u=0.0, pi=0.0)

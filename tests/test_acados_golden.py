@@ -70,3 +70,25 @@ def test_bisector_names_the_flipped_semantic(tmp_path, nlp, flip):
         pytest.skip(f"{name}={val} is not observable on these cases (defaults reproduce the file)")
     assert rows[0][1] <= target[1], ag.report(rows)
     assert max(rows[0][2]["err_all"].values()) == 0.0, ag.report(rows)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not FILES, reason="PARITY UNPINNED: no acados golden vectors in tests/golden/acados/ (see test_oracle_vs_acados_golden)")
+@pytest.mark.parametrize("path", FILES or ["<none>"])
+def test_product_vs_acados_golden(path):
+    """The CUDA path itself (through the C-ABI) against the recorded acados solves: north_star's 1e-6 on u0 and the trajectories."""
+    cases = ag.load_cases(path)
+    cmp_ = ag.compare(cases, ag.replay_product(cases))
+    assert ag.passes(cmp_), f"product disagrees with acados on {os.path.basename(path)}: {cmp_}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nlp", ["sqp_rti", "sqp"])
+def test_product_replay_on_standin(tmp_path, nlp):
+    """The product-side replayer on an oracle-made stand-in (default semantics): u0, x, u within 1e-6 of the recorded solves,
+    every status equal — the same assertion test_product_vs_acados_golden makes once a real file exists."""
+    path = str(tmp_path / f"acados_golden_{nlp}.mat")
+    ag.save_cases(path, ag.make_standin(nlp, {}), nlp)
+    cases = ag.load_cases(path)
+    cmp_ = ag.compare(cases, ag.replay_product(cases))
+    assert ag.passes(cmp_), cmp_
