@@ -168,10 +168,11 @@ enum : int {
 // P_{k+1} r_b move to TMEM as well, the record shrinks to 59 rows (4 problems per SM at N = 100).
 QS_HD constexpr int qw_rows(int C) { return C >= 3 ? R_ROWS_LONG : R_ROWS; }
 // offsets (doubles) inside the TMEM block of one local stage
-// (linearisation 0..31, written once per problem; 32..47 rewritten every IPM iteration in phase (2): the slack
-// reciprocals 1/t_l, 1/t_u and the barrier diagonal D = lam_l/t_l + lam_u/t_u, reused by phases (4)-(8) — 30 FP64
+// (A, B 0..15, h 16..19 and b, g 32..43 are written once per problem; 20..31 are rewritten every IPM iteration in phase (2):
+// the slack reciprocals 1/t_l, 1/t_u and the barrier diagonal D = lam_l/t_l + lam_u/t_u, reused by phases (4)-(8) — 30 FP64
 // divisions per stage and iteration become 6; 48..63, long horizons only: P_k (10) and P_{k+1} r_b (4))
-enum : int { QW_TM_AB = 0, QW_TM_BV = 16, QW_TM_HH = 20, QW_TM_G = 24, QW_TM_IT = 32, QW_TM_D = 40, QW_TM_P = 48, QW_TM_STAGE = 48, QW_TM_STAGE_LONG = 64 };
+// r02: [h | 1/t | D] are one 16-double group (one tcgen05.ld / st where two or three were issued) and [b | g] another
+enum : int { QW_TM_AB = 0, QW_TM_HH = 16, QW_TM_IT = 20, QW_TM_D = 28, QW_TM_BV = 32, QW_TM_G = 36, QW_TM_P = 48, QW_TM_STAGE = 48, QW_TM_STAGE_LONG = 64 };
 QS_HD constexpr int qw_tm_stage(int C) { return C >= 3 ? QW_TM_STAGE_LONG : QW_TM_STAGE; }
 // Mapping of a horizon onto a warp.  seg = 16: two problems per warp, one per 16-lane segment, each lane owning
 // C = ceil((N+1)/16) stages; seg = 32: one problem per warp, C = ceil((N+1)/32).  Measured on B200 (tools/gpu_half_sweep.py):
@@ -537,6 +538,16 @@ QS_HD void qw_ld_it(const Ctx& w, int base, double* it8) { w.template tm_ld<8>(b
 // h_k (3 values) at the linearisation point and beta_k = v_bound'(s_k) (0 unless h_variant 1): 4 doubles
 template <class Ctx>
 QS_HD void qw_ld_h(const Ctx& w, int base, double* h4) { w.template tm_ld<4>(base + QW_TM_HH, h4); }
+// h_k / beta_k (4) and the slack reciprocals (8) with ONE load of the [h | 1/t | D] group
+template <class Ctx>
+QS_HD void qw_ld_hit(const Ctx& w, int base, double* h4, double* it8) {
+    double v[16];
+    w.template tm_ld<16>(base + QW_TM_HH, v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h4[i] = v[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) it8[i] = v[4 + i];
+}
 // One Newton solve with the current factorisation: rhs gt (R_GT rows) and r_b (R_RB) ->
 // step dz (R_GT rows, aliased), costate offsets p_k (R_PV), feed-forward k_ff (R_KFF).
 template <class Ctx, int C, int SEG>
@@ -821,9 +832,9 @@ QS_HD void qw_init(const Ctx& w, double* __restrict__ sm, const QpConst& Q, cons
     for (int j = 0; j < C; ++j) {
         const int k = lane * C + j;
         const bool on = act && k < N;
-        double v[32];
+        double v[48];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.0;
+        for (int i = 0; i < 48; ++i) v[i] = 0.0;
         if (act && k <= N) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) QW_SM(R_Z + i, j) = 0.0;
@@ -844,6 +855,7 @@ QS_HD void qw_init(const Ctx& w, double* __restrict__ sm, const QpConst& Q, cons
         }
         w.tm_st16(j * qw_tm_stage(C), v);                      // warp-collective: every lane stores (zeros when idle)
         w.tm_st16(j * qw_tm_stage(C) + 16, v + 16);
+        w.tm_st16(j * qw_tm_stage(C) + 32, v + 32);
         if (on) {
             const double* h = v + QW_TM_HH;
             if (k == 0) {
@@ -912,9 +924,15 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             StageLin L;
             double gk[8], hk[4], bv[4];
             qw_ld_lin(w, j * qw_tm_stage(C), L);
-            w.template tm_ld<8>(j * qw_tm_stage(C) + QW_TM_G, gk);
+            {
+                double bg[16];                                  // [b | g] group
+                w.template tm_ld<16>(j * qw_tm_stage(C) + QW_TM_BV, bg);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) bv[i] = bg[i];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) gk[i] = bg[4 + i];
+            }
             w.template tm_ld<4>(j * qw_tm_stage(C) + QW_TM_HH, hk);
-            w.template tm_ld<4>(j * qw_tm_stage(C) + QW_TM_BV, bv);
             if (!act || k > N) continue;
             double z6[6], pik[4];
 #pragma unroll
@@ -1021,8 +1039,14 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
 #pragma unroll
                 for (int i = 0; i < 6; ++i) QW_SM(R_GT + i, j) = gt[i];
             }
-            w.template tm_st<8>(j * qw_tm_stage(C) + QW_TM_IT, it8);
-            w.template tm_st<4>(j * qw_tm_stage(C) + QW_TM_D, D);
+            {
+                double hid[16];                                 // [h | 1/t | D] group in one store (h unchanged)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { hid[i] = hk[i]; hid[12 + i] = D[i]; }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) hid[4 + i] = it8[i];
+                w.tm_st16(j * qw_tm_stage(C) + QW_TM_HH, hid);
+            }
             if (!act || k > N) continue;
             if (k == N) {                                   // terminal value function: J = Q_N, A = 0, C = 0
 #pragma unroll
@@ -1173,8 +1197,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
             for (int j = 0; j < C; ++j) {
                 const int k = lane * C + j;
                 double hk[4], it8[8];
-                qw_ld_h(w, j * qw_tm_stage(C), hk);
-                qw_ld_it(w, j * qw_tm_stage(C), it8);
+                qw_ld_hit(w, j * qw_tm_stage(C), hk, it8);
                 if (!act || k >= N) continue;
                 double gt[6], z6[6];
 #pragma unroll
@@ -1205,8 +1228,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                 for (int j = 0; j < C; ++j) {
                     const int k = lane * C + j;
                     double hk[4], it8[8];
-                    qw_ld_h(w, j * qw_tm_stage(C), hk);
-                    qw_ld_it(w, j * qw_tm_stage(C), it8);
+                    qw_ld_hit(w, j * qw_tm_stage(C), hk, it8);
                     if (!act || k >= N) continue;
                     double z6[6], dz6[6];
 #pragma unroll
@@ -1243,8 +1265,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
         for (int j = 0; j < C; ++j) {
             const int k = lane * C + j;
             double hk[4], it8[8];
-            qw_ld_h(w, j * qw_tm_stage(C), hk);
-            qw_ld_it(w, j * qw_tm_stage(C), it8);
+            qw_ld_hit(w, j * qw_tm_stage(C), hk, it8);
             if (!act || k >= N) continue;
             double z6[6], dz6[6];
 #pragma unroll
@@ -1270,8 +1291,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
         for (int j = 0; j < C; ++j) {
             const int k = lane * C + j;
             double hk[4], it8[8], Pst[16];
-            qw_ld_h(w, j * qw_tm_stage(C), hk);
-            qw_ld_it(w, j * qw_tm_stage(C), it8);
+            qw_ld_hit(w, j * qw_tm_stage(C), hk, it8);
             if constexpr (C >= 3) w.template tm_ld<16>(j * qw_tm_stage(C) + QW_TM_P, Pst);
             if (!act || k > N) continue;
             double dz[6];

@@ -62,6 +62,8 @@ struct qspush_solver {
     // qspush_step: one CUDA graph per flag combination (captured on first use, dropped when options / cost / bounds change)
     cudaGraphExec_t step_exec[4] = {nullptr, nullptr, nullptr, nullptr};
     double* d_guess = nullptr;     // qspush_snapshot_guess: copy of the u slab
+    double* d_ring[2] = {nullptr, nullptr};   // qspush_closed_loop input-delay rings (plant, controller), kept between calls
+    size_t ring_doubles[2] = {0, 0};
     int* d_idx = nullptr;          // reference index of the current period (read by k_step_prepare)
     int step_launches = 0;         // kernels inside one step graph
     bool capturing = false;        // the step graph is being captured
@@ -396,6 +398,7 @@ void qspush_solver_free(qspush_solver* s) {
     if (s->h_ndone) cudaFreeHost(s->h_ndone);
     drop_step_graphs(s);
     if (s->d_guess) cudaFree(s->d_guess);
+    for (double* r : s->d_ring) if (r) cudaFree(r);
     if (s->d_idx) cudaFree(s->d_idx);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -920,10 +923,14 @@ int qspush_closed_loop(qspush_solver* s, const double* traj, int T, const double
     for (int r = 0; r < 2; ++r) {                                // u_buff_plant / u_buff_contr start as zeros (helper.m:212, NMPC_controller.m:109)
         const int d = r ? L.dc : L.dp;
         if (d == 0) continue;
-        void* ring = nullptr;
-        CK(cudaMalloc(&ring, (size_t)d * B * 2 * sizeof(double))); tmp.p.push_back(ring);
-        CK(cudaMemsetAsync(ring, 0, (size_t)d * B * 2 * sizeof(double), s->stream));
-        (r ? L.ring_contr : L.ring_plant) = (double*)ring;
+        const size_t need = (size_t)d * B * 2;                   // owned by the solver: the call stays asynchronous in device-memory mode
+        if (s->ring_doubles[r] < need) {
+            if (s->d_ring[r]) { CK(cudaStreamSynchronize(s->stream)); cudaFree(s->d_ring[r]); s->d_ring[r] = nullptr; s->ring_doubles[r] = 0; }
+            CK(cudaMalloc(&s->d_ring[r], need * sizeof(double)));
+            s->ring_doubles[r] = need;
+        }
+        CK(cudaMemsetAsync(s->d_ring[r], 0, need * sizeof(double), s->stream));
+        (r ? L.ring_contr : L.ring_plant) = s->d_ring[r];
     }
     const size_t msm = model_smem_bytes(s->nmodels);
     CK(cudaFuncSetAttribute(k_loop_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
