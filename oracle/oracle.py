@@ -197,7 +197,7 @@ DEFAULT_OPTS = dict(
     qp_tol_comp=1e-18, qp_t_min=1e-12, qp_gamma_f=0.01, qp_stall=10,
     # recalled acados semantics as switches (qs_oracle.hpp); defaults = what the restatement believes
     sem_cost_scale=0, sem_h0_s_row=0, sem_full_step_dual=0, sem_merit_weights=0, sem_armijo=0, sem_erk_steps=1,
-    sem_qp_maxiter_fails=0, sem_mod_strict=0, sem_qp_pivot_fails=0,
+    sem_qp_maxiter_fails=0, sem_mod_strict=0, sem_qp_pivot_fails=0, qp_split_step=1,
 )
 SEMANTIC_SWITCHES = {          # name -> the alternatives to try when acados golden vectors disagree
     "sem_cost_scale": (1, 2), "sem_h0_s_row": (1,), "sem_full_step_dual": (1,), "sem_merit_weights": (1, 2), "sem_armijo": (1,),

@@ -144,6 +144,7 @@ struct OcpOpts {
     double qp_t_min = 1e-12;           // slack floor: pairs with t <= 4 t_min count as converged, their centering target is lam * t_min (bounds lam / t)
     double qp_gamma_f = 0.01;          // step to the boundary: blocking pair keeps gamma_f * (predicted mu reduction) of its value
     int    qp_stall = 10;              // iterations without halving the normalised residual before a point below 1e-6 is accepted
+    int    qp_split_step = 1;          // 1: separate primal / dual step lengths (r02); 0: one step length for both (r01)
     // ---- RECALLED acados v0.2.1 semantics as switches (none of it could be run here).  The defaults are
     // what the restatement believes; when golden vectors from a real acados run (tools/acados_golden.m) disagree,
     // tests/test_acados_golden.py flips these one at a time and reports which flip removes the mismatch.

@@ -257,7 +257,7 @@ def test_qp_solution_sensitivity_to_tolerance_is_documented_behaviour():
     wl = make_rti_workload(None, batch=B, N=N, seed=2)
     pr = orc.Ocp(om, N, 0.05).prepare(wl["x0"], np.zeros(B, dtype=np.int32), np.zeros((B, N + 1, 4)), wl["u_init"])
     args = (pr["x0"], wl["yref"], wl["yref_e"], pr["x"], pr["u"])
-    r01 = dict(qp_t_min=0.0, qp_gamma_f=0.0, qp_stall=5)
+    r01 = dict(qp_t_min=0.0, qp_gamma_f=0.0, qp_stall=5, qp_split_step=0)
     ref = orc.Ocp(om, N, 0.05).qp(*args, nthreads=4)
     loose = orc.Ocp(om, N, 0.05, qp_tol=1e-6, qp_tol_comp=1e-6, **r01).qp(*args, nthreads=4)
     assert np.abs(loose["du"] - ref["du"]).max() > 1e-3

@@ -166,7 +166,7 @@ def test_round1_stopping_rule_was_not_exact():
     away from the exact solution on a sizeable fraction of the problems — the two implementations agreed with each other
     more than with the QP."""
     om, ocp, wl, pr, args = qp_case("santal", 40, 64)
-    old = orc.Ocp(om, 40, 0.05, qp_tol=1e-12, qp_tol_comp=1e-12, qp_t_min=0.0, qp_gamma_f=0.0, qp_stall=5).qp(*args, nthreads=8)
+    old = orc.Ocp(om, 40, 0.05, qp_tol=1e-12, qp_tol_comp=1e-12, qp_t_min=0.0, qp_gamma_f=0.0, qp_stall=5, qp_split_step=0).qp(*args, nthreads=8)
     d, ex = exact_solution(ocp, args, old)
     e_old = np.abs(old["du"] - ex["du"]).reshape(64, -1).max(1)
     e_new = np.abs(ocp.qp(*args, nthreads=8)["du"] - ex["du"]).reshape(64, -1).max(1)

@@ -1259,7 +1259,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
     }
     QW_TICK(7);
     // ================= (8) step length and update =================
-    double a_max = 1.0, m_num = 1.0, m_den = 1.0;
+    double m_num = 1.0, m_den = 1.0, l_num = 1.0, l_den = 1.0;         // ratio tests: slacks (primal step) / multipliers (dual step)
     {
 #pragma unroll 1
         for (int j = 0; j < C; ++j) {
@@ -1277,13 +1277,14 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                                         QW_SM(R_LAM + c, j), QW_SM(R_LAM + 3 + c, j), QW_SM(R_T + c, j), QW_SM(R_T + 3 + c, j),
                                         it8[c], it8[4 + c], Q.lh[c] - hk[c], Q.uh[c] - hk[c], smu, Q.t_min);
                 ratio_min(QW_SM(R_T + c, j), s_.dtl, m_num, m_den); ratio_min(QW_SM(R_T + 3 + c, j), s_.dtu, m_num, m_den);
-                ratio_min(QW_SM(R_LAM + c, j), s_.dll, m_num, m_den); ratio_min(QW_SM(R_LAM + 3 + c, j), s_.dlu, m_num, m_den);
+                ratio_min(QW_SM(R_LAM + c, j), s_.dll, l_num, l_den); ratio_min(QW_SM(R_LAM + 3 + c, j), s_.dlu, l_num, l_den);
             }
         }
     }
-    a_max = w.template wmin<SEG>(fmin(a_max, m_num / m_den));
-    const double alpha = qp_step_length(Q, a_max, smu, mu);
-    if (!(alpha == alpha) && !st.fin) { status = 2; st.fin = true; }
+    const double a_p = w.template wmin<SEG>(fmin(1.0, m_num / m_den)), a_d = w.template wmin<SEG>(fmin(1.0, l_num / l_den));
+    double alpha, alpha_d;
+    qp_step_lengths(Q, a_p, a_d, smu, mu, alpha, alpha_d);
+    if ((!(alpha == alpha) || !(alpha_d == alpha_d)) && !st.fin) { status = 2; st.fin = true; }
     if (!w.wany(st.fin ? 0 : 1)) return 1;
     act = act && !st.fin;
     {
@@ -1303,7 +1304,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                 for (int i = 0; i < 10; ++i) { if constexpr (C >= 3) Pk[i] = Pst[i]; else Pk[i] = QW_SM(R_P + i, j); }
                 sym4_mul(Pk, dxk, dp);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) QW_SM(R_PIK + i, j) = fma(alpha, dp[i] + QW_SM(R_PV + i, j), QW_SM(R_PIK + i, j));
+                for (int i = 0; i < 4; ++i) QW_SM(R_PIK + i, j) = fma(alpha_d, dp[i] + QW_SM(R_PV + i, j), QW_SM(R_PIK + i, j));
             }
             if (k < N) {
                 double z6[6];
@@ -1317,8 +1318,8 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
                                             it8[c], it8[4 + c], Q.lh[c] - hk[c], Q.uh[c] - hk[c], smu, Q.t_min);
                     QW_SM(R_T + c, j) = fma(alpha, s_.dtl, QW_SM(R_T + c, j));
                     QW_SM(R_T + 3 + c, j) = fma(alpha, s_.dtu, QW_SM(R_T + 3 + c, j));
-                    QW_SM(R_LAM + c, j) = fma(alpha, s_.dll, QW_SM(R_LAM + c, j));
-                    QW_SM(R_LAM + 3 + c, j) = fma(alpha, s_.dlu, QW_SM(R_LAM + 3 + c, j));
+                    QW_SM(R_LAM + c, j) = fma(alpha_d, s_.dll, QW_SM(R_LAM + c, j));
+                    QW_SM(R_LAM + 3 + c, j) = fma(alpha_d, s_.dlu, QW_SM(R_LAM + 3 + c, j));
                 }
             }
 #pragma unroll
