@@ -68,7 +68,8 @@ typedef struct {
      * from the QP solution; at 1e-18 the returned point is within 1e-9 of it whatever path the IPM took. */
     double qp_tol_comp;             /* tolerance on max lam * t (1e-18)                                        */
     double qp_t_min;                /* slack floor (1e-12): pairs with t <= 4 t_min count as converged, centering target lam * t_min */
-    double qp_gamma_f;              /* step to the boundary: blocking pair keeps gamma_f * predicted mu reduction (0.01; 0 = fixed qp_tau) */
+    double qp_gamma_f;              /* step to the boundary: blocking pair keeps gamma_f * predicted mu reduction (0.01; 0 = fixed qp_tau);
+                                       primal (z, t) and dual (pi, lam) steps go to their own boundaries with that fraction            */
     int    qp_stall;                /* iterations without halving the normalised residual before a point below 1e-6 is accepted (10) */
 } qspush_opts;
 
