@@ -1335,7 +1335,7 @@ QS_HD int qw_iterate(const Ctx& w, double* __restrict__ sm, const QpConst& Q, Qw
 
 // ---- write the point back to the slabs: V.z (du, dx), V.pi (pi[k] = pi_{k+1}), V.lam, V.t
 template <class Ctx, int C, int SEG>
-QS_HD void qw_writeback(const Ctx& w, double* __restrict__ sm, const QpConst& Q, const QpView& V, bool live) {
+QS_HD void qw_writeback(const Ctx& w, double* __restrict__ sm, const QpConst& Q, const QpView& V, bool live, bool step_and_slacks = true) {
     const int N = Q.N;
     const int lane = w.lane() & (SEG - 1);
     const int Lw_ = qp_warp_lanes(N, C);
@@ -1346,15 +1346,17 @@ QS_HD void qw_writeback(const Ctx& w, double* __restrict__ sm, const QpConst& Q,
         for (int j = 0; j < C; ++j) {
             const int k = lane * C + j;
             if (k > N) continue;
+            if (step_and_slacks) {                          // (du, dx): read by the SQP-level kernels only; the RTI epilogue applies it from shared memory
 #pragma unroll
-            for (int i = 0; i < 6; ++i) QS_AT(V.z, k, 6, i) = QW_SM(R_Z + i, j);
+                for (int i = 0; i < 6; ++i) QS_AT(V.z, k, 6, i) = QW_SM(R_Z + i, j);
+            }
             if (k >= 1) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) QS_AT(V.pi, k - 1, 4, i) = QW_SM(R_PIK + i, j);
             }
             if (k < N) {
 #pragma unroll
-                for (int i = 0; i < 6; ++i) { QS_AT(V.lam, k, 6, i) = QW_SM(R_LAM + i, j); QS_AT(V.t, k, 6, i) = QW_SM(R_T + i, j); }
+                for (int i = 0; i < 6; ++i) { QS_AT(V.lam, k, 6, i) = QW_SM(R_LAM + i, j); if (step_and_slacks) QS_AT(V.t, k, 6, i) = QW_SM(R_T + i, j); }
             }
         }
     }

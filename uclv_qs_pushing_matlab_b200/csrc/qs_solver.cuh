@@ -384,7 +384,7 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm_warp, int pe
                 }
             }
         }
-        qw_writeback<Ctx, C, SEG>(w, sm, Qc, V, live);
+        qw_writeback<Ctx, C, SEG>(w, sm, Qc, V, live, apply == 0);      // RTI: the step and the slacks stay on chip (12 of 28 doubles per stage not stored)
         if (live && lane == 0) {
             S.qpstat[b] = st.status;
             if (apply) S.qp_iter[b] = st.it; else S.qp_iter[b] += st.it;
