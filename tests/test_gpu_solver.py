@@ -246,6 +246,12 @@ def test_config3_full_size_properties():
     assert u[:, :, 0].min() > -1e-9 and u[:, :, 0].max() < 0.03 + 1e-9 and np.abs(u[:, :, 1]).max() < 0.05 + 1e-9
     assert x[:, 1:N, 3].min() > -0.06 - 1e-9 and x[:, 1:N, 3].max() < 0.011 + 1e-9     # h is constrained at k = 1..N-1 (nothing at k = N)
     assert np.array_equal(x[:, 0], s.get("x0"))                     # x_0 + dx_0 = x0bar exactly
+    # the oracle on ALL 4096 problems: whole predicted trajectory, status and IPM iteration count of every instance
+    ocp_all, pr_all = _oracle_prepared(om, wl, N)
+    ra = ocp_all.solve("rti", pr_all["x0"], wl["yref"], wl["yref_e"], pr_all["x"], pr_all["u"], nthreads=16)
+    assert np.abs(u[:, 0] - ra["u"][:, 0]).max() < 1e-8             # u0 (north_star: 1e-6), 100 % of the batch
+    assert np.abs(u - ra["u"]).max() < 1e-8 and np.abs(x - ra["x"]).max() < 1e-8
+    assert np.array_equal(st, ra["status"]) and np.abs(it - ra["qp_iter"]).max() <= 2 and (it == ra["qp_iter"]).mean() > 0.9
     idx = np.arange(0, B, 64)
     sub = {k: v[idx] for k, v in wl.items()}
     ocp, pr = _oracle_prepared(om, sub, N)
@@ -278,6 +284,13 @@ def test_config4_gpu_share_properties():
     assert x[:, 1:N, 3].min() > -0.06 - 1e-9 and x[:, 1:N, 3].max() < 0.011 + 1e-9
     assert np.array_equal(x[:, 0], s.get("x0"))
     for o in range(4):
+        # the oracle on EVERY problem of the shape's bucket (2048 each): whole predicted trajectory and status
+        ia = np.where(wl["object_id"] == o)[0]
+        wa = {k: v[ia] for k, v in wl.items()}
+        ocp_a, pr_a = _oracle_prepared(oms[o], wa, N)
+        ra = ocp_a.solve("rti", pr_a["x0"], wa["yref"], wa["yref_e"], pr_a["x"], pr_a["u"], nthreads=16)
+        assert np.abs(u[ia] - ra["u"]).max() < 1e-8 and np.abs(x[ia] - ra["x"]).max() < 1e-8, names[o]
+        assert np.array_equal(st[ia], ra["status"]), names[o]
         idx = np.where(wl["object_id"] == o)[0][::64]
         sub = {k: v[idx] for k, v in wl.items()}
         ocp, pr = _oracle_prepared(oms[o], sub, N)
