@@ -17,6 +17,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "mex.h"
 #include "qspush.h"
@@ -141,6 +142,8 @@ static double matlab_mod_single(double s, double b) {
 }
 
 /* helper.closed_loop_matlab over NMPC_controller.solve; rec: steps x 10 = [x(4), u0(2), status, sqp_iter, cost, wrapped s] */
+static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec; }
+
 static void closed_loop(backend* b, const qspush_model* plant, double bb, int N, double dt, int steps, int T, const double* yref, double* rec) {
     qspush_ctrl cc;
     qspush_ctrl_default(&cc);
@@ -221,7 +224,9 @@ int main(int argc, char** argv) {
 
     backend A; memset(&A, 0, sizeof A); A.use_mex = 1; A.N = N;
     ocp_new(&A.ocp, ply, 0, mu_sg, mu_sp, mass, tau_max, N, dt, mode ? "sqp" : "sqp_rti");
+    const double tA0 = now_s();
     closed_loop(&A, plant, bb, N, dt, steps, T, yref, recA);
+    const double tA = now_s() - tA0;
     /* single-stage field with an explicit stage through the raw gateway (what an older qspush_ocp.m sent): accepted */
     { mxArray* v = mat(yref, 4, 1); mex(0, NULL, 5, S_("set"), A.ocp.s, D_(2), D_(N), v, NULL, NULL, NULL); mxDestroyArray(v); }
     { mxArray* t = ocp_get(&A.ocp, "time_tot", 1, 0); if (!(mxGetScalar(t) > 0.0)) { fprintf(stderr, "time_tot not positive\n"); return 6; } mxDestroyArray(t); }
@@ -233,7 +238,9 @@ int main(int argc, char** argv) {
     qspush_opts o; qspush_opts_default(&o); o.mode = mode;                                         /* what the gateway's solver_create sets */
     const qspush_model* mm = mB;
     CHK(qspush_solver_create(&mm, 1, N, dt, 1, 0, &o, &B.s));
+    const double tB0 = now_s();
     closed_loop(&B, plant, bb, N, dt, steps, T, yref, recB);
+    const double tB = now_s() - tB0;
     qspush_solver_free(B.s); qspush_model_free(mB);
 
     const int same = memcmp(recA, recB, sizeof(double) * (size_t)steps * 10) == 0;
@@ -244,6 +251,8 @@ int main(int argc, char** argv) {
     fclose(fo);
     printf("mex_replay: %d periods through mexFunction, %s the direct C-ABI run; final x = %.6f m, status(last) = %d\n", steps,
            same ? "bit-identical to" : "DIFFERENT from", recA[(size_t)(steps - 1) * 10], (int)recA[(size_t)(steps - 1) * 10 + 6]);
+    printf("mex_replay: wall time per control period (host rollout through qspush_eval_*, %d field calls, solve, gets): %.3f ms through mexFunction, %.3f ms through the C-ABI\n",
+           N + 12, 1e3 * tA / steps, 1e3 * tB / steps);
     qspush_model_free(plant);
     free(yref); free(recA); free(recB);
     return same ? 0 : 6;

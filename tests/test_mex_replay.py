@@ -24,7 +24,7 @@ def _exe():
     deps = SRCS + [os.path.join(ROOT, "tests", "stubs", "mex.h"), os.path.join(ROOT, "include", "qspush.h")]
     if not os.path.exists(EXE) or max(os.path.getmtime(p) for p in deps) > os.path.getmtime(EXE):
         lib = os.path.join(ROOT, "uclv_qs_pushing_matlab_b200")
-        subprocess.check_call(["gcc", "-O1", "-std=c99", "-Wall", "-I" + os.path.join(ROOT, "tests", "stubs"), "-I" + os.path.join(ROOT, "include"), *SRCS,
+        subprocess.check_call(["gcc", "-O1", "-std=gnu99", "-Wall", "-I" + os.path.join(ROOT, "tests", "stubs"), "-I" + os.path.join(ROOT, "include"), *SRCS,
                                "-L" + lib, "-lqspush", "-Wl,-rpath," + lib, "-Wl,-rpath,$ORIGIN/../uclv_qs_pushing_matlab_b200", "-lm", "-o", EXE])
     return EXE
 
