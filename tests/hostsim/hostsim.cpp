@@ -142,6 +142,7 @@ struct WarpCtxHost {
     }
     void sync() const { exchange(0.0); }
     bool cta_all(bool pred) const { return pred; }      // one emulated warp per CTA
+    bool lockstep() const { return false; }
     // tensor-memory block of the lane (tcgen05.ld / tcgen05.st on the device; warp-collective there, so the emulator
     // makes them collectives too: a lane that skips one deadlocks the emulated warp instead of passing silently)
     template <int n> void tm_ld(int off, double* v) const { sync(); for (int i = 0; i < n; ++i) v[i] = g_emu->tm[lane_][off + i]; }

@@ -246,7 +246,7 @@ __device__ __forceinline__ void qp_order_cta(const SolverDev& S, int* __restrict
 }
 __global__ void __launch_bounds__(1024) k_qp_order(SolverDev S, int* __restrict__ order) { qp_order_cta(S, order); }
 template <int C, int HV, int SEG>
-__global__ void __launch_bounds__(32 * QW_MAX_WARPS, 1) k_qp_warp(SolverDev S, IpmOpts o, int apply, int per_problem_doubles) {
+__global__ void __launch_bounds__(32 * QW_MAX_WARPS, 1) k_qp_warp(SolverDev S, IpmOpts o, int apply, int per_problem_doubles, int lockstep) {
     extern __shared__ __align__(16) double qw_smem[];
     __shared__ unsigned tmem_base;
     const int wid = threadIdx.x >> 5;
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(32 * QW_MAX_WARPS, 1) k_qp_warp(SolverDev S, I
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tbase = tmem_base;
-    WarpCtxDev w{(int)(threadIdx.x & 31), tbase + (((unsigned)(wid & 3) * 32u) << 16) + (unsigned)(wid >> 2) * 256u};
+    WarpCtxDev w{(int)(threadIdx.x & 31), tbase + (((unsigned)(wid & 3) * 32u) << 16) + (unsigned)(wid >> 2) * 256u, lockstep};
     // work queue: one atomic per warp fetches 32 / SEG consecutive problems, segment `seg` takes the seg-th of them
     auto next = [&](int seg) -> int {
         constexpr int PPW = 32 / SEG;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(32 * QW_MAX_WARPS, 1) k_qp_warp(SolverDev S, I
         }
     };
     qp_warp_persistent<WarpCtxDev, C, HV, SEG>(w, qw_smem + (size_t)wid * (32 / SEG) * per_problem_doubles, per_problem_doubles, S, o, apply, next);
-    // every warp left the loop through the same CTA-wide vote: no TMEM access is in flight any more
+    // the warps leave the loop independently or through the CTA-wide vote (w.lockstep()); once all of them are here no TMEM access is in flight
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tbase) : "memory");

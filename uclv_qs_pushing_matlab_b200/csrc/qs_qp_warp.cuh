@@ -40,6 +40,7 @@ namespace qs {
 struct WarpCtxDev {
     int lane_;
     unsigned tm_;        // TMEM address of this warp's private block: (32 * (warp % 4)) << 16 | first column
+    int ls_;             // 1: the warps of this CTA meet at a vote once per IPM iteration (chosen by launch_qp)
     // The 32-bit destination registers are asm OUTPUTS (not block-local temporaries copied out with mov.b64): the register
     // allocator then places the LDTM destination block where the consumers read it, each aligned pair being one double —
     // with block-local temporaries every load was followed by one MOV per 32-bit register (6 % of the kernel's instructions).
@@ -127,8 +128,9 @@ struct WarpCtxDev {
         else return (m & (((1u << SEG) - 1u) << (lane_ & ~(SEG - 1)))) != 0u;
     }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
-    // CTA-wide vote: keeps the warps of a CTA (one problem each) in lockstep, one barrier per IPM iteration,
-    // so that they share instruction fetches; returns true when every warp of the CTA has finished
+    // CTA-wide vote of the CTAs with more than one warp per scheduler (one barrier per IPM iteration so that the warps share
+    // instruction fetches; every CTA did this up to r02 v14); returns true when every warp of the CTA has finished
+    __device__ __forceinline__ bool lockstep() const { return ls_ != 0; }
     __device__ __forceinline__ bool cta_all(bool pred) const { return __syncthreads_and(pred ? 1 : 0) != 0; }
     __device__ __forceinline__ int bcast_int(int v) const { return __shfl_sync(0xffffffffu, v, 0); }
 };

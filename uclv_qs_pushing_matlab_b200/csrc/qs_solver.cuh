@@ -329,9 +329,8 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm_warp, int pe
     const int N = S.N;
     QpView V;
     QwState st;
-    // bind problem b to this segment: slab views + linearisation and initial point into shared memory / TMEM.  Done
-    // right after the previous problem finishes, i.e. BEFORE the next lockstep vote: the other warps of the CTA are
-    // still inside their IPM iteration then, so nobody waits for the loads of a newly fetched problem.
+    // bind problem b to this segment: slab views + linearisation and initial point into shared memory / TMEM, right after the
+    // previous problem finishes (the other warps of the CTA go on with their own problems meanwhile).
     auto bind = [&](int b_) {
         const bool live = b_ >= 0;
         const int bb = live ? b_ : 0;
@@ -352,11 +351,14 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm_warp, int pe
         QW_TICK(9);
     }
     for (;;) {
-        // lockstep point once per IPM iteration (measured: voting every 2nd / 4th iteration is 9 % / 16 % slower,
-        // the warps drift and stop sharing instruction fetches); leaves when the queue is drained
+        // The warps of a CTA run independently and leave when the queue is drained.  Up to r02 v14 they met at a CTA-wide vote once
+        // per IPM iteration to share instruction fetches (on the r01 kernels voting every 2nd / 4th iteration was 9 % / 16 % slower);
+        // with the instruction stream halved since then the vote costs more than it gives (N = 40: 1.8 % / 2.4 % faster without it at
+        // 4096 / 16 384 instances, same results bit for bit) except in the 7-warp CTAs of N = 20 ... 23: launch_qp sets w.lockstep()
+        // there (table in its comment).
         QW_T0();
         const bool idle = !w.wany(b >= 0 ? 1 : 0);         // no segment of this warp has a problem
-        if (w.cta_all(idle)) break;
+        if (w.lockstep() ? w.cta_all(idle) : idle) break;
         QW_TICK(0);
         if (idle) continue;
         const int fin = qw_iterate<Ctx, C, HV, SEG>(w, sm, Qc, st);

@@ -633,9 +633,17 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
         }
         Dq.order = s->d_order;
     }
+    // CTA-wide vote once per IPM iteration (the warps of a CTA then share their instruction fetches; every launch did this up to
+    // r02 v14) only where it still pays.  Measured on the r02 v16 kernels at 4096 / 16 384 instances, vote vs none
+    // (profiles/r02_v16_lockstep_sweep.txt): 4 warps per CTA (N = 40 / 47 / 100) -1.3 ... -2.4 % without, 3 warps (N = 63) -1.1 /
+    // -1.7 %, 5 warps (N = 31) -4 / -7 %, 6 warps (N = 15, 24, 25) -11 ... -12 % / -1 ... -4 %, 8 warps (N = 5 ... 18) -3 ... -4 % /
+    // 0 ... +2 %; only the 7-warp CTAs (N = 20 ... 23: schedulers host 2, 2, 2, 1 warps) run faster with the vote: +0.6 ... 1.8 % /
+    // +4 ... 6 % without.  QSPUSH_LOCKSTEP=0/1 forces either (development aid).
+    static const char* ls_env = std::getenv("QSPUSH_LOCKSTEP");
+    const int lockstep = ls_env ? (std::atoi(ls_env) != 0) : (Wl == 7);
 #define QW_LAUNCH(CC, HV, SEG)                                                                                     \
     CK(cudaFuncSetAttribute(k_qp_warp<CC, HV, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    k_qp_warp<CC, HV, SEG><<<blocks, 32 * Wl, smem, s->stream>>>(Dq, io, apply, pwd)
+    k_qp_warp<CC, HV, SEG><<<blocks, 32 * Wl, smem, s->stream>>>(Dq, io, apply, pwd, lockstep)
     const int hvf = D.h_variant ? 1 : 0;
     switch ((plan.seg == 16 ? 16 : plan.seg == 8 ? 32 : 0) + C * 2 + hvf) {
 #if QW_PLAN8_MAX >= 0
