@@ -354,8 +354,8 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm_warp, int pe
         // The warps of a CTA run independently and leave when the queue is drained.  Up to r02 v14 they met at a CTA-wide vote once
         // per IPM iteration to share instruction fetches (on the r01 kernels voting every 2nd / 4th iteration was 9 % / 16 % slower);
         // with the instruction stream halved since then the vote costs more than it gives (N = 40: 1.8 % / 2.4 % faster without it at
-        // 4096 / 16 384 instances, same results bit for bit) except in the 7-warp CTAs of N = 20 ... 23: launch_qp sets w.lockstep()
-        // there (table in its comment).
+        // 4096 / 16 384 instances, same results bit for bit) except in the 7-warp CTAs of N = 20 ... 23 and in full-SQP mode:
+        // launch_qp sets w.lockstep() there (measurements in its comment).
         QW_T0();
         const bool idle = !w.wany(b >= 0 ? 1 : 0);         // no segment of this warp has a problem
         if (w.lockstep() ? w.cta_all(idle) : idle) break;

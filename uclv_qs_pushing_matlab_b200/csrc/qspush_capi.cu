@@ -638,9 +638,12 @@ static int launch_qp(qspush_solver* s, const SolverDev& D, const IpmOpts& io, in
     // (profiles/r02_v16_lockstep_sweep.txt): 4 warps per CTA (N = 40 / 47 / 100) -1.3 ... -2.4 % without, 3 warps (N = 63) -1.1 /
     // -1.7 %, 5 warps (N = 31) -4 / -7 %, 6 warps (N = 15, 24, 25) -11 ... -12 % / -1 ... -4 %, 8 warps (N = 5 ... 18) -3 ... -4 % /
     // 0 ... +2 %; only the 7-warp CTAs (N = 20 ... 23: schedulers host 2, 2, 2, 1 warps) run faster with the vote: +0.6 ... 1.8 % /
-    // +4 ... 6 % without.  QSPUSH_LOCKSTEP=0/1 forces either (development aid).
+    // +4 ... 6 % without.  Full SQP (apply == 0: per-launch work queues that skip the converged problems, IPM iteration counts from 5 to
+    // the limit) keeps the vote at every horizon: without it N = 10 / 31 / 40 / 63 / 100 are 7 / 14 / 4 / 2 / 5 % slower (16 384
+    // instances, tools/gpu_sqp_lockstep.py; config 5 on 8 GPUs 0.975 s against 0.930 s).  QSPUSH_LOCKSTEP=0/1 forces either
+    // (development aid).
     static const char* ls_env = std::getenv("QSPUSH_LOCKSTEP");
-    const int lockstep = ls_env ? (std::atoi(ls_env) != 0) : (Wl == 7);
+    const int lockstep = ls_env ? (std::atoi(ls_env) != 0) : (!apply || Wl == 7);
 #define QW_LAUNCH(CC, HV, SEG)                                                                                     \
     CK(cudaFuncSetAttribute(k_qp_warp<CC, HV, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     k_qp_warp<CC, HV, SEG><<<blocks, 32 * Wl, smem, s->stream>>>(Dq, io, apply, pwd, lockstep)
