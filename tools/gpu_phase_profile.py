@@ -14,7 +14,7 @@ for rep in range(2):
     s.prepare(); s.sync(); lib.qspush_dev_phase_cycles(buf)
     s.solve(); s.sync(); lib.qspush_dev_phase_cycles(buf)
 v = np.array(list(buf), dtype=np.float64)
-names = ["vote wait", "(1) residuals+tests", "(2) barrier+elements+local combine", "(3) element scan", "(4) local Riccati", "(5/7) rhs + affine stats", "solve (x2)", "(6) sigma etc", "(8) step+update", "init", "finish+next"]
-tot = v[:11].sum(); its = s.get_int("qp_iter").sum()
+names = ["vote wait", "(1) residuals+tests", "(2) barrier+elements+local combine", "(3) element scan", "(4) local Riccati", "(5/7) rhs + affine stats", "solve (x2)", "(6) sigma etc", "(8) step+update", "init (bind)", "next ticket (queue atomic + order)", "L2 prefetch of the next problem", "write-back", "K5 epilogue (x += dx, u += du, cost, status)"]
+tot = v[:14].sum(); its = s.get_int("qp_iter").sum()
 print("total warp-cycles %.3e over %d IPM iterations -> %.0f cycles per iteration per warp" % (tot, its, tot / its))
 for n, c in zip(names, v): print("  %-38s %6.2f %%   %8.0f cycles/iter" % (n, 100 * c / tot, c / its))

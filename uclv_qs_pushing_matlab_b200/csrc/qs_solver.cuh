@@ -386,7 +386,9 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm_warp, int pe
                 }
             }
         }
+        QW_TICK(11);
         qw_writeback<Ctx, C, SEG>(w, sm, Qc, V, live, apply == 0);      // RTI: the step and the slacks stay on chip (12 of 28 doubles per stage not stored)
+        QW_TICK(12);
         if (live && lane == 0) {
             S.qpstat[b] = st.status;
             if (apply) S.qp_iter[b] = st.it; else S.qp_iter[b] += st.it;
@@ -438,7 +440,7 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm_warp, int pe
             }
         }
         b = b_next;
-        QW_TICK(10);
+        QW_TICK(13);
         if (w.wany(b >= 0 ? 1 : 0)) bind(b);
         QW_TICK(9);
     }
