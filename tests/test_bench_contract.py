@@ -45,3 +45,17 @@ def test_product_arm_has_no_cpu_fallback():
     r = subprocess.run([sys.executable, "bench.py", "--steps", "1", "--warmup", "1"], cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and "no CPU path" in (r.stdout + r.stderr)
     assert not [l for l in r.stdout.splitlines() if l.startswith("{")]      # no bench line is printed
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """N > 1: the driver launches the reference arm like the product arm (torchrun, one rank per GPU); rank 0 alone runs the oracle
+    on the N-GPU workload's config (config 4, strong scaling) and prints, the other ranks exit 0 without work."""
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29513", "bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    js = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(js) == 1
+    d = json.loads(js[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["scaling"] == "strong" and d["config"]["workload"].startswith("config4")
+    assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
