@@ -363,29 +363,13 @@ QS_HD void qp_warp_persistent(const Ctx& w, double* __restrict__ sm_warp, int pe
         if (idle) continue;
         const int fin = qw_iterate<Ctx, C, HV, SEG>(w, sm, Qc, st);
         if (fin == 0) continue;
-        // ---- the problems of this warp are finished: fetch the next ones FIRST (the queue atomic and the first touch of
-        // the next problem's linearisation then overlap the write-back and the epilogue), write back, K5 epilogue, bind
+        // ---- the problems of this warp are finished: fetch the next ticket FIRST (the queue atomic then overlaps the write-back
+        // and the epilogue), write back, K5 epilogue, bind.  (Up to r02 v16 the lanes also issued prefetch.global.L2 for the next
+        // problem's linearisation here; k_linearise has just written those lines, they are L2-resident, and without the 114 prefetch
+        // instructions per lane the control period is 1 % faster: 2.91e6 -> 2.94e6 it/s.)
         const bool live = b >= 0;
         const int b_next = next(seg);
         QW_TICK(10);
-        if (b_next >= 0) {
-            const int Lw_ = qp_warp_lanes(N, C);
-            if (lane < Lw_) {
-#pragma unroll 1
-                for (int j = 0; j < C; ++j) {
-                    const int k = lane * C + j;
-                    if (k >= N) continue;
-#if defined(__CUDA_ARCH__) && !defined(QW_NO_PREFETCH)
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { asm volatile("prefetch.global.L2 [%0];" ::"l"(&QS_EL(S.A, k * 8 + i, b_next))); asm volatile("prefetch.global.L2 [%0];" ::"l"(&QS_EL(S.Bm, k * 8 + i, b_next))); }
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(&QS_EL(S.g, k * 6 + i, b_next)));
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { asm volatile("prefetch.global.L2 [%0];" ::"l"(&QS_EL(S.b, k * 4 + i, b_next))); asm volatile("prefetch.global.L2 [%0];" ::"l"(&QS_EL(S.hv, k * 4 + i, b_next))); }
-#endif
-                }
-            }
-        }
         QW_TICK(11);
         qw_writeback<Ctx, C, SEG>(w, sm, Qc, V, live, apply == 0);      // RTI: the step and the slacks stay on chip (12 of 28 doubles per stage not stored)
         QW_TICK(12);
